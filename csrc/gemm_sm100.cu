@@ -1,0 +1,363 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a with fused training epilogues.
+//
+//   D[M,N] = alpha * A[M,K] . B[N,K]^T          (both operands K-major, bf16, fp32 accumulate)
+//
+// One CTA computes one 128 x BN output tile (optionally one K-split of it):
+//   warp 0   : TMA producer  (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx-count)
+//   warp 1   : MMA issuer    (one elected lane issues tcgen05.mma, accumulator lives in TMEM)
+//   warp 2   : TMEM allocator / deallocator
+//   warps 4-7: epilogue      (tcgen05.ld TMEM -> registers -> fused math -> global)
+//
+// Fused epilogues cover everything a dense layer needs in training (reference ops K1/K2 of
+// MatMul+BiasAdd+{Relu,Sigmoid,Tanh}, their gradients and BiasAddGrad):
+//   * bias add + activation, bf16 output and its transpose (the transpose feeds the K-major
+//     operand of the next wgrad GEMM, so no separate transpose kernel exists),
+//   * dgrad: multiply by act'(previous activation) read from the forward buffer,
+//   * column sums (bias gradient) via an in-register transpose-reduce + one red per column,
+//   * fp32 store or atomic accumulate (split-K / straight into the flat gradient buffer that the
+//     push kernel consumes).
+//
+// The B operand may live in *peer* GPU memory: the tensor map simply carries the peer-mapped
+// address, and the TMA engine pulls weight tiles over NVLink while the MMA pipeline runs
+// (the "pull-fused" first dense layer of the parameter-server design).
+#include "sm100_ptx.cuh"
+#include "sf_api.h"
+
+namespace sf {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;           // 64 bf16 = 128 B = one swizzle row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 256;
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  switch (act) {
+    case SF_ACT_RELU: return fmaxf(x, 0.f);
+    case SF_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case SF_ACT_TANH: return tanhf(x);
+    default: return x;
+  }
+}
+// derivative expressed through the activation *output* a
+__device__ __forceinline__ float act_bwd_from_out(float a, int act) {
+  switch (act) {
+    case SF_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case SF_ACT_SIGMOID: return a * (1.f - a);
+    case SF_ACT_TANH: return 1.f - a * a;
+    default: return 1.f;
+  }
+}
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+  // + barriers (full, empty per stage, tmem_full) + tmem slot, + 1024 alignment slack
+  static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const SfGemmEpilogue ep, int M, int N, int K, int kblocks_per_split) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 128B swizzle needs 1024-byte aligned stage bases
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * kBM;
+  const int total_kb = (K + kBK - 1) / kBK;
+  const int kb_begin = blockIdx.z * kblocks_per_split;
+  int kb_end = kb_begin + kblocks_per_split;
+  if (kb_end > total_kb) kb_end = total_kb;
+  const int num_kb = kb_end - kb_begin;   // host guarantees >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<S::kTmemCols>(tmem_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // weights (B) are re-read by every M tile: keep them in L2; activations stream through.
+      const uint64_t hintA = ep.a_evict_first ? kEvictFirst : kEvictNormal;
+      const uint64_t hintB = kEvictLast;
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % S::kStages;
+        const uint32_t ph = (i / S::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 0x100 + s);
+        uint8_t* a_dst = stage_base + s * S::kStageBytes;
+        uint8_t* b_dst = a_dst + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kStageBytes);
+        const int kc = (kb_begin + i) * kBK;
+        tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0, hintA);
+        tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0, hintB);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kBM, BN);
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % S::kStages;
+        const uint32_t ph = (i / S::kStages) & 1;
+        mbar_wait(&full_bar[s], ph, 0x200 + s);
+        tc_fence_after_sync();
+        const uint32_t a_addr = smem_u32(stage_base + s * S::kStageBytes);
+        const uint32_t b_addr = a_addr + S::kABytes;
+        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
+          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);      // smem slot reusable once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);        // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int e = warp - 4;              // == warp % 4 -> TMEM lane quarter this warp may touch
+    mbar_wait(tmem_full_bar, 0, 0x300);
+    tc_fence_after_sync();
+    const int row = m0 + e * 32 + lane;
+    const bool row_ok = row < M;
+    const bool is_split0 = (blockIdx.z == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (col0 >= ep.n_store_limit) break;   // whole chunk outside every output pitch
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
+
+      if (ep.bias != nullptr && is_split0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) f[j] += __ldg(ep.bias + col0 + j);
+      }
+      if (ep.act != SF_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+      }
+      if (ep.aux != nullptr && row_ok) {
+        const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (col0 + g * 8 < ep.ld_aux) {
+            const uint4 q = *reinterpret_cast<const uint4*>(ap + g * 8);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 a2 = __bfloat1622float2(h[t]);
+              f[g * 8 + 2 * t] *= act_bwd_from_out(a2.x, ep.aux_act);
+              f[g * 8 + 2 * t + 1] *= act_bwd_from_out(a2.y, ep.aux_act);
+            }
+          }
+        }
+      }
+      // padded columns / rows contribute exact zeros everywhere below
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j >= N || !row_ok) f[j] = 0.f;
+
+      if (ep.colsum != nullptr) {
+        // transpose-reduce over the 32 rows held by this warp: 31 shuffles, lane j ends up with
+        // the sum of column col0 + j.
+        float r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = f[j];
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+          const bool upper = (lane & w) != 0;
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            const float send = upper ? r[j] : r[j + w];
+            const float keep = upper ? r[j + w] : r[j];
+            r[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+          }
+        }
+        // after the butterfly lane l holds column bitrev-free index: position is l itself
+        if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, r[0]);
+      }
+
+      if (ep.out_f32 != nullptr && row_ok) {
+        float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+        if (ep.accumulate) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) atomicAdd(op + j, f[j]);
+        } else if ((ep.ld_f32 & 3) == 0 && col0 + 32 <= N &&
+                   (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(op + 4 * g) =
+                make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) op[j] = f[j];
+        }
+      }
+      if (ep.out_bf16 != nullptr && row_ok) {
+        __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (col0 + g * 8 < ep.ld_bf16) {
+            uint4 q;
+            q.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+            q.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+            q.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+            q.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(op + g * 8) = q;
+          }
+        }
+      }
+      if (ep.outT_bf16 != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N)
+            ep.outT_bf16[static_cast<size_t>(col0 + j) * ep.ld_t + row] = __float2bfloat16(f[j]);
+      }
+    }
+    tc_fence_before_sync();
+  }
+
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after_sync();
+    tmem_dealloc<S::kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+}  // namespace sf
+
+extern "C" int sf_make_tmap_bf16_kmajor(CUtensorMap* out, const void* base, uint64_t rows,
+                                        uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+  auto fn = sf::get_encode();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {cols, rows};                 // innermost first
+  cuuint64_t strides[1] = {ld_elems * 2};            // bytes, dim 1
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(sf::kBK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : static_cast<int>(r);
+}
+
+extern "C" int sf_gemm_pick_bn(int M, int N) {
+  // Small problems are latency bound: prefer more CTAs (smaller BN) until the grid covers the
+  // 148 SMs; big problems want the widest tile for operand reuse.
+  const int m_tiles = (M + sf::kBM - 1) / sf::kBM;
+  const int cands[4] = {256, 128, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cands[i];
+    if (bn > 32 && bn / 2 >= N) continue;              // tile mostly padding
+    const int n_tiles = (N + bn - 1) / bn;
+    if (m_tiles * n_tiles >= 148 || bn == 32) return bn;
+  }
+  return 32;
+}
+
+extern "C" int sf_gemm_prepare(SfGemm* g) {
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return -2;
+  if (g->bn == 0) g->bn = sf_gemm_pick_bn(g->M, g->N);
+  if (g->split_k <= 0) g->split_k = 1;
+  int rc = sf_make_tmap_bf16_kmajor(&g->tmA, g->a, g->M, g->K, g->lda, sf::kBM);
+  if (rc) return rc;
+  rc = sf_make_tmap_bf16_kmajor(&g->tmB, g->b, g->N, g->K, g->ldb, g->bn);
+  if (rc) return rc;
+  const int total_kb = (g->K + sf::kBK - 1) / sf::kBK;
+  if (g->split_k > total_kb) g->split_k = total_kb;
+  g->kblocks_per_split = (total_kb + g->split_k - 1) / g->split_k;
+  g->split_k = (total_kb + g->kblocks_per_split - 1) / g->kblocks_per_split;
+  if (g->split_k > 1) g->ep.accumulate = 1;
+  // largest column any output can hold
+  int lim = g->N;
+  if (g->ep.out_bf16 && g->ep.ld_bf16 > lim) lim = g->ep.ld_bf16;
+  g->ep.n_store_limit = lim;
+  return 0;
+}
+
+template <int BN>
+static cudaError_t launch_bn(const SfGemm* g, cudaStream_t st) {
+  using S = sf::GemmSmem<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sf::sf_gemm_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((g->N + BN - 1) / BN, (g->M + sf::kBM - 1) / sf::kBM, g->split_k);
+  sf::sf_gemm_kernel<BN><<<grid, sf::kGemmThreads, S::kBytes, st>>>(g->tmA, g->tmB, g->ep, g->M,
+                                                                   g->N, g->K, g->kblocks_per_split);
+  return cudaGetLastError();
+}
+
+extern "C" int sf_gemm_launch(const SfGemm* g, cudaStream_t st) {
+  cudaError_t e;
+  switch (g->bn) {
+    case 32: e = launch_bn<32>(g, st); break;
+    case 64: e = launch_bn<64>(g, st); break;
+    case 128: e = launch_bn<128>(g, st); break;
+    case 256: e = launch_bn<256>(g, st); break;
+    default: return -3;
+  }
+  return static_cast<int>(e);
+}
+
+extern "C" unsigned int sf_read_error_code() {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, sf::g_sf_error_code, sizeof(v));
+  return v;
+}

@@ -1,0 +1,451 @@
+// Fused parameter-server push / pull for sm_100a.
+//
+// push  (reference: POST /update -> optimizer.apply_gradients, one optimizer step PER PUSH,
+//        sparkflow/HogwildSparkModel.py:219-242): the *worker* launches this kernel.  It streams
+//        its local gradient, loads the master's p / slot tiles through peer-mapped NVLink
+//        addresses, applies the optimizer rule in registers, stores p / slots back to the master
+//        and publishes the bf16 copies (row-major and transposed, i.e. both K-major GEMM operand
+//        layouts) to the master and - through an NVLS multicast alias or explicit peer stores -
+//        to the replicas.  No NCCL, no host, no master-side SMs.
+//        Hogwild (acquire_lock=False): no lock, racing read-modify-writes over NVLink.
+//        Lock mode: device writer-priority RW lock (mirror of sparkflow/RWLock.py semantics) held
+//        in the master's control block, taken by CTA 0 and released by the last CTA to finish.
+// pull  (reference: GET /parameters): copies the master's bf16 publish buffer (and optionally the
+//        fp32 params) into the local replica under the read side of the same lock.
+//
+// All ten TF-1.x optimizers of tensorflow_async.py:19-30 are implemented as update functors.
+#include "sm100_ptx.cuh"
+#include "sf_api.h"
+
+namespace sf {
+
+constexpr uint32_t kLockWriter = 1u << 16;
+constexpr uint32_t kLockWaitOne = 1u << 17;
+constexpr uint32_t kLockReaders = 0xFFFFu;
+constexpr unsigned long long kLockTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- writer-priority readers/writer lock on one 32-bit word (system scope, works over NVLink)
+__device__ void rw_acquire_write(uint32_t* lock) {
+  atom_add_acqrel_sys(lock, kLockWaitOne);                 // announce: blocks new readers
+  const unsigned long long t0 = gtime_ns();
+  while (true) {
+    const uint32_t v = ld_acquire_sys(lock);
+    if ((v & (kLockReaders | kLockWriter)) == 0) {
+      if (atom_cas_acqrel_sys(lock, v, v - kLockWaitOne + kLockWriter) == v) return;
+    } else {
+      __nanosleep(64);
+    }
+    if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x401);
+  }
+}
+__device__ void rw_release_write(uint32_t* lock) {
+  atom_add_acqrel_sys(lock, 0u - kLockWriter);
+}
+__device__ void rw_acquire_read(uint32_t* lock) {
+  const unsigned long long t0 = gtime_ns();
+  while (true) {
+    const uint32_t v = ld_acquire_sys(lock);
+    if ((v & kLockWriter) == 0 && (v >> 17) == 0) {        // no writer active, none waiting
+      if (atom_cas_acqrel_sys(lock, v, v + 1) == v) return;
+    } else {
+      __nanosleep(64);
+    }
+    if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x402);
+  }
+}
+__device__ void rw_release_read(uint32_t* lock) {
+  atom_add_acqrel_sys(lock, 0u - 1u);
+}
+
+// ---- in-grid coordination on the worker's own memory --------------------------------------
+// local_sync words: 0 = grant epoch, 1 = granted value (optimizer step t), 2 = done counter,
+//                   3 = launch counter.  All CTAs of the grid must be co-resident (grid <= #SMs).
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ---- optimizer rules (TF 1.x training_ops semantics) ---------------------------------------
+struct Upd {
+  float p, s0, s1, s2;
+};
+
+__device__ __forceinline__ float sgnf(float x) { return (x > 0.f) - (x < 0.f); }
+
+template <int OPT>
+__device__ __forceinline__ void apply_rule(Upd& u, float g, const SfHyper& h, float t, float lr_t) {
+  if constexpr (OPT == SF_OPT_SGD) {
+    u.p -= h.lr * g;
+  } else if constexpr (OPT == SF_OPT_MOMENTUM) {
+    u.s0 = h.momentum * u.s0 + g;
+    u.p -= h.nesterov ? (h.lr * g + h.lr * h.momentum * u.s0) : (h.lr * u.s0);
+  } else if constexpr (OPT == SF_OPT_ADAM) {
+    u.s0 = h.beta1 * u.s0 + (1.f - h.beta1) * g;
+    u.s1 = h.beta2 * u.s1 + (1.f - h.beta2) * g * g;
+    u.p -= lr_t * u.s0 / (sqrtf(u.s1) + h.eps);
+  } else if constexpr (OPT == SF_OPT_RMSPROP) {
+    u.s0 = h.decay * u.s0 + (1.f - h.decay) * g * g;            // ms
+    float denom = u.s0 + h.eps;
+    if (h.centered) {
+      u.s2 = h.decay * u.s2 + (1.f - h.decay) * g;              // mg
+      denom -= u.s2 * u.s2;
+    }
+    u.s1 = h.momentum * u.s1 + h.lr * g * rsqrtf(denom);        // mom
+    u.p -= u.s1;
+  } else if constexpr (OPT == SF_OPT_ADAGRAD) {
+    u.s0 += g * g;
+    u.p -= h.lr * g * rsqrtf(u.s0);
+  } else if constexpr (OPT == SF_OPT_ADADELTA) {
+    u.s0 = h.rho * u.s0 + (1.f - h.rho) * g * g;
+    const float upd = sqrtf(u.s1 + h.eps) * rsqrtf(u.s0 + h.eps) * g;
+    u.s1 = h.rho * u.s1 + (1.f - h.rho) * upd * upd;
+    u.p -= h.lr * upd;
+  } else if constexpr (OPT == SF_OPT_ADAGRAD_DA) {
+    u.s0 += g;                                                  // gradient accumulator
+    u.s1 += g * g;                                              // squared accumulator
+    float tmp = u.s0;
+    if (h.l1 > 0.f) tmp = sgnf(u.s0) * fmaxf(fabsf(u.s0) - h.l1 * t, 0.f);
+    u.p = (-h.lr * tmp) / (h.l2 * t * h.lr + sqrtf(u.s1));
+  } else if constexpr (OPT == SF_OPT_FTRL) {
+    const float gs = g + 2.f * h.l2_shrinkage * u.p;
+    const float acc_new = u.s0 + g * g;
+    float pow_new, pow_old;
+    if (h.lr_power == -0.5f) {
+      pow_new = sqrtf(acc_new);
+      pow_old = sqrtf(u.s0);
+    } else {
+      pow_new = __powf(acc_new, -h.lr_power);
+      pow_old = __powf(u.s0, -h.lr_power);
+    }
+    const float sigma = (pow_new - pow_old) / h.lr;
+    u.s1 += gs - sigma * u.p;                                   // linear
+    const float quad = pow_new / h.lr + 2.f * h.l2;
+    u.p = fabsf(u.s1) > h.l1 ? (sgnf(u.s1) * h.l1 - u.s1) / quad : 0.f;
+    u.s0 = acc_new;
+  } else if constexpr (OPT == SF_OPT_PROXIMAL_ADAGRAD) {
+    u.s0 += g * g;
+    const float lr_a = h.lr * rsqrtf(u.s0);
+    const float prox = u.p - lr_a * g;
+    u.p = (h.l1 > 0.f ? sgnf(prox) * fmaxf(fabsf(prox) - lr_a * h.l1, 0.f) : prox) / (1.f + h.l2 * lr_a);
+  } else if constexpr (OPT == SF_OPT_PROXIMAL_SGD) {
+    const float prox = u.p - h.lr * g;
+    u.p = (h.l1 > 0.f ? sgnf(prox) * fmaxf(fabsf(prox) - h.lr * h.l1, 0.f) : prox) / (1.f + h.l2 * h.lr);
+  }
+}
+
+template <int OPT> struct Slots { static constexpr int n = 0; };
+template <> struct Slots<SF_OPT_MOMENTUM> { static constexpr int n = 1; };
+template <> struct Slots<SF_OPT_ADAM> { static constexpr int n = 2; };
+template <> struct Slots<SF_OPT_RMSPROP> { static constexpr int n = 3; };
+template <> struct Slots<SF_OPT_ADAGRAD> { static constexpr int n = 1; };
+template <> struct Slots<SF_OPT_ADADELTA> { static constexpr int n = 2; };
+template <> struct Slots<SF_OPT_ADAGRAD_DA> { static constexpr int n = 2; };
+template <> struct Slots<SF_OPT_FTRL> { static constexpr int n = 2; };
+template <> struct Slots<SF_OPT_PROXIMAL_ADAGRAD> { static constexpr int n = 1; };
+
+constexpr int kTileR = 32;
+constexpr int kTileC = 64;
+constexpr int kPushThreads = 256;
+
+__device__ __forceinline__ void st_shadow8(__nv_bfloat16* dst, uint2 q, bool mc) {
+  if (mc) {
+    asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(dst),
+                 "f"(__uint_as_float(q.x)), "f"(__uint_as_float(q.y))
+                 : "memory");
+  } else {
+    asm volatile("st.global.relaxed.sys.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(q.x),
+                 "r"(q.y)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc) {
+  if (mc) multimem_st_u4(reinterpret_cast<uint4*>(dst), q);
+  else st_stream_u4(reinterpret_cast<uint4*>(dst), q);
+}
+template <int OPT>
+__global__ void __launch_bounds__(kPushThreads, 1)
+push_kernel(const SfPushArgs a, uint32_t* local_sync) {
+  __shared__ uint32_t s_t;
+  __shared__ uint32_t s_epoch;
+  __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
+  const int tid = threadIdx.x;
+  constexpr int NS = Slots<OPT>::n;
+
+  // ---------------- acquire / step number ----------------
+  if (tid == 0) {
+    uint32_t t;
+    if (a.lock_mode == SF_LOCK_RW) {
+      const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
+      if (blockIdx.x == 0) {
+        rw_acquire_write(a.ctrl + SF_CTRL_LOCK);
+        t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
+        local_sync[1] = t;
+        __threadfence();
+        st_release_gpu(local_sync + 0, epoch + 1);
+      } else {
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_gpu(local_sync + 0) != epoch + 1) {
+          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x403);
+        }
+        t = local_sync[1];
+      }
+      s_epoch = epoch;
+    } else {
+      // Hogwild: read the step count racily, exactly like unlocked TF beta-power variables
+      t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
+      s_epoch = 0;
+    }
+    s_t = t;
+  }
+  __syncthreads();
+  const float t = static_cast<float>(s_t);
+  float lr_t = a.h.lr;
+  if constexpr (OPT == SF_OPT_ADAM) {
+    lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
+  }
+  const bool mc = a.shadow_is_mc != 0;
+
+  // ---------------- tiles ----------------
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    const int seg_i = a.tile_map[tile * 3 + 0];
+    const int r0 = a.tile_map[tile * 3 + 1] * kTileR;
+    const int c0 = a.tile_map[tile * 3 + 2] * kTileC;
+    const SfTensorSeg sg = a.segs[seg_i];
+    const bool vec = ((sg.cols & 3) == 0) && ((sg.offset & 3) == 0);
+    const int tx = tid & 15, ty = tid >> 4;
+    const int c = c0 + tx * 4;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int rl = ty + 16 * half;
+      const int r = r0 + rl;
+      float w[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < sg.rows && c < sg.cols) {
+        const int64_t e = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
+        const int nv = (sg.cols - c) >= 4 ? 4 : (sg.cols - c);
+        float g[4] = {0, 0, 0, 0}, p[4] = {0, 0, 0, 0}, x0[4] = {0, 0, 0, 0}, x1[4] = {0, 0, 0, 0},
+              x2[4] = {0, 0, 0, 0};
+        if (vec) {
+          const float4 gv = *reinterpret_cast<const float4*>(a.grad + e);
+          g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+          *reinterpret_cast<float4*>(a.grad + e) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!a.drop) {
+            const float4 pv = ld_stream_f4(reinterpret_cast<const float4*>(a.p + e));
+            p[0] = pv.x; p[1] = pv.y; p[2] = pv.z; p[3] = pv.w;
+            if constexpr (NS >= 1) { const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(a.s0 + e)); x0[0] = q.x; x0[1] = q.y; x0[2] = q.z; x0[3] = q.w; }
+            if constexpr (NS >= 2) { const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(a.s1 + e)); x1[0] = q.x; x1[1] = q.y; x1[2] = q.z; x1[3] = q.w; }
+            if constexpr (NS >= 3) { const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(a.s2 + e)); x2[0] = q.x; x2[1] = q.y; x2[2] = q.z; x2[3] = q.w; }
+          }
+        } else {
+          for (int j = 0; j < nv; ++j) {
+            g[j] = a.grad[e + j];
+            a.grad[e + j] = 0.f;
+            if (!a.drop) {
+              p[j] = a.p[e + j];
+              if constexpr (NS >= 1) x0[j] = a.s0[e + j];
+              if constexpr (NS >= 2) x1[j] = a.s1[e + j];
+              if constexpr (NS >= 3) x2[j] = a.s2[e + j];
+            }
+          }
+        }
+        if (!a.drop) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            Upd u{p[j], x0[j], x1[j], x2[j]};
+            apply_rule<OPT>(u, g[j] * a.grad_scale, a.h, t, lr_t);
+            p[j] = u.p; x0[j] = u.s0; x1[j] = u.s1; x2[j] = u.s2;
+            w[j] = (j < nv) ? u.p : 0.f;      // lanes past the row end are padding: exact zeros
+          }
+          if (vec) {
+            st_stream_f4(reinterpret_cast<float4*>(a.p + e), make_float4(p[0], p[1], p[2], p[3]));
+            if constexpr (NS >= 1) st_stream_f4(reinterpret_cast<float4*>(a.s0 + e), make_float4(x0[0], x0[1], x0[2], x0[3]));
+            if constexpr (NS >= 2) st_stream_f4(reinterpret_cast<float4*>(a.s1 + e), make_float4(x1[0], x1[1], x1[2], x1[3]));
+            if constexpr (NS >= 3) st_stream_f4(reinterpret_cast<float4*>(a.s2 + e), make_float4(x2[0], x2[1], x2[2], x2[3]));
+          } else {
+            for (int j = 0; j < nv; ++j) {
+              a.p[e + j] = p[j];
+              if constexpr (NS >= 1) a.s0[e + j] = x0[j];
+              if constexpr (NS >= 2) a.s1[e + j] = x1[j];
+              if constexpr (NS >= 3) a.s2[e + j] = x2[j];
+            }
+          }
+          // row-major bf16 publish: [rows, w_ld]
+          if (sg.w_off >= 0) {
+            const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
+            // w_ld is a multiple of 8 and c of 4: the 8-byte store always fits, pads carry zeros
+            const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+            for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8(a.shadow_dst[d] + wo, q, mc && d == 0);
+          }
+        }
+      }
+      if (sg.wt_off >= 0 && !a.drop) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_tr[tx * 4 + j][rl] = __float2bfloat16(w[j]);
+      }
+    }
+    if (sg.wt_off >= 0 && !a.drop) {
+      __syncthreads();
+      // transposed bf16 publish: [cols, wt_ld]; each thread owns 8 consecutive rows of one column
+      const int cl = tid >> 2, part = tid & 3;
+      const int cc = c0 + cl, rr = r0 + part * 8;
+      if (cc < sg.cols && rr < sg.rows) {
+        const int64_t to = sg.wt_off + static_cast<int64_t>(cc) * sg.wt_ld + rr;
+        // wt_ld is a multiple of 8: the 16-byte store always fits, rows >= sg.rows carry zeros
+        const uint4 q = *reinterpret_cast<const uint4*>(&s_tr[cl][part * 8]);
+        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16(a.shadow_dst[d] + to, q, mc && d == 0);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---------------- completion ----------------
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();                       // my remote stores are visible system-wide
+    const uint32_t prev = atomicAdd(local_sync + 2, 1u);
+    if (prev == gridDim.x - 1) {                  // last CTA of this push
+      __threadfence_system();
+      local_sync[2] = 0;
+      if (a.loss_acc != nullptr) {
+        *a.loss_out = *a.loss_acc;
+        *a.loss_acc = 0.f;
+      }
+      if (a.drop) {
+        atom_add_relaxed_sys(a.ctrl + SF_CTRL_DROPPED, 1u);
+      } else {
+        atom_add_relaxed_sys(a.ctrl + SF_CTRL_STEP, 1u);
+        atom_add_relaxed_sys(a.ctrl + SF_CTRL_PUSHES, 1u);
+        atom_add_acqrel_sys(a.ctrl + SF_CTRL_VERSION, 1u);
+      }
+      if (a.lock_mode == SF_LOCK_RW) {
+        rw_release_write(a.ctrl + SF_CTRL_LOCK);
+        __threadfence();
+        st_release_gpu(local_sync + 3, s_epoch + 1);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// pull: master publish buffer -> local replica (16-byte streaming copies over NVLink)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
+  __shared__ uint32_t s_epoch;
+  const int tid = threadIdx.x;
+  if (a.lock_mode == SF_LOCK_RW) {
+    if (tid == 0) {
+      const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
+      if (blockIdx.x == 0) {
+        rw_acquire_read(a.ctrl + SF_CTRL_LOCK);
+        __threadfence();
+        st_release_gpu(local_sync + 0, epoch + 1);
+      } else {
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_gpu(local_sync + 0) != epoch + 1) {
+          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x404);
+        }
+      }
+      s_epoch = epoch;
+    }
+    __syncthreads();
+  }
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + tid;
+  {
+    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    uint4* d = reinterpret_cast<uint4*>(a.dst);
+    const size_t n16 = a.n_bf16 / 8;
+    // 4 independent 16-byte loads in flight per thread to cover the ~2 us NVLink latency
+    size_t i = gid;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+      const uint4 v0 = ld_stream_u4(s + i), v1 = ld_stream_u4(s + i + stride),
+                  v2 = ld_stream_u4(s + i + 2 * stride), v3 = ld_stream_u4(s + i + 3 * stride);
+      d[i] = v0; d[i + stride] = v1; d[i + 2 * stride] = v2; d[i + 3 * stride] = v3;
+    }
+    for (; i < n16; i += stride) d[i] = ld_stream_u4(s + i);
+  }
+  if (a.src_f32 != nullptr) {
+    const float4* s = reinterpret_cast<const float4*>(a.src_f32);
+    float4* d = reinterpret_cast<float4*>(a.dst_f32);
+    const size_t n16 = a.n_f32 / 4;
+    for (size_t i = gid; i < n16; i += stride) d[i] = ld_stream_f4(s + i);
+  }
+  if (gid == 0 && a.seen_version != nullptr) *a.seen_version = ld_relaxed_sys(a.ctrl + SF_CTRL_VERSION);
+  if (a.lock_mode == SF_LOCK_RW) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      const uint32_t prev = atomicAdd(local_sync + 2, 1u);
+      if (prev == gridDim.x - 1) {
+        local_sync[2] = 0;
+        rw_release_read(a.ctrl + SF_CTRL_LOCK);
+        __threadfence();
+        st_release_gpu(local_sync + 3, s_epoch + 1);
+      }
+    }
+  }
+}
+
+// single-thread lock exerciser used by the GPU tests (op: 0 = acquire_read, 1 = release_read,
+// 2 = acquire_write, 3 = release_write)
+__global__ void lock_test_kernel(uint32_t* ctrl, int op) {
+  switch (op) {
+    case 0: rw_acquire_read(ctrl + SF_CTRL_LOCK); break;
+    case 1: rw_release_read(ctrl + SF_CTRL_LOCK); break;
+    case 2: rw_acquire_write(ctrl + SF_CTRL_LOCK); break;
+    case 3: rw_release_write(ctrl + SF_CTRL_LOCK); break;
+  }
+}
+
+}  // namespace sf
+
+template <int OPT>
+static int launch_push(const SfPushArgs* a, uint32_t* ls, int grid, cudaStream_t st) {
+  sf::push_kernel<OPT><<<grid, sf::kPushThreads, 0, st>>>(*a, ls);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sf_push_launch(const SfPushArgs* a, uint32_t* local_sync, int grid, cudaStream_t st) {
+  if (grid <= 0) grid = a->num_tiles < 148 ? a->num_tiles : 148;
+  if (grid > 148) grid = 148;          // lock mode needs every CTA resident
+  if (grid < 1) grid = 1;
+  switch (a->optimizer) {
+    case SF_OPT_SGD: return launch_push<SF_OPT_SGD>(a, local_sync, grid, st);
+    case SF_OPT_MOMENTUM: return launch_push<SF_OPT_MOMENTUM>(a, local_sync, grid, st);
+    case SF_OPT_ADAM: return launch_push<SF_OPT_ADAM>(a, local_sync, grid, st);
+    case SF_OPT_RMSPROP: return launch_push<SF_OPT_RMSPROP>(a, local_sync, grid, st);
+    case SF_OPT_ADAGRAD: return launch_push<SF_OPT_ADAGRAD>(a, local_sync, grid, st);
+    case SF_OPT_ADADELTA: return launch_push<SF_OPT_ADADELTA>(a, local_sync, grid, st);
+    case SF_OPT_ADAGRAD_DA: return launch_push<SF_OPT_ADAGRAD_DA>(a, local_sync, grid, st);
+    case SF_OPT_FTRL: return launch_push<SF_OPT_FTRL>(a, local_sync, grid, st);
+    case SF_OPT_PROXIMAL_ADAGRAD: return launch_push<SF_OPT_PROXIMAL_ADAGRAD>(a, local_sync, grid, st);
+    case SF_OPT_PROXIMAL_SGD: return launch_push<SF_OPT_PROXIMAL_SGD>(a, local_sync, grid, st);
+  }
+  return -4;
+}
+
+extern "C" int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int grid, cudaStream_t st) {
+  if (grid <= 0) {
+    const size_t n16 = a->n_bf16 / 8 + a->n_f32 / 4;
+    grid = static_cast<int>((n16 + 256 * 4 - 1) / (256 * 4));
+    if (grid > 148) grid = 148;
+    if (grid < 1) grid = 1;
+  }
+  sf::pull_kernel<<<grid, 256, 0, st>>>(*a, local_sync);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st) {
+  sf::lock_test_kernel<<<1, 1, 0, st>>>(ctrl, op);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,401 @@
+// Host runtime of sparkflow_b200 (C++): step-plan runner with CUDA-graph capture, prepared GEMM
+// objects (TMA descriptors are encoded once per buffer set), the CUDA-IPC symmetric-memory helper
+// that maps the master's buffers into every worker process, and thin pybind11 entry points for
+// every kernel.  Python hands over raw device addresses (torch owns the allocations); nothing in
+// here depends on libtorch.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "sf_api.h"
+
+namespace py = pybind11;
+
+namespace {
+
+inline void ck(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) {
+    throw std::runtime_error(std::string("sparkflow_b200 CUDA error in ") + what + ": " +
+                             cudaGetErrorString(e));
+  }
+}
+inline void ck_rc(int rc, const char* what) {
+  if (rc != 0) {
+    const char* msg = rc > 0 ? cudaGetErrorString(static_cast<cudaError_t>(rc)) : "invalid argument";
+    throw std::runtime_error(std::string("sparkflow_b200: ") + what + " failed (rc=" +
+                             std::to_string(rc) + ", " + msg + ")");
+  }
+}
+
+template <class T>
+inline T* P(uintptr_t v) { return reinterpret_cast<T*>(v); }
+inline cudaStream_t S(uintptr_t v) { return reinterpret_cast<cudaStream_t>(v); }
+
+template <class T>
+T getd(const py::dict& d, const char* k, T dflt) {
+  if (d.contains(k) && !d[k].is_none()) return d[k].cast<T>();
+  return dflt;
+}
+
+// ---------------------------------------------------------------------------
+// Prepared GEMM
+// ---------------------------------------------------------------------------
+struct Gemm {
+  SfGemm g;
+  explicit Gemm(const py::dict& d) {
+    std::memset(&g, 0, sizeof(g));
+    g.a = P<void>(getd<uintptr_t>(d, "a", 0));
+    g.b = P<void>(getd<uintptr_t>(d, "b", 0));
+    g.M = getd<int>(d, "M", 0);
+    g.N = getd<int>(d, "N", 0);
+    g.K = getd<int>(d, "K", 0);
+    g.lda = getd<int>(d, "lda", g.K);
+    g.ldb = getd<int>(d, "ldb", g.K);
+    g.bn = getd<int>(d, "bn", 0);
+    g.split_k = getd<int>(d, "split_k", 1);
+    g.ep.out_f32 = P<float>(getd<uintptr_t>(d, "out_f32", 0));
+    g.ep.ld_f32 = getd<int>(d, "ld_f32", g.N);
+    g.ep.out_bf16 = P<__nv_bfloat16>(getd<uintptr_t>(d, "out_bf16", 0));
+    g.ep.ld_bf16 = getd<int>(d, "ld_bf16", 0);
+    g.ep.outT_bf16 = P<__nv_bfloat16>(getd<uintptr_t>(d, "outT_bf16", 0));
+    g.ep.ld_t = getd<int>(d, "ld_t", 0);
+    g.ep.bias = P<const float>(getd<uintptr_t>(d, "bias", 0));
+    g.ep.aux = P<const __nv_bfloat16>(getd<uintptr_t>(d, "aux", 0));
+    g.ep.ld_aux = getd<int>(d, "ld_aux", 0);
+    g.ep.aux_act = getd<int>(d, "aux_act", 0);
+    g.ep.colsum = P<float>(getd<uintptr_t>(d, "colsum", 0));
+    g.ep.alpha = getd<float>(d, "alpha", 1.0f);
+    g.ep.act = getd<int>(d, "act", 0);
+    g.ep.accumulate = getd<int>(d, "accumulate", 0);
+    g.ep.a_evict_first = getd<int>(d, "a_evict_first", 0);
+    if ((g.lda % 8) || (g.ldb % 8)) throw std::runtime_error("gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)");
+    if (g.ep.out_bf16 && (g.ep.ld_bf16 % 8)) throw std::runtime_error("gemm: ld_bf16 must be a multiple of 8");
+    if (g.ep.aux && (g.ep.ld_aux % 8)) throw std::runtime_error("gemm: ld_aux must be a multiple of 8");
+    ck_rc(sf_gemm_prepare(&g), "sf_gemm_prepare (cuTensorMapEncodeTiled)");
+  }
+  void launch(uintptr_t stream) const { ck_rc(sf_gemm_launch(&g, S(stream)), "sf_gemm_launch"); }
+  int bn() const { return g.bn; }
+  int split_k() const { return g.split_k; }
+  py::tuple grid() const {
+    return py::make_tuple((g.N + g.bn - 1) / g.bn, (g.M + 127) / 128, g.split_k);
+  }
+};
+
+// ---------------------------------------------------------------------------
+// push / pull argument parsing
+// ---------------------------------------------------------------------------
+SfHyper parse_hyper(const py::dict& d) {
+  SfHyper h;
+  std::memset(&h, 0, sizeof(h));
+  h.lr = getd<float>(d, "lr", 0.01f);
+  h.beta1 = getd<float>(d, "beta1", 0.9f);
+  h.beta2 = getd<float>(d, "beta2", 0.999f);
+  h.eps = getd<float>(d, "eps", 1e-8f);
+  h.momentum = getd<float>(d, "momentum", 0.0f);
+  h.rho = getd<float>(d, "rho", 0.95f);
+  h.decay = getd<float>(d, "decay", 0.9f);
+  h.l1 = getd<float>(d, "l1", 0.0f);
+  h.l2 = getd<float>(d, "l2", 0.0f);
+  h.lr_power = getd<float>(d, "lr_power", -0.5f);
+  h.init_accum = getd<float>(d, "init_accum", 0.1f);
+  h.l2_shrinkage = getd<float>(d, "l2_shrinkage", 0.0f);
+  h.nesterov = getd<int>(d, "nesterov", 0);
+  h.centered = getd<int>(d, "centered", 0);
+  return h;
+}
+
+SfPushArgs parse_push(const py::dict& d) {
+  SfPushArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.p = P<float>(getd<uintptr_t>(d, "p", 0));
+  a.s0 = P<float>(getd<uintptr_t>(d, "s0", 0));
+  a.s1 = P<float>(getd<uintptr_t>(d, "s1", 0));
+  a.s2 = P<float>(getd<uintptr_t>(d, "s2", 0));
+  a.ctrl = P<uint32_t>(getd<uintptr_t>(d, "ctrl", 0));
+  auto dsts = getd<std::vector<uintptr_t>>(d, "shadow_dst", {});
+  if (dsts.size() > 8) throw std::runtime_error("push: at most 8 publish destinations");
+  a.n_shadow_dst = static_cast<int>(dsts.size());
+  for (size_t i = 0; i < dsts.size(); ++i) a.shadow_dst[i] = P<__nv_bfloat16>(dsts[i]);
+  a.shadow_is_mc = getd<int>(d, "shadow_is_mc", 0);
+  a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
+  a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
+  a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
+  a.segs = P<const SfTensorSeg>(getd<uintptr_t>(d, "segs", 0));
+  a.tile_map = P<const int32_t>(getd<uintptr_t>(d, "tile_map", 0));
+  a.num_tiles = getd<int>(d, "num_tiles", 0);
+  a.optimizer = getd<int>(d, "optimizer", SF_OPT_SGD);
+  a.lock_mode = getd<int>(d, "lock_mode", 0);
+  a.drop = getd<int>(d, "drop", 0);
+  a.grad_scale = getd<float>(d, "grad_scale", 1.0f);
+  a.h = parse_hyper(getd<py::dict>(d, "hyper", py::dict()));
+  if (!a.p || !a.ctrl || !a.grad || !a.segs || !a.tile_map || a.num_tiles <= 0)
+    throw std::runtime_error("push: p/ctrl/grad/segs/tile_map/num_tiles are required");
+  return a;
+}
+
+SfPullArgs parse_pull(const py::dict& d) {
+  SfPullArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.src = P<const __nv_bfloat16>(getd<uintptr_t>(d, "src", 0));
+  a.dst = P<__nv_bfloat16>(getd<uintptr_t>(d, "dst", 0));
+  a.src_f32 = P<const float>(getd<uintptr_t>(d, "src_f32", 0));
+  a.dst_f32 = P<float>(getd<uintptr_t>(d, "dst_f32", 0));
+  a.n_bf16 = getd<size_t>(d, "n_bf16", 0);
+  a.n_f32 = getd<size_t>(d, "n_f32", 0);
+  a.ctrl = P<uint32_t>(getd<uintptr_t>(d, "ctrl", 0));
+  a.seen_version = P<uint32_t>(getd<uintptr_t>(d, "seen_version", 0));
+  a.lock_mode = getd<int>(d, "lock_mode", 0);
+  if ((a.n_bf16 % 8) || (a.n_f32 % 4)) throw std::runtime_error("pull: sizes must be 16-byte multiples");
+  if (!a.ctrl) throw std::runtime_error("pull: ctrl is required");
+  return a;
+}
+
+// ---------------------------------------------------------------------------
+// Step plan: an ordered list of kernel launches, replayable as a CUDA graph.
+// ---------------------------------------------------------------------------
+class Plan {
+ public:
+  using Op = std::function<int(cudaStream_t)>;
+  ~Plan() { reset_graph(); }
+
+  void add(std::string name, Op op) {
+    names_.push_back(std::move(name));
+    ops_.push_back(std::move(op));
+    reset_graph();
+  }
+  void add_gemm(std::shared_ptr<Gemm> g, const std::string& name) {
+    add(name, [g](cudaStream_t st) { return sf_gemm_launch(&g->g, st); });
+  }
+  size_t size() const { return ops_.size(); }
+  std::vector<std::string> names() const { return names_; }
+
+  void run(uintptr_t stream) {
+    cudaStream_t st = S(stream);
+    for (size_t i = 0; i < ops_.size(); ++i) {
+      const int rc = ops_[i](st);
+      if (rc != 0) ck_rc(rc, names_[i].c_str());
+    }
+  }
+  // Capture the op list once; later steps are a single cudaGraphLaunch.
+  void capture(uintptr_t stream) {
+    reset_graph();
+    cudaStream_t st = S(stream);
+    ck(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal), "cudaStreamBeginCapture");
+    try {
+      run(stream);
+    } catch (...) {
+      cudaGraph_t dead = nullptr;
+      cudaStreamEndCapture(st, &dead);
+      if (dead) cudaGraphDestroy(dead);
+      throw;
+    }
+    ck(cudaStreamEndCapture(st, &graph_), "cudaStreamEndCapture");
+    ck(cudaGraphInstantiate(&exec_, graph_, 0), "cudaGraphInstantiate");
+  }
+  bool captured() const { return exec_ != nullptr; }
+  void replay(uintptr_t stream) {
+    if (!exec_) throw std::runtime_error("plan not captured");
+    ck(cudaGraphLaunch(exec_, S(stream)), "cudaGraphLaunch");
+  }
+  void replay_n(uintptr_t stream, int n) {
+    if (!exec_) throw std::runtime_error("plan not captured");
+    for (int i = 0; i < n; ++i) ck(cudaGraphLaunch(exec_, S(stream)), "cudaGraphLaunch");
+  }
+
+ private:
+  void reset_graph() {
+    if (exec_) { cudaGraphExecDestroy(exec_); exec_ = nullptr; }
+    if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
+  }
+  std::vector<Op> ops_;
+  std::vector<std::string> names_;
+  cudaGraph_t graph_ = nullptr;
+  cudaGraphExec_t exec_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// CUDA-IPC symmetric memory: cudaMalloc'ed segments exported to the peer processes of the box.
+// ---------------------------------------------------------------------------
+uintptr_t ipc_alloc(size_t bytes) {
+  void* p = nullptr;
+  ck(cudaMalloc(&p, bytes), "cudaMalloc(symmetric segment)");
+  ck(cudaMemset(p, 0, bytes), "cudaMemset(symmetric segment)");
+  return reinterpret_cast<uintptr_t>(p);
+}
+void ipc_free(uintptr_t p) { cudaFree(P<void>(p)); }
+py::bytes ipc_get_handle(uintptr_t p) {
+  cudaIpcMemHandle_t h;
+  ck(cudaIpcGetMemHandle(&h, P<void>(p)), "cudaIpcGetMemHandle");
+  return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+}
+uintptr_t ipc_open_handle(const std::string& raw) {
+  if (raw.size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("bad IPC handle size");
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, raw.data(), sizeof(h));
+  void* p = nullptr;
+  ck(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+  return reinterpret_cast<uintptr_t>(p);
+}
+void ipc_close_handle(uintptr_t p) { cudaIpcCloseMemHandle(P<void>(p)); }
+
+bool enable_peer_access(int peer) {
+  int dev = 0;
+  ck(cudaGetDevice(&dev), "cudaGetDevice");
+  if (dev == peer) return true;
+  int can = 0;
+  ck(cudaDeviceCanAccessPeer(&can, dev, peer), "cudaDeviceCanAccessPeer");
+  if (!can) return false;
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return true; }
+  ck(e, "cudaDeviceEnablePeerAccess");
+  return true;
+}
+
+py::bytes pack_segs(const std::vector<std::vector<int64_t>>& rows) {
+  std::vector<SfTensorSeg> v(rows.size());
+  for (size_t i = 0; i < rows.size(); ++i) {
+    const auto& r = rows[i];
+    if (r.size() != 7) throw std::runtime_error("pack_segs: (offset, rows, cols, w_off, w_ld, wt_off, wt_ld)");
+    std::memset(&v[i], 0, sizeof(SfTensorSeg));
+    v[i].offset = r[0];
+    v[i].rows = static_cast<int>(r[1]);
+    v[i].cols = static_cast<int>(r[2]);
+    v[i].w_off = r[3];
+    v[i].w_ld = static_cast<int>(r[4]);
+    v[i].wt_off = r[5];
+    v[i].wt_ld = static_cast<int>(r[6]);
+    if (v[i].w_off >= 0 && ((v[i].w_ld % 8) || (v[i].w_off % 8))) throw std::runtime_error("pack_segs: w_ld / w_off must be multiples of 8");
+    if (v[i].wt_off >= 0 && ((v[i].wt_ld % 8) || (v[i].wt_off % 8))) throw std::runtime_error("pack_segs: wt_ld / wt_off must be multiples of 8");
+  }
+  return py::bytes(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(SfTensorSeg));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "sparkflow_b200 native runtime (sm_100a kernels + step-plan runner)";
+  m.attr("ARCH") = "sm_100a";
+  m.attr("CTRL_WORDS") = static_cast<int>(SF_CTRL_WORDS);
+  m.attr("SEG_BYTES") = static_cast<int>(sizeof(SfTensorSeg));
+  m.attr("PUSH_TILE_R") = 32;
+  m.attr("PUSH_TILE_C") = 64;
+
+  py::class_<Gemm, std::shared_ptr<Gemm>>(m, "Gemm")
+      .def(py::init<const py::dict&>())
+      .def("launch", &Gemm::launch)
+      .def_property_readonly("bn", &Gemm::bn)
+      .def_property_readonly("split_k", &Gemm::split_k)
+      .def_property_readonly("grid", &Gemm::grid);
+
+  py::class_<Plan>(m, "Plan")
+      .def(py::init<>())
+      .def("__len__", &Plan::size)
+      .def("names", &Plan::names)
+      .def("run", &Plan::run)
+      .def("capture", &Plan::capture)
+      .def("captured", &Plan::captured)
+      .def("replay", &Plan::replay)
+      .def("replay_n", &Plan::replay_n, py::call_guard<py::gil_scoped_release>())
+      .def("add_gemm", &Plan::add_gemm, py::arg("gemm"), py::arg("name") = "gemm")
+      .def("add_cast_transpose",
+           [](Plan& p, uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,
+              int ld_t, int rows, int cols) {
+             p.add("cast_transpose", [=](cudaStream_t st) {
+               return idx ? sf_gather_cast_transpose(P<const float>(in), ld_in, P<const int32_t>(idx),
+                                                     P<__nv_bfloat16>(out), ld_out, P<__nv_bfloat16>(outT),
+                                                     ld_t, rows, cols, st)
+                          : sf_cast_transpose(P<const float>(in), ld_in, P<__nv_bfloat16>(out), ld_out,
+                                              P<__nv_bfloat16>(outT), ld_t, rows, cols, st);
+             });
+           })
+      .def("add_softmax_xent",
+           [](Plan& p, uintptr_t logits, int ld_logits, uintptr_t labels, int ld_labels, uintptr_t loss,
+              uintptr_t dz, int ld_dz, uintptr_t dzT, int ld_t, uintptr_t dbias, int rows, int cols) {
+             p.add("softmax_xent", [=](cudaStream_t st) {
+               return sf_softmax_xent(P<const float>(logits), ld_logits, P<const float>(labels), ld_labels,
+                                      P<float>(loss), P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT), ld_t,
+                                      P<float>(dbias), rows, cols, st);
+             });
+           })
+      .def("add_mse",
+           [](Plan& p, uintptr_t out, int ld_out, uintptr_t target, int ld_target, int act, uintptr_t loss,
+              uintptr_t dz, int ld_dz, uintptr_t dzT, int ld_t, uintptr_t dbias, int rows, int cols) {
+             p.add("mse", [=](cudaStream_t st) {
+               return sf_mse_loss(P<const float>(out), ld_out, P<const float>(target), ld_target, act,
+                                  P<float>(loss), P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT), ld_t,
+                                  P<float>(dbias), rows, cols, st);
+             });
+           })
+      .def("add_argmax",
+           [](Plan& p, uintptr_t in, int ld, uintptr_t out, int rows, int cols) {
+             p.add("argmax", [=](cudaStream_t st) {
+               return sf_argmax_rows(P<const float>(in), ld, P<float>(out), rows, cols, st);
+             });
+           })
+      .def("add_push",
+           [](Plan& p, const py::dict& d, uintptr_t local_sync, int grid) {
+             const SfPushArgs a = parse_push(d);
+             p.add("push", [=](cudaStream_t st) { return sf_push_launch(&a, P<uint32_t>(local_sync), grid, st); });
+           })
+      .def("add_pull", [](Plan& p, const py::dict& d, uintptr_t local_sync, int grid) {
+        const SfPullArgs a = parse_pull(d);
+        p.add("pull", [=](cudaStream_t st) { return sf_pull_launch(&a, P<uint32_t>(local_sync), grid, st); });
+      });
+
+  // direct (un-planned) entry points, used by tests and the eager paths
+  m.def("cast_transpose", [](uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,
+                             int ld_t, int rows, int cols, uintptr_t stream) {
+    ck_rc(idx ? sf_gather_cast_transpose(P<const float>(in), ld_in, P<const int32_t>(idx), P<__nv_bfloat16>(out),
+                                         ld_out, P<__nv_bfloat16>(outT), ld_t, rows, cols, S(stream))
+              : sf_cast_transpose(P<const float>(in), ld_in, P<__nv_bfloat16>(out), ld_out,
+                                  P<__nv_bfloat16>(outT), ld_t, rows, cols, S(stream)),
+          "cast_transpose");
+  });
+  m.def("softmax_xent", [](uintptr_t logits, int ld_logits, uintptr_t labels, int ld_labels, uintptr_t loss,
+                           uintptr_t dz, int ld_dz, uintptr_t dzT, int ld_t, uintptr_t dbias, int rows, int cols,
+                           uintptr_t stream) {
+    ck_rc(sf_softmax_xent(P<const float>(logits), ld_logits, P<const float>(labels), ld_labels, P<float>(loss),
+                          P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT), ld_t, P<float>(dbias), rows, cols,
+                          S(stream)),
+          "softmax_xent");
+  });
+  m.def("mse_loss", [](uintptr_t out, int ld_out, uintptr_t target, int ld_target, int act, uintptr_t loss,
+                       uintptr_t dz, int ld_dz, uintptr_t dzT, int ld_t, uintptr_t dbias, int rows, int cols,
+                       uintptr_t stream) {
+    ck_rc(sf_mse_loss(P<const float>(out), ld_out, P<const float>(target), ld_target, act, P<float>(loss),
+                      P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT), ld_t, P<float>(dbias), rows, cols,
+                      S(stream)),
+          "mse_loss");
+  });
+  m.def("argmax_rows", [](uintptr_t in, int ld, uintptr_t out, int rows, int cols, uintptr_t stream) {
+    ck_rc(sf_argmax_rows(P<const float>(in), ld, P<float>(out), rows, cols, S(stream)), "argmax_rows");
+  });
+  m.def("push", [](const py::dict& d, uintptr_t local_sync, int grid, uintptr_t stream) {
+    const SfPushArgs a = parse_push(d);
+    ck_rc(sf_push_launch(&a, P<uint32_t>(local_sync), grid, S(stream)), "push");
+  });
+  m.def("pull", [](const py::dict& d, uintptr_t local_sync, int grid, uintptr_t stream) {
+    const SfPullArgs a = parse_pull(d);
+    ck_rc(sf_pull_launch(&a, P<uint32_t>(local_sync), grid, S(stream)), "pull");
+  });
+  m.def("lock_op", [](uintptr_t ctrl, int op, uintptr_t stream) {
+    ck_rc(sf_lock_test(P<uint32_t>(ctrl), op, S(stream)), "lock_op");
+  });
+  m.def("gemm_pick_bn", &sf_gemm_pick_bn);
+  m.def("read_error_code", &sf_read_error_code);
+  m.def("pack_segs", &pack_segs);
+
+  m.def("ipc_alloc", &ipc_alloc);
+  m.def("ipc_free", &ipc_free);
+  m.def("ipc_get_handle", &ipc_get_handle);
+  m.def("ipc_open_handle", &ipc_open_handle);
+  m.def("ipc_close_handle", &ipc_close_handle);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("device_count", []() { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0; });
+}

@@ -1,0 +1,169 @@
+// C ABI between the sm_100a kernels (csrc/*.cu) and the host runtime (plan.cpp / bindings.cpp).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum SfAct { SF_ACT_NONE = 0, SF_ACT_RELU = 1, SF_ACT_SIGMOID = 2, SF_ACT_TANH = 3 };
+
+enum SfOptimizer {
+  SF_OPT_SGD = 0,
+  SF_OPT_MOMENTUM = 1,
+  SF_OPT_ADAM = 2,
+  SF_OPT_RMSPROP = 3,
+  SF_OPT_ADAGRAD = 4,
+  SF_OPT_ADADELTA = 5,
+  SF_OPT_ADAGRAD_DA = 6,
+  SF_OPT_FTRL = 7,
+  SF_OPT_PROXIMAL_ADAGRAD = 8,
+  SF_OPT_PROXIMAL_SGD = 9,
+};
+
+enum SfLockMode { SF_LOCK_NONE = 0 /* Hogwild */, SF_LOCK_RW = 1 /* writer-priority RW lock */ };
+
+// ---------------------------------------------------------------------------
+// GEMM
+// ---------------------------------------------------------------------------
+struct SfGemmEpilogue {
+  float* out_f32;                 // [M, ld_f32] optional
+  __nv_bfloat16* out_bf16;        // [M, ld_bf16] optional (ld multiple of 8, pad columns get 0)
+  __nv_bfloat16* outT_bf16;       // [N, ld_t]   optional transpose
+  const float* bias;              // [N] optional
+  const __nv_bfloat16* aux;       // [M, ld_aux] optional: multiply by act'(aux) (dgrad)
+  float* colsum;                  // [N] optional: atomicAdd column sums (bias gradient)
+  float alpha;
+  int ld_f32, ld_bf16, ld_t, ld_aux;
+  int act;                        // SfAct applied after bias
+  int aux_act;                    // SfAct whose derivative is taken at aux
+  int accumulate;                 // atomicAdd into out_f32
+  int n_store_limit;              // filled by sf_gemm_prepare
+  int a_evict_first;
+};
+
+struct SfGemm {
+  CUtensorMap tmA, tmB;           // filled by sf_gemm_prepare
+  const void* a;                  // bf16 [M, lda]  (K contiguous)
+  const void* b;                  // bf16 [N, ldb]  (K contiguous); may be a peer-mapped address
+  int M, N, K;
+  int lda, ldb;
+  int bn;                         // 0 = auto
+  int split_k;                    // 0/1 = none
+  int kblocks_per_split;          // filled
+  SfGemmEpilogue ep;
+};
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int sf_gemm_prepare(SfGemm* g);
+int sf_gemm_launch(const SfGemm* g, cudaStream_t st);
+int sf_gemm_pick_bn(int M, int N);
+unsigned int sf_read_error_code();
+
+// ---------------------------------------------------------------------------
+// Elementwise / reduction kernels (elementwise.cu)
+// ---------------------------------------------------------------------------
+// fp32 [rows, cols] (ld_in) -> bf16 [rows, ld_out] and optional transpose bf16 [cols, ld_t]
+int sf_cast_transpose(const float* in, int ld_in, __nv_bfloat16* out, int ld_out,
+                      __nv_bfloat16* outT, int ld_t, int rows, int cols, cudaStream_t st);
+// gather rows by index then cast/transposes (minibatch assembly on the device)
+int sf_gather_cast_transpose(const float* in, int ld_in, const int32_t* idx, __nv_bfloat16* out,
+                             int ld_out, __nv_bfloat16* outT, int ld_t, int rows, int cols,
+                             cudaStream_t st);
+// softmax cross-entropy with (soft) labels: mean loss (atomicAdd into loss[0]), dlogits = (p*sum(y) - y)/B
+int sf_softmax_xent(const float* logits, int ld_logits, const float* labels, int ld_labels,
+                    float* loss, __nv_bfloat16* dz, int ld_dz, __nv_bfloat16* dzT, int ld_t,
+                    float* dbias, int rows, int cols, cudaStream_t st);
+// mean squared error over all elements of out (after activation `act`, out is post-activation):
+// loss += mean((out-target)^2); dz = 2*(out-target)/(rows*cols) * act'(out)
+int sf_mse_loss(const float* out, int ld_out, const float* target, int ld_target, int act,
+                float* loss, __nv_bfloat16* dz, int ld_dz, __nv_bfloat16* dzT, int ld_t,
+                float* dbias, int rows, int cols, cudaStream_t st);
+int sf_argmax_rows(const float* in, int ld, float* out, int rows, int cols, cudaStream_t st);
+int sf_fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+// conv building blocks (NHWC, VALID, stride 1) and 2x2/s2 max-pool
+int sf_im2col_nhwc(const __nv_bfloat16* in, int n, int h, int w, int c, int kh, int kw,
+                   __nv_bfloat16* out, int ld_out, __nv_bfloat16* outT, int ld_t, cudaStream_t st);
+int sf_col2im_nhwc(const float* cols, int ld_cols, int n, int h, int w, int c, int kh, int kw,
+                   float* out, cudaStream_t st);
+int sf_maxpool2_fwd(const __nv_bfloat16* in, int n, int h, int w, int c, __nv_bfloat16* out,
+                    uint8_t* argmax, cudaStream_t st);
+int sf_maxpool2_bwd(const float* dout, const uint8_t* argmax, int n, int h, int w, int c,
+                    const __nv_bfloat16* act_out, int act, __nv_bfloat16* din, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// Fused push: optimizer step on the (possibly remote) master shard + bf16 publish (optim_push.cu)
+// ---------------------------------------------------------------------------
+struct SfTensorSeg {              // one trainable variable inside the flat buffers
+  int64_t offset;                 // element offset in the flat fp32 buffers
+  int rows, cols;                 // [in, out] (bias: rows = 1)
+  int64_t w_off;   int w_ld;      // bf16 copy   [rows, w_ld]   (-1 = none)
+  int64_t wt_off;  int wt_ld;     // bf16 transpose [cols, wt_ld] (-1 = none)
+};
+
+struct SfHyper {
+  float lr, beta1, beta2, eps;    // adam: beta1/beta2/eps ; rmsprop: decay=beta1 momentum=beta2
+  float momentum, rho, decay;
+  float l1, l2, lr_power, init_accum;
+  float l2_shrinkage;
+  int nesterov, centered;
+};
+
+struct SfPushArgs {
+  // master state (peer-mapped addresses when the master is another GPU)
+  float* p; float* s0; float* s1; float* s2;   // params + up to three slot buffers
+  uint32_t* ctrl;                 // control block in master memory (see SfCtrl offsets)
+  // bf16 publish destinations: master copy first, then any replicas that are pushed to directly.
+  // With NVLS a single multicast alias covers every replica (shadow_is_mc = 1).
+  __nv_bfloat16* shadow_dst[8];
+  int n_shadow_dst;
+  int shadow_is_mc;
+  float* grad;                    // local flat gradient (consumed, then zeroed for the next step)
+  float* loss_acc;                // local: loss accumulated by the loss kernel (consumed + zeroed)
+  float* loss_out;                // local: last step's loss for the host to read
+  const SfTensorSeg* segs;        // device array
+  const int32_t* tile_map;        // device array [num_tiles * 3] = (seg, tile_row, tile_col)
+  int num_tiles;
+  int optimizer;
+  int lock_mode;
+  int drop;                       // fault injection: consume the gradient but do not apply it
+  float grad_scale;
+  SfHyper h;
+};
+
+// control block layout (uint32 words) living in master memory
+enum SfCtrl {
+  SF_CTRL_LOCK = 0,         // RW lock word: [0,16) readers, bit 16 writer, [17,32) writers waiting
+  SF_CTRL_VERSION = 1,      // bumped once per applied push (seqlock-style version)
+  SF_CTRL_STEP = 2,         // global optimizer step count (adam beta powers)
+  SF_CTRL_PUSHES = 3,       // total pushes applied
+  SF_CTRL_ERRORS = 4,
+  SF_CTRL_DROPPED = 5,
+  SF_CTRL_WORDS = 64
+};
+
+// local_sync: 8 uint32 words in the *worker's own* memory used for in-grid coordination
+int sf_push_launch(const SfPushArgs* a, uint32_t* local_sync, int grid, cudaStream_t st);
+
+struct SfPullArgs {
+  const __nv_bfloat16* src;       // master publish buffer (peer-mapped)
+  __nv_bfloat16* dst;             // local replica
+  const float* src_f32;           // optional: fp32 master params
+  float* dst_f32;                 // optional local fp32 copy
+  size_t n_bf16;                  // elements (multiple of 8)
+  size_t n_f32;                   // elements (multiple of 4)
+  uint32_t* ctrl;                 // master control block
+  uint32_t* seen_version;         // local: version observed by this pull
+  int lock_mode;
+};
+int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int grid, cudaStream_t st);
+
+// host-visible lock helpers for tests (single-thread kernels)
+int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st);
+
+#ifdef __cplusplus
+}
+#endif

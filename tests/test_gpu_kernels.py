@@ -1,0 +1,322 @@
+"""Numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from sparkflow_b200.ops import native
+from sparkflow_b200.ops.layout import ParamLayout, round_up
+from sparkflow_b200.ops.optimizers import OPT_IDS, OptimizerSpec, apply_update, init_slots
+
+ACT = {None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+
+def _act(x, a):
+    return {None: lambda v: v, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[a](x)
+
+
+def _dact(a_out, a):
+    if a == "relu":
+        return (a_out > 0).float()
+    if a == "sigmoid":
+        return a_out * (1 - a_out)
+    if a == "tanh":
+        return 1 - a_out * a_out
+    return torch.ones_like(a_out)
+
+
+@pytest.fixture(scope="module")
+def C():
+    return native.cuda_ext()
+
+
+def _bf16_pad(x, ld):
+    out = torch.zeros(x.shape[0], ld, dtype=torch.bfloat16, device="cuda")
+    out[:, : x.shape[1]] = x.to(torch.bfloat16)
+    return out
+
+
+def _run_gemm(C, M, N, K, bn=0, split_k=1, bias=False, act=None, aux_act=None, colsum=False, want_bf16=True,
+              want_t=True, accumulate=False, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    a = torch.randn(M, K, device="cuda", generator=g) * 0.5
+    b = torch.randn(N, K, device="cuda", generator=g) * 0.5
+    lda, ldb = round_up(K, 8), round_up(K, 8)
+    a16, b16 = _bf16_pad(a, lda), _bf16_pad(b, ldb)
+    ref = a16[:, :K].float() @ b16[:, :K].float().t()
+    ldn = round_up(N, 8)
+    ldt = round_up(M, 8)
+    out_f32 = torch.full((M, N), 7.0 if accumulate else float("nan"), device="cuda")
+    out_bf16 = torch.zeros(M, ldn, dtype=torch.bfloat16, device="cuda") if want_bf16 else None
+    outT = torch.zeros(N, ldt, dtype=torch.bfloat16, device="cuda") if want_t else None
+    bias_t = torch.randn(N, device="cuda", generator=g) if bias else None
+    aux = None
+    if aux_act is not None:
+        aux = _bf16_pad(_act(torch.randn(M, N, device="cuda", generator=g), aux_act), ldn)
+    cs = torch.zeros(N, device="cuda") if colsum else None
+    d = dict(a=native.ptr(a16), b=native.ptr(b16), M=M, N=N, K=K, lda=lda, ldb=ldb, bn=bn, split_k=split_k,
+             out_f32=native.ptr(out_f32), ld_f32=N, out_bf16=native.ptr(out_bf16), ld_bf16=ldn,
+             outT_bf16=native.ptr(outT), ld_t=ldt, bias=native.ptr(bias_t), act=ACT[act], aux=native.ptr(aux),
+             ld_aux=ldn, aux_act=ACT[aux_act], colsum=native.ptr(cs), alpha=1.0, accumulate=int(accumulate))
+    gm = C.Gemm(d)
+    gm.launch(native.current_stream())
+    torch.cuda.synchronize()
+    assert C.read_error_code() == 0
+    exp = ref
+    if bias:
+        exp = exp + bias_t
+    exp = _act(exp, act)
+    if aux is not None:
+        exp = exp * _dact(aux[:, :N].float(), aux_act)
+    tol = dict(rtol=2e-2, atol=2e-2 * max(1.0, K ** 0.5 * 0.25))
+    got = out_f32 - 7.0 if accumulate else out_f32
+    torch.testing.assert_close(got, exp, **tol)
+    if want_bf16:
+        torch.testing.assert_close(out_bf16[:, :N].float(), exp, rtol=3e-2, atol=tol["atol"] + 0.05)
+        assert torch.all(out_bf16[:, N:] == 0)
+    if want_t:
+        torch.testing.assert_close(outT[:, :M].float().t(), exp, rtol=3e-2, atol=tol["atol"] + 0.05)
+    if colsum:
+        torch.testing.assert_close(cs, exp.sum(0), rtol=2e-2, atol=tol["atol"] * 4)
+    return gm
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 32, 64), (128, 64, 128), (300, 256, 784), (300, 10, 256),
+                                     (784, 256, 300), (256, 10, 300), (1000, 520, 1000)])
+def test_gemm_plain(C, M, N, K):
+    _run_gemm(C, M, N, K)
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
+def test_gemm_tile_widths(C, bn):
+    _run_gemm(C, 384, 512, 320, bn=bn)
+
+
+def test_gemm_bias_relu(C):
+    _run_gemm(C, 300, 256, 784, bias=True, act="relu")
+
+
+def test_gemm_bias_sigmoid_tanh(C):
+    _run_gemm(C, 257, 130, 200, bias=True, act="sigmoid")
+    _run_gemm(C, 257, 130, 200, bias=True, act="tanh")
+
+
+def test_gemm_dgrad_epilogue(C):
+    _run_gemm(C, 300, 256, 10, aux_act="relu", colsum=True)
+    _run_gemm(C, 300, 256, 256, aux_act="sigmoid", colsum=True)
+
+
+def test_gemm_split_k_accumulate(C):
+    gm = _run_gemm(C, 32, 64, 4096, split_k=8, want_bf16=False, want_t=False, accumulate=True)
+    assert gm.split_k == 8
+
+
+def test_gemm_large(C):
+    _run_gemm(C, 2048, 2048, 2048, want_t=False)
+
+
+def test_cast_transpose(C):
+    x = torch.randn(300, 784, device="cuda")
+    ld, ldt = round_up(784, 8), round_up(300, 8)
+    out = torch.full((300, ld), 9.0, dtype=torch.bfloat16, device="cuda")
+    outT = torch.full((784, ldt), 9.0, dtype=torch.bfloat16, device="cuda")
+    C.cast_transpose(native.ptr(x), 784, 0, native.ptr(out), ld, native.ptr(outT), ldt, 300, 784,
+                     native.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out[:, :784], x.to(torch.bfloat16))
+    assert torch.equal(outT[:, :300], x.to(torch.bfloat16).t())
+    assert torch.all(outT[:, 300:] == 0)
+    idx = torch.randperm(300, device="cuda", dtype=torch.int32)[:128].contiguous()
+    out2 = torch.zeros(128, ld, dtype=torch.bfloat16, device="cuda")
+    C.cast_transpose(native.ptr(x), 784, native.ptr(idx), native.ptr(out2), ld, 0, 0, 128, 784,
+                     native.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out2[:, :784], x[idx.long()].to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("B,Cc", [(300, 10), (64, 1000), (7, 3)])
+def test_softmax_xent(C, B, Cc):
+    z = torch.randn(B, Cc, device="cuda") * 3
+    y = torch.nn.functional.one_hot(torch.randint(0, Cc, (B,), device="cuda"), Cc).float()
+    ld, ldt = round_up(Cc, 8), round_up(B, 8)
+    loss = torch.zeros(1, device="cuda")
+    dz = torch.full((B, ld), 5.0, dtype=torch.bfloat16, device="cuda")
+    dzT = torch.zeros(Cc, ldt, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(Cc, device="cuda")
+    C.softmax_xent(native.ptr(z), Cc, native.ptr(y), Cc, native.ptr(loss), native.ptr(dz), ld, native.ptr(dzT), ldt,
+                   native.ptr(db), B, Cc, native.current_stream())
+    torch.cuda.synchronize()
+    zr = z.clone().requires_grad_(True)
+    ref = -(y * torch.log_softmax(zr, 1)).sum(1).mean()
+    ref.backward()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dz[:, :Cc].float(), zr.grad, rtol=2e-2, atol=1e-4)
+    torch.testing.assert_close(dzT[:, :B].float().t(), zr.grad, rtol=2e-2, atol=1e-4)
+    assert torch.all(dz[:, Cc:] == 0)
+    torch.testing.assert_close(db, zr.grad.sum(0), rtol=1e-3, atol=1e-5)
+
+
+@pytest.mark.parametrize("act", [None, "sigmoid"])
+def test_mse(C, act):
+    B, Cc = 256, 784
+    pre = torch.randn(B, Cc, device="cuda", requires_grad=True)
+    out = _act(pre, act)
+    tgt = torch.rand(B, Cc, device="cuda")
+    ref = ((out - tgt) ** 2).mean()
+    ref.backward()
+    ld, ldt = round_up(Cc, 8), round_up(B, 8)
+    loss = torch.zeros(1, device="cuda")
+    dz = torch.zeros(B, ld, dtype=torch.bfloat16, device="cuda")
+    dzT = torch.zeros(Cc, ldt, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(Cc, device="cuda")
+    o = out.detach().contiguous()
+    C.mse_loss(native.ptr(o), Cc, native.ptr(tgt), Cc, ACT[act], native.ptr(loss), native.ptr(dz), ld,
+               native.ptr(dzT), ldt, native.ptr(db), B, Cc, native.current_stream())
+    torch.cuda.synchronize()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(dz[:, :Cc].float(), pre.grad, rtol=2e-2, atol=1e-7)
+    torch.testing.assert_close(dzT[:, :B].float().t(), pre.grad, rtol=2e-2, atol=1e-7)
+    torch.testing.assert_close(db, pre.grad.sum(0), rtol=1e-3, atol=1e-7)
+
+
+def test_argmax(C):
+    z = torch.randn(333, 10, device="cuda")
+    out = torch.zeros(333, device="cuda")
+    C.argmax_rows(native.ptr(z), 10, native.ptr(out), 333, 10, native.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(out.long(), z.argmax(1))
+
+
+SHAPES = [("dense/kernel", (784, 256)), ("dense/bias", (256,)), ("dense_1/kernel", (256, 256)),
+          ("dense_1/bias", (256,)), ("dense_2/kernel", (256, 10)), ("dense_2/bias", (10,))]
+
+
+def _push_setup(C, spec, lock_mode=0):
+    lay = ParamLayout.build(SHAPES)
+    dev = "cuda"
+    p = torch.zeros(lay.total, device=dev)
+    mask = torch.from_numpy(lay.valid_mask()).to(dev)
+    p[mask] = torch.randn(int(mask.sum()), device=dev) * 0.1
+    slots = init_slots(spec, p)
+    while len(slots) < 3:
+        slots.append(None)
+    ctrl = torch.zeros(C.CTRL_WORDS, dtype=torch.int32, device=dev)
+    shadow = torch.zeros(lay.shadow_total, dtype=torch.bfloat16, device=dev)
+    grad = torch.zeros(lay.total, device=dev)
+    segs = torch.frombuffer(bytearray(C.pack_segs(lay.seg_rows())), dtype=torch.uint8).to(dev)
+    tmap = torch.from_numpy(lay.tile_map()).to(dev)
+    lsync = torch.zeros(8, dtype=torch.int32, device=dev)
+    loss_acc = torch.zeros(1, device=dev)
+    loss_out = torch.zeros(1, device=dev)
+    args = dict(p=native.ptr(p), s0=native.ptr(slots[0]), s1=native.ptr(slots[1]), s2=native.ptr(slots[2]),
+                ctrl=native.ptr(ctrl), shadow_dst=[native.ptr(shadow)], grad=native.ptr(grad),
+                loss_acc=native.ptr(loss_acc), loss_out=native.ptr(loss_out), segs=native.ptr(segs),
+                tile_map=native.ptr(tmap), num_tiles=int(tmap.shape[0]), optimizer=spec.opt_id,
+                lock_mode=lock_mode, grad_scale=1.0, hyper=spec.native_hyper())
+    keep = dict(lay=lay, p=p, slots=slots, ctrl=ctrl, shadow=shadow, grad=grad, segs=segs, tmap=tmap, lsync=lsync,
+                loss_acc=loss_acc, loss_out=loss_out, mask=mask)
+    return args, keep
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("gradient_descent", dict(learning_rate=0.1)),
+    ("momentum", dict(learning_rate=0.1, momentum=0.9)),
+    ("momentum", dict(learning_rate=0.1, momentum=0.9, use_nesterov=True)),
+    ("adam", dict(learning_rate=0.01, beta1=0.85, beta2=0.98, epsilon=1e-8)),
+    ("rmsprop", dict(learning_rate=0.05, decay=0.95, momentum=0.1, epsilon=1e-10)),
+    ("rmsprop", dict(learning_rate=0.05, decay=0.95, momentum=0.1, epsilon=1e-6, centered=True)),
+    ("adagrad", dict(learning_rate=0.1, initial_accumulator_value=0.1)),
+    ("adadelta", dict(learning_rate=1.0, rho=0.95, epsilon=1e-6)),
+    ("adagrad_da", dict(learning_rate=0.1, l1_regularization_strength=0.001, l2_regularization_strength=0.01)),
+    ("ftrl", dict(learning_rate=0.1, l1_regularization_strength=0.001, l2_regularization_strength=0.01)),
+    ("proximal_adagrad", dict(learning_rate=0.1, l1_regularization_strength=0.001, l2_regularization_strength=0.01)),
+    ("proximal_gradient_descent", dict(learning_rate=0.1, l1_regularization_strength=0.001,
+                                       l2_regularization_strength=0.01)),
+])
+@pytest.mark.parametrize("lock_mode", [0, 1])
+def test_push_matches_reference_optimizer(C, name, kw, lock_mode):
+    spec = OptimizerSpec.from_tf_kwargs(name, kw)
+    args, k = _push_setup(C, spec, lock_mode)
+    p_ref = k["p"].clone()
+    s_ref = [s.clone() for s in k["slots"] if s is not None]
+    for step in range(1, 4):
+        g = torch.zeros_like(k["grad"])
+        g[k["mask"]] = torch.randn(int(k["mask"].sum()), device="cuda") * 0.05
+        k["grad"].copy_(g)
+        k["loss_acc"].fill_(float(step))
+        C.push(args, native.ptr(k["lsync"]), 0, native.current_stream())
+        torch.cuda.synchronize()
+        assert C.read_error_code() == 0
+        apply_update(spec, p_ref, g, s_ref, step)
+        torch.testing.assert_close(k["p"][k["mask"]], p_ref[k["mask"]], rtol=2e-4, atol=2e-6)
+        for a, b in zip([s for s in k["slots"] if s is not None], s_ref):
+            torch.testing.assert_close(a[k["mask"]], b[k["mask"]], rtol=2e-4, atol=1e-6)
+        assert torch.all(k["grad"] == 0), "push must consume (zero) the gradient buffer"
+        assert float(k["loss_out"][0]) == float(step) and float(k["loss_acc"][0]) == 0.0
+        ctrl = k["ctrl"].cpu().numpy()
+        assert ctrl[0] == 0 and ctrl[1] == step and ctrl[2] == step and ctrl[3] == step
+    exp = torch.from_numpy(k["lay"].publish_reference(k["p"].cpu().numpy())).to(torch.bfloat16)
+    assert torch.equal(k["shadow"].cpu(), exp)
+
+
+def test_push_drop_fault_injection(C):
+    spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.01))
+    args, k = _push_setup(C, spec)
+    args["drop"] = 1
+    before = k["p"].clone()
+    k["grad"][k["mask"]] = 1.0
+    C.push(args, native.ptr(k["lsync"]), 0, native.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(before, k["p"]) and torch.all(k["grad"] == 0)
+    assert int(k["ctrl"][5]) == 1 and int(k["ctrl"][3]) == 0
+
+
+@pytest.mark.parametrize("lock_mode", [0, 1])
+def test_pull_copies_publish_buffer(C, lock_mode):
+    n16, n32 = 64 * 1000, 4 * 300
+    src = torch.randn(n16, device="cuda").to(torch.bfloat16)
+    dst = torch.zeros_like(src)
+    s32 = torch.randn(n32, device="cuda")
+    d32 = torch.zeros_like(s32)
+    ctrl = torch.zeros(C.CTRL_WORDS, dtype=torch.int32, device="cuda")
+    ctrl[1] = 41
+    seen = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lsync = torch.zeros(8, dtype=torch.int32, device="cuda")
+    d = dict(src=native.ptr(src), dst=native.ptr(dst), src_f32=native.ptr(s32), dst_f32=native.ptr(d32),
+             n_bf16=n16, n_f32=n32, ctrl=native.ptr(ctrl), seen_version=native.ptr(seen), lock_mode=lock_mode)
+    for _ in range(2):
+        C.pull(d, native.ptr(lsync), 0, native.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(src, dst) and torch.equal(s32, d32) and int(seen[0]) == 41 and int(ctrl[0]) == 0
+
+
+def test_device_rwlock_word(C):
+    ctrl = torch.zeros(C.CTRL_WORDS, dtype=torch.int32, device="cuda")
+    st = native.current_stream()
+    C.lock_op(native.ptr(ctrl), 0, st); C.lock_op(native.ptr(ctrl), 0, st)
+    torch.cuda.synchronize()
+    assert int(ctrl[0]) == 2
+    C.lock_op(native.ptr(ctrl), 1, st); C.lock_op(native.ptr(ctrl), 1, st)
+    C.lock_op(native.ptr(ctrl), 2, st)
+    torch.cuda.synchronize()
+    assert int(ctrl[0]) == 1 << 16
+    C.lock_op(native.ptr(ctrl), 3, st)
+    torch.cuda.synchronize()
+    assert int(ctrl[0]) == 0
+
+
+def test_plan_capture_replay(C):
+    x = torch.randn(64, 32, device="cuda")
+    out = torch.zeros(64, 32, dtype=torch.bfloat16, device="cuda")
+    plan = C.Plan()
+    plan.add_cast_transpose(native.ptr(x), 32, 0, native.ptr(out), 32, 0, 0, 64, 32)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        plan.run(st.cuda_stream)
+        st.synchronize()
+        plan.capture(st.cuda_stream)
+        out.zero_()
+        plan.replay(st.cuda_stream)
+    st.synchronize()
+    assert torch.equal(out, x.to(torch.bfloat16))
