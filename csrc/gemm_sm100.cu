@@ -161,7 +161,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ep.bias != nullptr && is_split0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) f[j] += __ldg(ep.bias + col0 + j);
+          if (col0 + j < N) f[j] += ep.bias[col0 + j];   // may be peer memory: plain load
       }
       if (ep.act != SF_ACT_NONE) {
 #pragma unroll

@@ -1,0 +1,398 @@
+"""B200 engine: master parameter state + per-GPU worker that executes compiled step plans.
+
+Mapping of the reference's runtime (SURVEY.md sections 1, 3.1, 5.1) onto one B200 box:
+
+* parameter-server process (Flask, HogwildSparkModel.py:175-244)  ->  :class:`MasterState`, one
+  cudaMalloc'ed segment on the driver GPU holding the flat fp32 params, the optimizer slots, the bf16
+  publish buffer and a 256-byte control block (RW lock word, version, step counters).  The segment
+  is exported with CUDA IPC so every worker process addresses it over NVLink.
+* Spark partition worker (``handle_model``, HogwildSparkModel.py:38-100)  ->  :class:`DeviceWorker`:
+  one process per GPU.  A training step is a *compiled plan* – pull, input cast, tcgen05 GEMMs with
+  fused epilogues, loss kernel, wgrad/dgrad GEMMs, fused push – captured once into a CUDA graph and
+  replayed, so a step costs one graph launch on the host.
+* ``GET /parameters`` -> ``pull`` kernel (or TMA reads of the master's publish buffer straight from
+  the GEMMs in ``direct`` mode);  ``POST /update`` -> ``push`` kernel (optimizer applied on the master
+  shard over NVLink, lock-free or under the device RW lock).
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..graph.ir import GraphIR
+from ..models.compiler import ACT_IDS, LayerPlan, compile_graph
+from ..ops import native
+from ..ops.layout import ParamLayout, round_up
+from ..ops.optimizers import OptimizerSpec
+
+_ALIGN = 256
+
+
+class _RawCuda:
+    """Expose a raw device allocation to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _view(ptr: int, nbytes: int, dtype: torch.dtype, device: torch.device) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device).view(dtype)
+
+
+@dataclass
+class MasterLayout:
+    """Byte offsets of the fields inside the master segment."""
+    ctrl: int
+    p: int
+    slots: Tuple[int, int, int]
+    shadow: int
+    nbytes: int
+
+    @classmethod
+    def build(cls, layout: ParamLayout, ctrl_words: int) -> "MasterLayout":
+        off = 0
+
+        def take(n):
+            nonlocal off
+            start = off
+            off = round_up(off + n, _ALIGN)
+            return start
+
+        ctrl = take(ctrl_words * 4)
+        p = take(layout.total * 4)
+        slots = tuple(take(layout.total * 4) for _ in range(3))
+        shadow = take(layout.shadow_total * 2)
+        return cls(ctrl, p, slots, shadow, off)
+
+
+class MasterState:
+    """The parameter server's state on the driver GPU (or a mapping of it in a worker process)."""
+
+    def __init__(self, layout: ParamLayout, spec: OptimizerSpec, device: torch.device, base_ptr: Optional[int] = None):
+        self.C = native.cuda_ext()
+        self.layout, self.spec, self.device = layout, spec, device
+        self.ml = MasterLayout.build(layout, self.C.CTRL_WORDS)
+        self.owner = base_ptr is None
+        with torch.cuda.device(device):
+            self.base = self.C.ipc_alloc(self.ml.nbytes) if self.owner else int(base_ptr)
+        nb = self.ml.nbytes
+        self._bytes = _view(self.base, nb, torch.uint8, device)
+        self.ctrl = self._bytes[self.ml.ctrl:self.ml.ctrl + self.C.CTRL_WORDS * 4].view(torch.int32)
+        self.p = self._bytes[self.ml.p:self.ml.p + layout.total * 4].view(torch.float32)
+        self.slots = [self._bytes[o:o + layout.total * 4].view(torch.float32) for o in self.ml.slots]
+        self.shadow = self._bytes[self.ml.shadow:self.ml.shadow + layout.shadow_total * 2].view(torch.bfloat16)
+
+    # -- owner-side API ---------------------------------------------------------------------------
+    def ipc_handle(self) -> bytes:
+        with torch.cuda.device(self.device):
+            return bytes(self.C.ipc_get_handle(self.base))
+
+    @classmethod
+    def from_ipc(cls, layout: ParamLayout, spec: OptimizerSpec, device: torch.device, handle: bytes) -> "MasterState":
+        C = native.cuda_ext()
+        with torch.cuda.device(device):
+            base = C.ipc_open_handle(handle)
+        return cls(layout, spec, device, base_ptr=base)
+
+    def load_weights(self, weights: Sequence[np.ndarray]) -> None:
+        """Initialise params, slots, control block and the bf16 publish buffer (owner only)."""
+        flat = self.layout.flatten(weights)
+        self.p.copy_(torch.from_numpy(flat))
+        for i, s in enumerate(self.slots):
+            s.fill_(self.spec.slot_init(i) if i < self.spec.num_slots else 0.0)
+        self.ctrl.zero_()
+        pub = torch.from_numpy(self.layout.publish_reference(flat)).to(torch.bfloat16)
+        self.shadow.copy_(pub)
+        torch.cuda.synchronize(self.device)
+
+    def weights(self) -> List[np.ndarray]:
+        torch.cuda.synchronize(self.device)
+        return self.layout.unflatten(self.p.detach().cpu().numpy())
+
+    def slot_arrays(self) -> List[List[np.ndarray]]:
+        return [self.layout.unflatten(s.detach().cpu().numpy()) for s in self.slots[: self.spec.num_slots]]
+
+    def counters(self) -> Dict[str, int]:
+        c = self.ctrl.cpu().numpy()
+        return {"lock": int(c[0]), "version": int(c[1]), "step": int(c[2]), "pushes": int(c[3]), "errors": int(c[4]),
+                "dropped": int(c[5])}
+
+    def close(self) -> None:
+        if self.base:
+            with torch.cuda.device(self.device):
+                (self.C.ipc_free if self.owner else self.C.ipc_close_handle)(self.base)
+            self.base = 0
+
+
+@dataclass
+class StepBuffers:
+    x_stage: torch.Tensor          # fp32 [B, D]   H2D target
+    y_stage: Optional[torch.Tensor]
+    loss_out: torch.Tensor
+    result: Optional[torch.Tensor] = None
+
+
+class DeviceWorker:
+    """One GPU's replica + compiled step plans."""
+
+    def __init__(self, ir: GraphIR, tf_input: str, tf_label: Optional[str], spec: OptimizerSpec, master: MasterState,
+                 acquire_lock: bool = False, pull_mode: Optional[str] = None, use_graphs: bool = True,
+                 device: Optional[torch.device] = None):
+        self.C = native.cuda_ext()
+        self.ir = ir
+        self.plan: LayerPlan = compile_graph(ir, tf_input, tf_label, None, need_loss=True)
+        if not self.plan.is_mlp():
+            raise NotImplementedError("conv plans are built by ConvWorker")
+        self.spec, self.master = spec, master
+        self.layout = master.layout
+        self.device = device or master.device
+        self.lock_mode = 1 if acquire_lock else 0
+        self.pull_mode = pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")
+        if self.pull_mode == "direct" and self.lock_mode:
+            self.pull_mode = "copy"            # a locked pull must be a private snapshot
+        self.use_graphs = use_graphs and os.environ.get("SPARKFLOW_NO_GRAPHS") != "1"
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        dev = self.device
+        lay = self.layout
+        # local replica of what a pull fetches
+        self.replica = torch.zeros(lay.shadow_total, dtype=torch.bfloat16, device=dev)
+        self.vec_local = torch.zeros(max(lay.vec_count, 4), dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(lay.total, dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sync_push = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.sync_pull = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.seen_version = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.segs_dev = torch.frombuffer(bytearray(self.C.pack_segs(lay.seg_rows())), dtype=torch.uint8).to(dev)
+        self.tile_map = torch.from_numpy(lay.tile_map()).to(dev)
+        self._plans: Dict[Tuple[int, int], object] = {}
+        self._bufs: Dict[Tuple[int, int], StepBuffers] = {}
+        self._keep: List[object] = []
+        self.drop_next = 0
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------------------------------
+    def _weight_src(self) -> torch.Tensor:
+        """Where the forward/backward GEMMs read bf16 weights from."""
+        return self.master.shadow if self.pull_mode == "direct" else self.replica
+
+    def _bias_ptr(self, seg) -> int:
+        if self.pull_mode == "direct":
+            return native.ptr(self.master.p) + seg.offset * 4
+        return native.ptr(self.vec_local) + (seg.offset - self.layout.vec_offset) * 4
+
+    def _push_args(self, loss_out: torch.Tensor, drop: int = 0) -> dict:
+        m = self.master
+        slots = m.slots
+        return dict(p=native.ptr(m.p), s0=native.ptr(slots[0]), s1=native.ptr(slots[1]), s2=native.ptr(slots[2]),
+                    ctrl=native.ptr(m.ctrl), shadow_dst=[native.ptr(m.shadow)], grad=native.ptr(self.grads),
+                    loss_acc=native.ptr(self.loss_acc), loss_out=native.ptr(loss_out), segs=native.ptr(self.segs_dev),
+                    tile_map=native.ptr(self.tile_map), num_tiles=int(self.tile_map.shape[0]), optimizer=self.spec.opt_id,
+                    lock_mode=self.lock_mode, drop=drop, grad_scale=1.0, hyper=self.spec.native_hyper())
+
+    def _pull_args(self) -> dict:
+        lay, m = self.layout, self.master
+        return dict(src=native.ptr(m.shadow), dst=native.ptr(self.replica), n_bf16=lay.shadow_total,
+                    src_f32=native.ptr(m.p) + lay.vec_offset * 4 if lay.vec_count else 0,
+                    dst_f32=native.ptr(self.vec_local) if lay.vec_count else 0, n_f32=lay.vec_count,
+                    ctrl=native.ptr(m.ctrl), seen_version=native.ptr(self.seen_version), lock_mode=self.lock_mode)
+
+    # ------------------------------------------------------------------------------------------
+    def build_plan(self, B: int, slot: int = 0, with_pull: bool = True, with_push: bool = True):
+        """Compile the step for batch size ``B`` reading from staging-buffer set ``slot``."""
+        key = (B, slot, with_pull, with_push)
+        if key in self._plans:
+            return self._plans[key], self._bufs[key]
+        C, dev, lay, lp = self.C, self.device, self.layout, self.plan
+        dense = [l for l in lp.layers if l.kind == "dense"]
+        L = len(dense)
+        ldB = round_up(B, 8)
+        D = lp.input_dim
+        x_stage = torch.zeros(B, D, dtype=torch.float32, device=dev)
+        y_stage = None if lp.target_is_input else torch.zeros(B, lp.label_dim, dtype=torch.float32, device=dev)
+        loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
+        widths = [D] + [l.out_features for l in dense]
+        acts = [torch.zeros(B, round_up(w, 8), dtype=torch.bfloat16, device=dev) for w in widths[:-1]]
+        actsT = [torch.zeros(w, ldB, dtype=torch.bfloat16, device=dev) for w in widths[:-1]]
+        out_f32 = torch.zeros(B, widths[-1], dtype=torch.float32, device=dev)
+        dz = [torch.zeros(B, round_up(w, 8), dtype=torch.bfloat16, device=dev) for w in widths[1:]]
+        dzT = [torch.zeros(w, ldB, dtype=torch.bfloat16, device=dev) for w in widths[1:]]
+        wsrc = self._weight_src()
+        plan = C.Plan()
+        gemms = []
+        if with_pull and self.pull_mode != "direct":
+            plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
+        plan.add_cast_transpose(native.ptr(x_stage), D, 0, native.ptr(acts[0]), acts[0].shape[1], native.ptr(actsT[0]), ldB, B, D)
+        # ---------------- forward ----------------
+        for i, l in enumerate(dense):
+            ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
+            last = i == L - 1
+            d = dict(a=native.ptr(acts[i]), lda=acts[i].shape[1], b=native.ptr(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld,
+                     M=B, N=ks.cols, K=ks.rows, bias=self._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
+            if last:
+                d.update(out_f32=native.ptr(out_f32), ld_f32=widths[-1])
+            else:
+                d.update(out_bf16=native.ptr(acts[i + 1]), ld_bf16=acts[i + 1].shape[1], outT_bf16=native.ptr(actsT[i + 1]), ld_t=ldB)
+            g = C.Gemm(d)
+            gemms.append(g)
+            plan.add_gemm(g, f"fwd{i}")
+        # ---------------- loss ----------------
+        last_bias = lay.by_name(dense[-1].bias) if dense[-1].bias else None
+        db_ptr = native.ptr(self.grads) + last_bias.offset * 4 if last_bias else 0
+        target = x_stage if lp.target_is_input else y_stage
+        if lp.loss == "softmax_xent":
+            plan.add_softmax_xent(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], native.ptr(self.loss_acc),
+                                  native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
+        else:
+            plan.add_mse(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], ACT_IDS[dense[-1].act],
+                         native.ptr(self.loss_acc), native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
+        # ---------------- backward ----------------
+        for i in range(L - 1, -1, -1):
+            l = dense[i]
+            ks = lay.by_name(l.kernel)
+            wg = C.Gemm(dict(a=native.ptr(actsT[i]), lda=ldB, b=native.ptr(dzT[i]), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
+                             out_f32=native.ptr(self.grads) + ks.offset * 4, ld_f32=ks.cols))
+            gemms.append(wg)
+            plan.add_gemm(wg, f"wgrad{i}")
+            if i > 0:
+                prev = dense[i - 1]
+                pb = lay.by_name(prev.bias) if prev.bias else None
+                dg = C.Gemm(dict(a=native.ptr(dz[i]), lda=dz[i].shape[1], b=native.ptr(wsrc) + ks.w_off * 2, ldb=ks.w_ld,
+                                 M=B, N=ks.rows, K=ks.cols, aux=native.ptr(acts[i]), ld_aux=acts[i].shape[1],
+                                 aux_act=ACT_IDS[prev.act], out_bf16=native.ptr(dz[i - 1]), ld_bf16=dz[i - 1].shape[1],
+                                 outT_bf16=native.ptr(dzT[i - 1]), ld_t=ldB,
+                                 colsum=native.ptr(self.grads) + pb.offset * 4 if pb else 0))
+                gemms.append(dg)
+                plan.add_gemm(dg, f"dgrad{i}")
+        if with_push:
+            plan.add_push(self._push_args(loss_out), native.ptr(self.sync_push), 0)
+        self._keep.extend([acts, actsT, out_f32, dz, dzT, gemms])
+        bufs = StepBuffers(x_stage, y_stage, loss_out)
+        self._plans[key], self._bufs[key] = plan, bufs
+        self.launches_per_step = len(plan)
+        return plan, bufs
+
+    # ------------------------------------------------------------------------------------------
+    def build_forward_plan(self, B: int, upto: Optional[int] = None, post: Optional[str] = None, with_loss: bool = False,
+                           with_pull: bool = False):
+        """Forward-only plan: up to dense layer ``upto`` (inclusive, default last) producing an fp32
+        output (+ArgMax), or the full forward + loss kernel (no gradients) when ``with_loss``."""
+        key = ("fwd", B, upto, post, with_loss, with_pull)
+        if key in self._plans:
+            return self._plans[key], self._bufs[key]
+        C, dev, lay, lp = self.C, self.device, self.layout, self.plan
+        dense = [l for l in lp.layers if l.kind == "dense"]
+        if upto is None:
+            upto = len(dense) - 1
+        D = lp.input_dim
+        x_stage = torch.zeros(B, D, dtype=torch.float32, device=dev)
+        y_stage = None
+        if with_loss and not lp.target_is_input:
+            y_stage = torch.zeros(B, lp.label_dim, dtype=torch.float32, device=dev)
+        widths = [D] + [l.out_features for l in dense]
+        acts = [torch.zeros(B, round_up(w, 8), dtype=torch.bfloat16, device=dev) for w in widths[: upto + 1]]
+        out_f32 = torch.zeros(B, widths[upto + 1], dtype=torch.float32, device=dev)
+        result = torch.zeros(B, dtype=torch.float32, device=dev) if post == "ArgMax" else out_f32
+        loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
+        wsrc = self._weight_src()
+        plan = C.Plan()
+        gemms = []
+        if with_pull and self.pull_mode != "direct":
+            plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
+        if upto >= 0:
+            plan.add_cast_transpose(native.ptr(x_stage), D, 0, native.ptr(acts[0]), acts[0].shape[1], 0, 0, B, D)
+        for i in range(upto + 1):
+            l = dense[i]
+            ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
+            d = dict(a=native.ptr(acts[i]), lda=acts[i].shape[1], b=native.ptr(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld,
+                     M=B, N=ks.cols, K=ks.rows, bias=self._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
+            if i == upto:
+                d.update(out_f32=native.ptr(out_f32), ld_f32=widths[upto + 1])
+            else:
+                d.update(out_bf16=native.ptr(acts[i + 1]), ld_bf16=acts[i + 1].shape[1])
+            g = C.Gemm(d)
+            gemms.append(g)
+            plan.add_gemm(g, f"fwd{i}")
+        if with_loss:
+            target = x_stage if lp.target_is_input else y_stage
+            if lp.loss == "softmax_xent":
+                plan.add_softmax_xent(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], native.ptr(loss_out),
+                                      0, 0, 0, 0, 0, B, widths[-1])
+            else:
+                plan.add_mse(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], ACT_IDS[dense[-1].act],
+                             native.ptr(loss_out), 0, 0, 0, 0, 0, B, widths[-1])
+        elif post == "ArgMax":
+            plan.add_argmax(native.ptr(out_f32), widths[upto + 1], native.ptr(result), B, widths[upto + 1])
+        self._keep.extend([acts, out_f32, gemms, result])
+        bufs = StepBuffers(x_stage, y_stage, loss_out)
+        bufs.result = result
+        self._plans[key], self._bufs[key] = plan, bufs
+        return plan, bufs
+
+    EVAL_CHUNK = 4096
+
+    def partition_loss(self, X: torch.Tensor, Y: Optional[torch.Tensor]) -> float:
+        """Full-partition loss with the worker's current weights (reference: HogwildSparkModel.py:94-96)."""
+        n = X.shape[0]
+        total = 0.0
+        for r in range(0, n, self.EVAL_CHUNK):
+            rows = min(self.EVAL_CHUNK, n - r)
+            plan, bufs = self.build_forward_plan(rows, with_loss=True)
+            with torch.cuda.stream(self.stream):
+                bufs.x_stage.copy_(X[r:r + rows], non_blocking=True)
+                if bufs.y_stage is not None and Y is not None:
+                    bufs.y_stage.copy_(Y[r:r + rows], non_blocking=True)
+                bufs.loss_out.zero_()
+                plan.run(self.stream.cuda_stream)
+            self.stream.synchronize()
+            total += float(bufs.loss_out[0]) * rows
+        return total / max(n, 1)
+
+    def predict(self, X: np.ndarray, upto: int, post: Optional[str]) -> np.ndarray:
+        n = X.shape[0]
+        Xp = torch.as_tensor(np.ascontiguousarray(X, dtype=np.float32)).pin_memory()
+        outs = []
+        for r in range(0, n, self.EVAL_CHUNK):
+            rows = min(self.EVAL_CHUNK, n - r)
+            plan, bufs = self.build_forward_plan(rows, upto=upto, post=post)
+            with torch.cuda.stream(self.stream):
+                bufs.x_stage.copy_(Xp[r:r + rows], non_blocking=True)
+                plan.run(self.stream.cuda_stream)
+            self.stream.synchronize()
+            outs.append(bufs.result.detach().cpu().numpy().copy())
+        return np.concatenate(outs, axis=0) if outs else np.zeros((0,), np.float32)
+
+    def need_w_map(self) -> Tuple[Dict[str, bool], Dict[str, bool]]:
+        return plan_publish_needs(self.plan)
+
+    # ------------------------------------------------------------------------------------------
+    def run_plan(self, plan) -> None:
+        """Launch one step on the worker stream (CUDA graph after the first eager execution)."""
+        st = self.stream.cuda_stream
+        if not self.use_graphs:
+            plan.run(st)
+            return
+        if not plan.captured():
+            plan.run(st)                      # eager warm-up (sets func attributes, validates launches)
+            self.stream.synchronize()
+            # the eager step consumed the gradient; capture records a second, identical step
+            plan.capture(st)
+            return
+        plan.replay(st)
+
+
+def plan_publish_needs(lp: LayerPlan) -> Tuple[Dict[str, bool], Dict[str, bool]]:
+    """Which bf16 layouts each kernel variable must be published in (W for dgrad, W^T for forward)."""
+    need_w: Dict[str, bool] = {}
+    need_wt: Dict[str, bool] = {}
+    first = True
+    for l in lp.layers:
+        if l.kind in ("dense", "conv"):
+            need_wt[l.kernel] = True
+            need_w[l.kernel] = not first
+            first = False
+    return need_w, need_wt

@@ -1,0 +1,204 @@
+"""Host parameter server: the CPU / gloo twin of the fused GPU push/pull path.
+
+Reference behaviour that is preserved (/root/reference/sparkflow/HogwildSparkModel.py:175-244):
+  * the master holds the weights AND all optimizer state; workers only ever send raw gradients;
+  * ONE optimizer step per push, gradients are never summed across workers;
+  * ``acquire_lock=False`` (Hogwild): pulls and updates race freely; ``True``: writer-priority RW lock;
+  * a failing update is swallowed and counted, training aborts after ``max_errors`` (= iters) failures.
+Reference behaviour that is fixed: no 8 s start-up sleep (readiness is explicit), no HTTP/pickle.
+
+Two transports expose the same ``pull`` / ``push`` calls to the worker loop:
+  * :class:`LocalTransport` – workers are threads of the driver process (Spark ``local[N]`` analogue);
+  * :class:`GlooTransport`  – one process per worker, rank 0 hosts the server threads, messages are
+    flat fp32 tensors over ``torch.distributed`` send/recv (BASELINE.json config 1: CPU / gloo).
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+import time
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ..ops.optimizers import OptimizerSpec, apply_update, init_slots
+from .rwlock import RWLock
+
+
+class TooManyFailures(RuntimeError):
+    pass
+
+
+class ParameterServer:
+    """Master copy of the flat parameters + optimizer slots."""
+
+    def __init__(self, weights: Sequence[np.ndarray], spec: OptimizerSpec, acquire_lock: bool = False, max_errors: int = 1000):
+        self.shapes = [tuple(np.shape(w)) for w in weights]
+        self.sizes = [int(np.prod(s)) if s else 1 for s in self.shapes]
+        flat = np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights]) if weights else np.zeros(0, np.float32)
+        self.p = torch.from_numpy(flat.copy())
+        self.spec = spec
+        self.slots = init_slots(spec, self.p)
+        self.lock = RWLock() if acquire_lock else None
+        self.max_errors = max_errors
+        self.pushes = 0
+        self.errors = 0
+        self.dropped = 0
+        self._counter = itertools.count(1)
+        self._count_lock = threading.Lock()
+        self.fault_hook: Optional[Callable[[int], Optional[str]]] = None     # push index -> None | 'drop' | 'raise' | 'delay:<s>'
+
+    # -- the two "routes" ---------------------------------------------------------------------------
+    def get_parameters(self) -> torch.Tensor:
+        if self.lock:
+            with self.lock.reading():
+                return self.p.clone()
+        return self.p.clone()
+
+    def update_parameters(self, grad_flat: torch.Tensor) -> str:
+        with self._count_lock:
+            idx = next(self._counter)
+        action = self.fault_hook(idx) if self.fault_hook else None
+        if action == "drop":
+            self.dropped += 1
+            return "dropped"
+        if action and action.startswith("delay:"):
+            time.sleep(float(action.split(":", 1)[1]))
+        try:
+            if action == "raise":
+                raise RuntimeError("injected update failure")
+            if grad_flat.numel() != self.p.numel():
+                raise ValueError("gradient size does not match the parameter vector")
+            if self.lock:
+                with self.lock.writing():
+                    self._apply(grad_flat)
+            else:
+                self._apply(grad_flat)
+        except Exception:
+            self.errors += 1
+            if self.errors >= self.max_errors:
+                raise TooManyFailures("Too many failures during training")
+            return "failed"
+        return "completed"
+
+    def _apply(self, g: torch.Tensor) -> None:
+        self.pushes += 1
+        apply_update(self.spec, self.p, g, self.slots, self.pushes)
+
+    # -- conversions ----------------------------------------------------------------------------------
+    def unflatten(self, flat: torch.Tensor) -> List[np.ndarray]:
+        out, off = [], 0
+        arr = flat.detach().cpu().numpy()
+        for shp, n in zip(self.shapes, self.sizes):
+            out.append(arr[off:off + n].reshape(shp).copy())
+            off += n
+        return out
+
+    def weights(self) -> List[np.ndarray]:
+        return self.unflatten(self.get_parameters())
+
+
+def flatten_grads(grads: Sequence) -> torch.Tensor:
+    return torch.cat([(g if isinstance(g, torch.Tensor) else torch.as_tensor(np.asarray(g))).reshape(-1).to(torch.float32).cpu() for g in grads])
+
+
+class LocalTransport:
+    def __init__(self, server: ParameterServer):
+        self.server = server
+
+    def pull(self) -> List[np.ndarray]:
+        return self.server.unflatten(self.server.get_parameters())
+
+    def push(self, grads: Sequence) -> str:
+        return self.server.update_parameters(flatten_grads(grads))
+
+    def close(self) -> None:
+        pass
+
+
+# -------------------------------------------------------------------------------------------------
+# gloo
+# -------------------------------------------------------------------------------------------------
+_OP_PULL, _OP_PUSH, _OP_DONE = 1, 2, 3
+
+
+class GlooServer:
+    """Rank-0 side: one service thread per remote worker (the reference's Flask is ``threaded=True``:
+    one thread per request, so updates from different workers interleave exactly like here)."""
+
+    def __init__(self, server: ParameterServer, world_size: int, group=None):
+        import torch.distributed as dist
+
+        self.server, self.world, self.group, self.dist = server, world_size, group, dist
+        self.threads = [threading.Thread(target=self._serve, args=(r,), daemon=True, name=f"ps-serve-{r}") for r in range(1, world_size)]
+        self.failure: Optional[BaseException] = None
+        for t in self.threads:
+            t.start()
+
+    def _serve(self, src: int) -> None:
+        dist = self.dist
+        n = self.server.p.numel()
+        try:
+            while True:
+                hdr = torch.zeros(2, dtype=torch.int64)
+                dist.recv(hdr, src=src, group=self.group, tag=src)
+                op = int(hdr[0])
+                if op == _OP_DONE:
+                    return
+                if op == _OP_PULL:
+                    dist.send(self.server.get_parameters(), dst=src, group=self.group, tag=1000 + src)
+                elif op == _OP_PUSH:
+                    g = torch.empty(n, dtype=torch.float32)
+                    dist.recv(g, src=src, group=self.group, tag=src)
+                    try:
+                        status = self.server.update_parameters(g)
+                    except TooManyFailures as exc:
+                        self.failure = exc
+                        status = "fatal"
+                    code = {"completed": 0, "failed": 1, "dropped": 2, "fatal": 3}[status]
+                    dist.send(torch.tensor([code], dtype=torch.int64), dst=src, group=self.group, tag=1000 + src)
+        except Exception as exc:  # pragma: no cover - transport failure
+            self.failure = exc
+
+    def join(self, timeout: Optional[float] = None) -> None:
+        for t in self.threads:
+            t.join(timeout)
+
+
+class GlooTransport:
+    """Worker-side stub (ranks != 0).  Rank 0's own worker uses a :class:`LocalTransport`."""
+
+    def __init__(self, rank: int, shapes: Sequence[tuple], group=None):
+        import torch.distributed as dist
+
+        self.rank, self.group, self.dist = rank, group, dist
+        self.shapes = [tuple(s) for s in shapes]
+        self.sizes = [int(np.prod(s)) if s else 1 for s in self.shapes]
+        self.n = int(sum(self.sizes))
+
+    def _hdr(self, op: int) -> None:
+        self.dist.send(torch.tensor([op, self.n], dtype=torch.int64), dst=0, group=self.group, tag=self.rank)
+
+    def pull(self) -> List[np.ndarray]:
+        self._hdr(_OP_PULL)
+        flat = torch.empty(self.n, dtype=torch.float32)
+        self.dist.recv(flat, src=0, group=self.group, tag=1000 + self.rank)
+        arr, out, off = flat.numpy(), [], 0
+        for shp, n in zip(self.shapes, self.sizes):
+            out.append(arr[off:off + n].reshape(shp).copy())
+            off += n
+        return out
+
+    def push(self, grads: Sequence) -> str:
+        self._hdr(_OP_PUSH)
+        self.dist.send(flatten_grads(grads), dst=0, group=self.group, tag=self.rank)
+        code = torch.zeros(1, dtype=torch.int64)
+        self.dist.recv(code, src=0, group=self.group, tag=1000 + self.rank)
+        status = {0: "completed", 1: "failed", 2: "dropped", 3: "fatal"}[int(code)]
+        if status == "fatal":
+            raise TooManyFailures("Too many failures during training")
+        return status
+
+    def close(self) -> None:
+        self._hdr(_OP_DONE)

@@ -1,0 +1,211 @@
+"""The per-partition training loop (engine-agnostic) and the two engines that execute its steps.
+
+Loop semantics are the reference's ``handle_model`` (/root/reference/sparkflow/HogwildSparkModel.py:38-100):
+
+* per outer iteration: pull, optional shuffle, then ONE of
+  A. ``mini_stochastic_iters >= 1`` – that many random minibatches (without replacement inside a batch),
+     all computed on the weights pulled at the start of the iteration (no re-pull), one push each;
+  B. ``mini_batch_size >= 1`` – a full sweep in contiguous minibatches, re-pulling before each;
+  C. otherwise – one gradient over the whole partition;
+* a failed push is reported ("Timeout error from partition ...") and training continues;
+* ``verbose`` / ``loss_callback``: full-partition loss after every outer iteration.
+
+Engines:
+* :class:`TorchEngine` – GraphProgram (autograd) + a host transport (threads or gloo). CPU path, and the
+  generic path for graphs the compiled plan does not cover.
+* :class:`B200Engine`  – DeviceWorker: compiled sm_100a step plans, pinned-host partitions fed through
+  a side stream, fused NVLink push/pull.
+"""
+from __future__ import annotations
+
+import uuid
+from typing import Callable, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from ..graph.executor import GraphProgram
+from ..graph.ir import GraphIR
+
+Rows = Union[slice, np.ndarray]
+
+
+def clamp_batch(n: int, mini_batch_size: int) -> int:
+    """``mini_batch_size > n  ->  n - 1`` (reference quirk, ml_util.py:105-106)."""
+    return n - 1 if mini_batch_size > n else mini_batch_size
+
+
+class Engine:
+    partition_rows = 0
+
+    def load_partition(self, features: np.ndarray, labels: Optional[np.ndarray]) -> None:
+        raise NotImplementedError
+
+    def train(self, rows: Rows, pull: bool) -> None:
+        raise NotImplementedError
+
+    def partition_loss(self) -> float:
+        raise NotImplementedError
+
+    def finish(self) -> None:
+        pass
+
+
+def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndarray], iters: int = 1000,
+                  mini_batch_size: int = -1, shuffle: bool = True, mini_stochastic_iters: int = -1, verbose: int = 0,
+                  loss_callback: Optional[Callable[[float, int, str], None]] = None, partition_id: Optional[str] = None,
+                  seed: Optional[int] = None) -> str:
+    partition_id = partition_id or uuid.uuid4().hex
+    n = int(features.shape[0])
+    if n == 0:
+        return partition_id
+    engine.load_partition(features, labels)
+    rng = np.random.default_rng(seed)
+    order: Optional[np.ndarray] = None
+    for i in range(iters):
+        if shuffle:
+            order = rng.permutation(n)
+
+        def rows_of(sel: Rows) -> Rows:
+            if order is None:
+                return sel
+            return order[sel]
+
+        if mini_stochastic_iters >= 1:
+            mbs = clamp_batch(n, mini_batch_size)
+            for j in range(mini_stochastic_iters):
+                if mbs <= 0:
+                    sel: Rows = slice(0, n)
+                else:
+                    sel = rng.choice(n, mbs, replace=False)
+                engine.train(rows_of(sel), pull=(j == 0))
+        elif mini_batch_size >= 1:
+            mbs = max(clamp_batch(n, mini_batch_size), 1)
+            for r in range(0, n, mbs):
+                engine.train(rows_of(slice(r, min(r + mbs, n))), pull=True)
+        else:
+            engine.train(rows_of(slice(0, n)), pull=True)
+
+        if verbose or loss_callback:
+            loss = engine.partition_loss()
+            if verbose:
+                print("Partition Id: %s, Iteration: %i, Loss: %f" % (partition_id, i, loss))
+            if loss_callback:
+                loss_callback(loss, i, partition_id)
+    engine.finish()
+    return partition_id
+
+
+# -------------------------------------------------------------------------------------------------
+class TorchEngine(Engine):
+    def __init__(self, ir: GraphIR, tf_input: str, tf_label: Optional[str], transport, device: str = "cpu",
+                 partition_id: str = ""):
+        self.prog = GraphProgram(ir, device)
+        self.tf_input, self.tf_label, self.transport = tf_input, tf_label, transport
+        self.weights: Optional[List[np.ndarray]] = None
+        self.partition_id = partition_id
+        self.failed_pushes = 0
+
+    def load_partition(self, features, labels):
+        self.X = torch.as_tensor(np.asarray(features, dtype=np.float32))
+        self.Y = None if labels is None else torch.as_tensor(np.asarray(labels, dtype=np.float32))
+        self.partition_rows = self.X.shape[0]
+
+    def _feed(self, rows: Rows):
+        idx = rows if isinstance(rows, slice) else torch.as_tensor(np.asarray(rows, dtype=np.int64))
+        feed = {self.tf_input: self.X[idx]}
+        if self.tf_label is not None and self.Y is not None:
+            feed[self.tf_label] = self.Y[idx]
+        return feed
+
+    def train(self, rows, pull):
+        if pull or self.weights is None:
+            self.weights = self.transport.pull()
+        _, grads = self.prog.loss_and_grads(self._feed(rows), self.weights)
+        try:
+            self.transport.push(grads)
+        except Exception as exc:
+            from .param_server import TooManyFailures
+
+            if isinstance(exc, TooManyFailures):
+                raise
+            self.failed_pushes += 1
+            print("Timeout error from partition %s" % self.partition_id)
+
+    def partition_loss(self) -> float:
+        return self.prog.loss(self._feed(slice(0, self.partition_rows)), self.weights or self.transport.pull())
+
+
+# -------------------------------------------------------------------------------------------------
+class B200Engine(Engine):
+    """Pinned-host partition + DeviceWorker.  Every step copies its minibatch host->device on a side
+    stream (double-buffered staging) and leaves the step's loss in a pinned host ring."""
+
+    LOSS_RING = 64
+
+    def __init__(self, worker):
+        self.w = worker
+        self.step_idx = 0
+        self.loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32).pin_memory()
+        self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
+        self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self._primed = [False, False]
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._gather = [None, None]
+
+    def load_partition(self, features, labels):
+        self.X = torch.as_tensor(np.ascontiguousarray(features, dtype=np.float32)).pin_memory()
+        self.Y = None
+        if labels is not None and not self.w.plan.target_is_input:
+            self.Y = torch.as_tensor(np.ascontiguousarray(labels, dtype=np.float32)).pin_memory()
+        self.partition_rows = self.X.shape[0]
+
+    def _host_batch(self, rows: Rows, slot: int):
+        if isinstance(rows, slice):
+            return self.X[rows], (None if self.Y is None else self.Y[rows])
+        idx = torch.as_tensor(np.asarray(rows, dtype=np.int64))
+        B = idx.numel()
+        g = self._gather[slot]
+        if g is None or g[0].shape[0] != B:
+            gx = torch.empty(B, self.X.shape[1], dtype=torch.float32).pin_memory()
+            gy = None if self.Y is None else torch.empty(B, self.Y.shape[1], dtype=torch.float32).pin_memory()
+            g = self._gather[slot] = (gx, gy)
+        torch.index_select(self.X, 0, idx, out=g[0])
+        if g[1] is not None:
+            torch.index_select(self.Y, 0, idx, out=g[1])
+        return g
+
+    def train(self, rows, pull):
+        w = self.w
+        slot = self.step_idx & 1
+        B = (rows.stop - rows.start) if isinstance(rows, slice) else len(rows)
+        plan, bufs = w.build_plan(B, slot, with_pull=pull)
+        if self._primed[slot]:
+            self._slot_free[slot].synchronize()            # host gather buffer + staging are reusable
+        hx, hy = self._host_batch(rows, slot)
+        with torch.cuda.stream(w.copy_stream):
+            bufs.x_stage.copy_(hx, non_blocking=True)
+            self.h2d_bytes += hx.numel() * 4
+            if bufs.y_stage is not None and hy is not None:
+                bufs.y_stage.copy_(hy, non_blocking=True)
+                self.h2d_bytes += hy.numel() * 4
+            self._slot_ready[slot].record(w.copy_stream)
+        w.stream.wait_event(self._slot_ready[slot])
+        w.run_plan(plan)
+        with torch.cuda.stream(w.stream):
+            self.loss_ring[self.step_idx % self.LOSS_RING].copy_(bufs.loss_out[0], non_blocking=True)
+            self.d2h_bytes += 4
+            self._slot_free[slot].record(w.stream)
+        self._primed[slot] = True
+        self.step_idx += 1
+
+    def last_loss(self) -> float:
+        self.w.stream.synchronize()
+        return float(self.loss_ring[(self.step_idx - 1) % self.LOSS_RING])
+
+    def partition_loss(self) -> float:
+        return self.w.partition_loss(self.X, self.Y)
+
+    def finish(self):
+        self.w.stream.synchronize()
