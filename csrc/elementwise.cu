@@ -37,6 +37,8 @@ cast_transpose_kernel(const float* __restrict__ in, int ld_in, const int32_t* __
                       __nv_bfloat16* __restrict__ out, int ld_out, __nv_bfloat16* __restrict__ outT,
                       int ld_t, int rows, int cols) {
   __shared__ float tile[32][33];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
 #pragma unroll
@@ -72,6 +74,8 @@ softmax_xent_kernel(const float* __restrict__ logits, int ld_logits, const float
                     __nv_bfloat16* __restrict__ dzT, int ld_t, float* __restrict__ dbias, int rows,
                     int cols) {
   extern __shared__ float s_db[];   // [cols]
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) s_db[c] = 0.f;
@@ -125,6 +129,8 @@ mse_kernel(const float* __restrict__ out, int ld_out, const float* __restrict__ 
   __shared__ float tile[32][33];
   __shared__ float s_col[32];
   __shared__ float s_loss[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   if (threadIdx.x < 32) s_col[threadIdx.x] = 0.f;
@@ -168,6 +174,8 @@ mse_kernel(const float* __restrict__ out, int ld_out, const float* __restrict__ 
 
 __global__ void __launch_bounds__(256)
 argmax_rows_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int rows, int cols) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* z = in + static_cast<size_t>(warp) * ld;
@@ -193,8 +201,8 @@ extern "C" int sf_cast_transpose(const float* in, int ld_in, __nv_bfloat16* out,
   const int span_c = (out && ld_out > cols) ? ld_out : cols;
   const int span_r = (outT && ld_t > rows) ? ld_t : rows;
   dim3 grid((span_c + 31) / 32, (span_r + 31) / 32);
-  sf::cast_transpose_kernel<false><<<grid, 256, 0, st>>>(in, ld_in, nullptr, out, ld_out, outT, ld_t, rows, cols);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::cast_transpose_kernel<false>, grid, dim3(256), 0, st, in, ld_in,
+                                     static_cast<const int32_t*>(nullptr), out, ld_out, outT, ld_t, rows, cols));
 }
 
 extern "C" int sf_gather_cast_transpose(const float* in, int ld_in, const int32_t* idx,
@@ -203,8 +211,8 @@ extern "C" int sf_gather_cast_transpose(const float* in, int ld_in, const int32_
   const int span_c = (out && ld_out > cols) ? ld_out : cols;
   const int span_r = (outT && ld_t > rows) ? ld_t : rows;
   dim3 grid((span_c + 31) / 32, (span_r + 31) / 32);
-  sf::cast_transpose_kernel<true><<<grid, 256, 0, st>>>(in, ld_in, idx, out, ld_out, outT, ld_t, rows, cols);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::cast_transpose_kernel<true>, grid, dim3(256), 0, st, in, ld_in, idx, out,
+                                     ld_out, outT, ld_t, rows, cols));
 }
 
 extern "C" int sf_softmax_xent(const float* logits, int ld_logits, const float* labels, int ld_labels,
@@ -212,9 +220,8 @@ extern "C" int sf_softmax_xent(const float* logits, int ld_logits, const float* 
                                float* dbias, int rows, int cols, cudaStream_t st) {
   int blocks = (rows + 7) / 8;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  sf::softmax_xent_kernel<<<blocks, 256, cols * sizeof(float), st>>>(
-      logits, ld_logits, labels, ld_labels, loss, dz, ld_dz, dzT, ld_t, dbias, rows, cols);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::softmax_xent_kernel, dim3(blocks), dim3(256), cols * sizeof(float), st,
+                                     logits, ld_logits, labels, ld_labels, loss, dz, ld_dz, dzT, ld_t, dbias, rows, cols));
 }
 
 extern "C" int sf_mse_loss(const float* out, int ld_out, const float* target, int ld_target, int act,
@@ -222,15 +229,13 @@ extern "C" int sf_mse_loss(const float* out, int ld_out, const float* target, in
                            float* dbias, int rows, int cols, cudaStream_t st) {
   const int span_c = (dz && ld_dz > cols) ? ld_dz : cols;
   dim3 grid((span_c + 31) / 32, (rows + 31) / 32);
-  sf::mse_kernel<<<grid, 256, 0, st>>>(out, ld_out, target, ld_target, act, loss, dz, ld_dz, dzT, ld_t,
-                                       dbias, rows, cols);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::mse_kernel, grid, dim3(256), 0, st, out, ld_out, target, ld_target, act,
+                                     loss, dz, ld_dz, dzT, ld_t, dbias, rows, cols));
 }
 
 extern "C" int sf_argmax_rows(const float* in, int ld, float* out, int rows, int cols, cudaStream_t st) {
   const int blocks = (rows * 32 + 255) / 256;
-  sf::argmax_rows_kernel<<<blocks, 256, 0, st>>>(in, ld, out, rows, cols);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::argmax_rows_kernel, dim3(blocks), dim3(256), 0, st, in, ld, out, rows, cols));
 }
 
 extern "C" int sf_fill_zero(void* p, size_t bytes, cudaStream_t st) {

@@ -73,6 +73,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + S::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;
@@ -98,6 +99,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the previous kernel; global memory is touched below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -166,6 +168,52 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (ep.act != SF_ACT_NONE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+      }
+      if (ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
+        // whole row lives in this thread (host guarantees N <= 32): softmax + CE + gradient in registers
+        float ysum = 0.f, zy = 0.f, mx = -INFINITY, yv[32];
+        const float* yp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool ok = row_ok && (col0 + j < N);
+          yv[j] = ok ? yp[col0 + j] : 0.f;
+          if (ok) mx = fmaxf(mx, f[j]);
+        }
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + j < N && row_ok) {
+            se += __expf(f[j] - mx);
+            ysum += yv[j];
+            zy += yv[j] * f[j];
+          }
+        }
+        const float inv_b = 1.f / static_cast<float>(M);
+        float lrow = row_ok ? ((mx + __logf(se)) * ysum - zy) * inv_b : 0.f;
+        const float inv_se = row_ok ? 1.f / se : 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          f[j] = (col0 + j < N && row_ok) ? (__expf(f[j] - mx) * inv_se * ysum - yv[j]) * inv_b : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
+        if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow);
+      } else if (ep.loss_mode == SF_LOSS_MSE) {
+        const float scale = 2.f / (static_cast<float>(M) * static_cast<float>(N));
+        const float* tp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target + col0;
+        float lrow = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (row_ok && col0 + j < N) {
+            const float d = f[j] - tp[j];
+            lrow += d * d;
+            f[j] = d * scale * act_bwd_from_out(f[j], ep.act);
+          } else {
+            f[j] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
+        if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow * 0.5f * scale);
       }
       if (ep.aux != nullptr && row_ok) {
         const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + col0;
@@ -321,6 +369,11 @@ extern "C" int sf_gemm_prepare(SfGemm* g) {
   g->kblocks_per_split = (total_kb + g->split_k - 1) / g->split_k;
   g->split_k = (total_kb + g->kblocks_per_split - 1) / g->kblocks_per_split;
   if (g->split_k > 1) g->ep.accumulate = 1;
+  if (g->ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
+    if (g->N > 32 || g->split_k > 1) return -5;     // the row must fit one epilogue chunk
+    g->bn = 32;
+  }
+  if (g->ep.loss_mode != SF_LOSS_NONE && (g->split_k > 1 || !g->ep.target || !g->ep.loss)) return -5;
   // largest column any output can hold
   int lim = g->N;
   if (g->ep.out_bf16 && g->ep.ld_bf16 > lim) lim = g->ep.ld_bf16;
@@ -339,9 +392,8 @@ static cudaError_t launch_bn(const SfGemm* g, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((g->N + BN - 1) / BN, (g->M + sf::kBM - 1) / sf::kBM, g->split_k);
-  sf::sf_gemm_kernel<BN><<<grid, sf::kGemmThreads, S::kBytes, st>>>(g->tmA, g->tmB, g->ep, g->M,
-                                                                   g->N, g->K, g->kblocks_per_split);
-  return cudaGetLastError();
+  return sf::launch(sf::sf_gemm_kernel<BN>, grid, dim3(sf::kGemmThreads), S::kBytes, st, g->tmA, g->tmB, g->ep,
+                    g->M, g->N, g->K, g->kblocks_per_split);
 }
 
 extern "C" int sf_gemm_launch(const SfGemm* g, cudaStream_t st) {
@@ -355,6 +407,8 @@ extern "C" int sf_gemm_launch(const SfGemm* g, cudaStream_t st) {
   }
   return static_cast<int>(e);
 }
+
+extern "C" void sf_set_pdl(int enabled) { sf::pdl_enabled() = enabled ? 1 : 0; }
 
 extern "C" unsigned int sf_read_error_code() {
   unsigned int v = 0;

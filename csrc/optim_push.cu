@@ -178,6 +178,8 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_t;
   __shared__ uint32_t s_epoch;
   __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   constexpr int NS = Slots<OPT>::n;
 
@@ -341,6 +343,8 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
 __global__ void __launch_bounds__(256, 1)
 pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_epoch;
+  pdl_launch_dependents();
+  pdl_wait();
   const int tid = threadIdx.x;
   if (a.lock_mode == SF_LOCK_RW) {
     if (tid == 0) {
@@ -411,8 +415,7 @@ __global__ void lock_test_kernel(uint32_t* ctrl, int op) {
 
 template <int OPT>
 static int launch_push(const SfPushArgs* a, uint32_t* ls, int grid, cudaStream_t st) {
-  sf::push_kernel<OPT><<<grid, sf::kPushThreads, 0, st>>>(*a, ls);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::push_kernel<OPT>, dim3(grid), dim3(sf::kPushThreads), 0, st, *a, ls));
 }
 
 extern "C" int sf_push_launch(const SfPushArgs* a, uint32_t* local_sync, int grid, cudaStream_t st) {
@@ -441,8 +444,7 @@ extern "C" int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int gri
     if (grid > 148) grid = 148;
     if (grid < 1) grid = 1;
   }
-  sf::pull_kernel<<<grid, 256, 0, st>>>(*a, local_sync);
-  return static_cast<int>(cudaGetLastError());
+  return static_cast<int>(sf::launch(sf::pull_kernel, dim3(grid), dim3(256), 0, st, *a, local_sync));
 }
 
 extern "C" int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st) {

@@ -74,6 +74,10 @@ struct Gemm {
     g.ep.act = getd<int>(d, "act", 0);
     g.ep.accumulate = getd<int>(d, "accumulate", 0);
     g.ep.a_evict_first = getd<int>(d, "a_evict_first", 0);
+    g.ep.loss_mode = getd<int>(d, "loss_mode", 0);
+    g.ep.target = P<const float>(getd<uintptr_t>(d, "target", 0));
+    g.ep.ld_target = getd<int>(d, "ld_target", 0);
+    g.ep.loss = P<float>(getd<uintptr_t>(d, "loss", 0));
     if ((g.lda % 8) || (g.ldb % 8)) throw std::runtime_error("gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)");
     if (g.ep.out_bf16 && (g.ep.ld_bf16 % 8)) throw std::runtime_error("gemm: ld_bf16 must be a multiple of 8");
     if (g.ep.aux && (g.ep.ld_aux % 8)) throw std::runtime_error("gemm: ld_aux must be a multiple of 8");
@@ -162,24 +166,63 @@ SfPullArgs parse_pull(const py::dict& d) {
 class Plan {
  public:
   using Op = std::function<int(cudaStream_t)>;
-  ~Plan() { reset_graph(); }
+  static constexpr int kMaxBranches = 4;
+  Plan() {
+    for (int i = 0; i < kMaxBranches; ++i) { side_[i] = nullptr; ev_[i] = nullptr; }
+  }
+  ~Plan() {
+    reset_graph();
+    for (int i = 0; i < kMaxBranches; ++i) {
+      if (side_[i]) cudaStreamDestroy(side_[i]);
+      if (ev_[i]) cudaEventDestroy(ev_[i]);
+    }
+    if (ev_main_) cudaEventDestroy(ev_main_);
+  }
+
+  // ops added after branch(b) run on side stream b (0 = the caller's stream)
+  void branch(int b) {
+    if (b < 0 || b >= kMaxBranches) throw std::runtime_error("plan: bad branch id");
+    cur_branch_ = b;
+  }
+  // side stream b waits for everything issued so far on the main stream
+  void fork(int b) { add_ctl(1, b, "fork"); }
+  // the main stream waits for everything issued so far on side stream b
+  void join(int b) { add_ctl(2, b, "join"); }
 
   void add(std::string name, Op op) {
-    names_.push_back(std::move(name));
-    ops_.push_back(std::move(op));
+    items_.push_back(Item{std::move(name), std::move(op), cur_branch_, 0});
     reset_graph();
   }
   void add_gemm(std::shared_ptr<Gemm> g, const std::string& name) {
     add(name, [g](cudaStream_t st) { return sf_gemm_launch(&g->g, st); });
   }
-  size_t size() const { return ops_.size(); }
-  std::vector<std::string> names() const { return names_; }
+  size_t size() const {
+    size_t n = 0;
+    for (auto& it : items_) n += it.kind == 0;
+    return n;
+  }
+  std::vector<std::string> names() const {
+    std::vector<std::string> v;
+    for (auto& it : items_)
+      if (it.kind == 0) v.push_back(it.branch ? it.name + "@" + std::to_string(it.branch) : it.name);
+    return v;
+  }
 
   void run(uintptr_t stream) {
-    cudaStream_t st = S(stream);
-    for (size_t i = 0; i < ops_.size(); ++i) {
-      const int rc = ops_[i](st);
-      if (rc != 0) ck_rc(rc, names_[i].c_str());
+    cudaStream_t main = S(stream);
+    for (auto& it : items_) {
+      if (it.kind == 0) {
+        const int rc = it.op(it.branch ? side(it.branch) : main);
+        if (rc != 0) ck_rc(rc, it.name.c_str());
+      } else if (it.kind == 1) {
+        if (!ev_main_) ck(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming), "cudaEventCreate");
+        ck(cudaEventRecord(ev_main_, main), "cudaEventRecord(fork)");
+        ck(cudaStreamWaitEvent(side(it.branch), ev_main_, 0), "cudaStreamWaitEvent(fork)");
+      } else {
+        if (!ev_[it.branch]) ck(cudaEventCreateWithFlags(&ev_[it.branch], cudaEventDisableTiming), "cudaEventCreate");
+        ck(cudaEventRecord(ev_[it.branch], side(it.branch)), "cudaEventRecord(join)");
+        ck(cudaStreamWaitEvent(main, ev_[it.branch], 0), "cudaStreamWaitEvent(join)");
+      }
     }
   }
   // Capture the op list once; later steps are a single cudaGraphLaunch.
@@ -207,14 +250,37 @@ class Plan {
     if (!exec_) throw std::runtime_error("plan not captured");
     for (int i = 0; i < n; ++i) ck(cudaGraphLaunch(exec_, S(stream)), "cudaGraphLaunch");
   }
+  size_t graph_nodes() const {
+    size_t n = 0;
+    if (graph_) cudaGraphGetNodes(graph_, nullptr, &n);
+    return n;
+  }
 
  private:
+  struct Item {
+    std::string name;
+    Op op;
+    int branch;
+    int kind;   // 0 = kernel op, 1 = fork, 2 = join
+  };
+  void add_ctl(int kind, int b, const char* name) {
+    if (b <= 0 || b >= kMaxBranches) throw std::runtime_error("plan: fork/join need a side branch id in [1,3]");
+    items_.push_back(Item{name, nullptr, b, kind});
+    reset_graph();
+  }
+  cudaStream_t side(int b) {
+    if (!side_[b]) ck(cudaStreamCreateWithFlags(&side_[b], cudaStreamNonBlocking), "cudaStreamCreate(side)");
+    return side_[b];
+  }
   void reset_graph() {
     if (exec_) { cudaGraphExecDestroy(exec_); exec_ = nullptr; }
     if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
   }
-  std::vector<Op> ops_;
-  std::vector<std::string> names_;
+  std::vector<Item> items_;
+  int cur_branch_ = 0;
+  cudaStream_t side_[kMaxBranches];
+  cudaEvent_t ev_[kMaxBranches];
+  cudaEvent_t ev_main_ = nullptr;
   cudaGraph_t graph_ = nullptr;
   cudaGraphExec_t exec_ = nullptr;
 };
@@ -302,6 +368,10 @@ PYBIND11_MODULE(_C, m) {
       .def("captured", &Plan::captured)
       .def("replay", &Plan::replay)
       .def("replay_n", &Plan::replay_n, py::call_guard<py::gil_scoped_release>())
+      .def("branch", &Plan::branch)
+      .def("fork", &Plan::fork)
+      .def("join", &Plan::join)
+      .def("graph_nodes", &Plan::graph_nodes)
       .def("add_gemm", &Plan::add_gemm, py::arg("gemm"), py::arg("name") = "gemm")
       .def("add_cast_transpose",
            [](Plan& p, uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,
@@ -388,6 +458,7 @@ PYBIND11_MODULE(_C, m) {
     ck_rc(sf_lock_test(P<uint32_t>(ctrl), op, S(stream)), "lock_op");
   });
   m.def("gemm_pick_bn", &sf_gemm_pick_bn);
+  m.def("set_pdl", &sf_set_pdl);
   m.def("read_error_code", &sf_read_error_code);
   m.def("pack_segs", &pack_segs);
 

@@ -39,7 +39,15 @@ struct SfGemmEpilogue {
   int accumulate;                 // atomicAdd into out_f32
   int n_store_limit;              // filled by sf_gemm_prepare
   int a_evict_first;
+  // fused loss (last dense layer): the epilogue turns the activation into dL/dz in registers, so
+  // out_bf16 / outT_bf16 / colsum receive dz, dz^T and the bias gradient directly.
+  int loss_mode;                  // 0 none, 1 softmax cross-entropy (N <= 32), 2 mean squared error
+  const float* target;            // [M, ld_target] labels (one-hot / soft) or regression targets
+  int ld_target;
+  float* loss;                    // scalar accumulator (mean loss)
 };
+
+enum SfLossMode { SF_LOSS_NONE = 0, SF_LOSS_SOFTMAX_XENT = 1, SF_LOSS_MSE = 2 };
 
 struct SfGemm {
   CUtensorMap tmA, tmB;           // filled by sf_gemm_prepare
@@ -61,6 +69,7 @@ int sf_gemm_prepare(SfGemm* g);
 int sf_gemm_launch(const SfGemm* g, cudaStream_t st);
 int sf_gemm_pick_bn(int M, int N);
 unsigned int sf_read_error_code();
+void sf_set_pdl(int enabled);
 
 // ---------------------------------------------------------------------------
 // Elementwise / reduction kernels (elementwise.cu)

@@ -327,9 +327,39 @@ __device__ __forceinline__ void multimem_st_u4(uint4* mc_ptr, const uint4& v) {
                : "memory");
 }
 
+// Programmatic dependent launch: the next kernel's prologue (barrier init, TMEM alloc, descriptor
+// prefetch) overlaps this kernel's tail; `pdl_wait` blocks until every prerequisite grid has
+// completed and its memory is visible.  Both are no-ops for launches without the PDL attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Host-side launch helper: every kernel of the step is launched with the programmatic stream
+// serialization attribute (unless disabled), which stream capture turns into programmatic graph edges.
+inline int& pdl_enabled() {
+  static int v = 1;
+  return v;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace sf

@@ -1,0 +1,121 @@
+"""``HogwildSparkModel``: asynchronous parameter-server training over the partitions of an RDD.
+
+Public API parity with /root/reference/sparkflow/HogwildSparkModel.py:103-272 (constructor keywords,
+``train(rdd) -> list of numpy weights``, ``stop_server()``, ``determine_master``, module-level
+``get_server_weights`` / ``put_deltas_to_server``), with the Flask/HTTP/pickle machinery replaced by
+:class:`sparkflow_b200.parallel.session.TrainingSession` (fused NVLink push/pull kernels on B200,
+threads or gloo on CPU).  ``serverStartup`` is accepted and ignored: readiness is explicit, there is
+no start-up sleep.
+"""
+from __future__ import annotations
+
+import random
+import socket
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from .ml_util import handle_features
+from .ops.optimizers import OptimizerSpec
+from .parallel import dist as D
+from .parallel.session import TrainingSession
+
+# live sessions by master url, so the module-level helper functions of the reference keep working
+_SERVERS: Dict[str, "HogwildSparkModel"] = {}
+
+
+def get_server_weights(master_url: str = "localhost:5000") -> List[np.ndarray]:
+    """Current master weights (reference: HTTP GET /parameters, HogwildSparkModel.py:22-28)."""
+    model = _SERVERS.get(master_url) or _SERVERS.get(_port_key(master_url))
+    if model is None:
+        raise ConnectionError(f"no parameter server is running at {master_url}")
+    return model._session.weights()
+
+
+def put_deltas_to_server(delta, master_url: str = "localhost:5000") -> None:
+    """Apply one gradient list as ONE optimizer step on the master (reference: HTTP POST /update)."""
+    model = _SERVERS.get(master_url) or _SERVERS.get(_port_key(master_url))
+    if model is None:
+        raise ConnectionError(f"no parameter server is running at {master_url}")
+    model._session.push_external(delta)
+
+
+def _port_key(url: str) -> str:
+    return ":" + url.rsplit(":", 1)[-1]
+
+
+class HogwildSparkModel(object):
+    """Hogwild! / locked asynchronous SGD: every partition is a worker that pulls the master
+    parameters, computes a gradient on a minibatch and pushes it; the master applies one optimizer
+    step per push without aggregating across workers."""
+
+    def __init__(self, tensorflowGraph=None, iters=1000, tfInput=None, tfLabel=None, optimizer=None, master_url=None,
+                 serverStartup=8, acquire_lock=False, mini_batch=-1, mini_stochastic_iters=-1, shuffle=True, verbose=0,
+                 partition_shuffles=1, loss_callback: Optional[Callable] = None, port=5000, engine="auto", seed=None,
+                 initial_weights=None):
+        self.tensorflowGraph = tensorflowGraph
+        self.iters = iters
+        self.tfInput = tfInput
+        self.tfLabel = tfLabel
+        self.acquire_lock = acquire_lock
+        self.mini_batch = mini_batch
+        self.mini_stochastic_iters = mini_stochastic_iters
+        self.verbose = verbose
+        self.shuffle = shuffle
+        self.partition_shuffles = partition_shuffles
+        self.loss_callback = loss_callback
+        self.port = port
+        self.master_url = master_url if master_url is not None else HogwildSparkModel.determine_master(port)
+        if optimizer is None:
+            optimizer = OptimizerSpec.from_tf_kwargs("gradient_descent", {"learning_rate": 0.01})
+        if not isinstance(optimizer, OptimizerSpec):
+            raise TypeError("optimizer must come from build_optimizer(...) or tf.train.*Optimizer of sparkflow_b200's tf shim")
+        self.optimizer = optimizer
+        self._session = TrainingSession(tensorflowGraph, tfInput, tfLabel, optimizer, acquire_lock=acquire_lock, iters=iters,
+                                        mini_batch=mini_batch, mini_stochastic_iters=mini_stochastic_iters, shuffle=shuffle,
+                                        verbose=verbose, loss_callback=loss_callback, engine=engine, seed=seed,
+                                        initial_weights=initial_weights)
+        self.start_server()
+
+    @staticmethod
+    def determine_master(port):
+        try:
+            return socket.gethostbyname(socket.gethostname()) + ":" + str(port)
+        except Exception:
+            return "localhost:" + str(port)
+
+    def start_server(self, *_ignored):
+        """Bring the master state up (synchronously; returns when it is ready to serve)."""
+        self._session.open()
+        _SERVERS[self.master_url] = self
+        _SERVERS[_port_key(self.master_url)] = self
+        self.server = self._session
+
+    def stop_server(self):
+        """Release the master state. Idempotent."""
+        for k in [k for k, v in _SERVERS.items() if v is self]:
+            _SERVERS.pop(k, None)
+        self._session.close()
+
+    def train(self, rdd):
+        """Run ``partition_shuffles`` rounds of ``iters`` iterations over every partition and return
+        the final master weights as a list of numpy arrays (trainable-variable order)."""
+        try:
+            supervised = self.tfLabel is not None
+            ctx = self._session.ctx
+            for rnd in range(self.partition_shuffles):
+                parts = [handle_features(iter(p), supervised) for p in rdd.partitions()]
+                parts = [(f, l) for f, l in parts if f.shape[0] > 0]
+                self._session.train_partitions(parts)
+                if self.partition_shuffles - rnd > 1:
+                    seed = D.broadcast_object(ctx, random.randrange(1 << 30), src=0)
+                    state = random.getstate()
+                    random.seed(seed)                      # identical repartition on every rank
+                    rdd = rdd.repartition(rdd.getNumPartitions())
+                    random.setstate(state)
+            weights = self._session.weights()
+            self.stop_server()
+            return weights
+        except Exception:
+            self.stop_server()
+            raise

@@ -367,6 +367,23 @@ def _enc_scalar(fn: int, t: str, v: Any) -> bytes:
     return _enc_key(fn, 0) + _enc_varint(int(v))
 
 
+# messages whose scalar fields are members of a oneof: explicit presence, zeros ARE serialised
+_ONEOF_MESSAGES = {"AttrValue"}
+
+
+def _is_default(t: str, v: Any) -> bool:
+    if t in ("string", "bytes"):
+        return v == "" or v == b""
+    if t == "bool":
+        return not v
+    if t.startswith("enum:"):
+        return v == 0 or v == ENUMS[t[5:]].get(0)
+    try:
+        return float(v) == 0.0
+    except (TypeError, ValueError):
+        return False
+
+
 def encode(msg: str, obj: Dict[str, Any]) -> bytes:
     """proto3-JSON-shaped dict -> binary protobuf (fields emitted in field-number order)."""
     schema = S[msg]
@@ -384,6 +401,8 @@ def encode(msg: str, obj: Dict[str, Any]) -> bytes:
                 entry += _enc_key(2, 2) + _enc_varint(len(sub)) + sub
                 out += _enc_key(fn, 2) + _enc_varint(len(entry)) + entry
             continue
+        if not rep and msg not in _ONEOF_MESSAGES and not t.startswith("msg:") and _is_default(t, v):
+            continue                      # proto3: default-valued scalars are not serialised
         vals = v if rep else [v]
         for item in vals:
             if t.startswith("msg:"):

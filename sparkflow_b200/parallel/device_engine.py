@@ -141,10 +141,10 @@ class DeviceWorker:
 
     def __init__(self, ir: GraphIR, tf_input: str, tf_label: Optional[str], spec: OptimizerSpec, master: MasterState,
                  acquire_lock: bool = False, pull_mode: Optional[str] = None, use_graphs: bool = True,
-                 device: Optional[torch.device] = None):
+                 device: Optional[torch.device] = None, plan: Optional[LayerPlan] = None):
         self.C = native.cuda_ext()
         self.ir = ir
-        self.plan: LayerPlan = compile_graph(ir, tf_input, tf_label, None, need_loss=True)
+        self.plan: LayerPlan = plan if plan is not None else compile_graph(ir, tf_input, tf_label, None, need_loss=True)
         if not self.plan.is_mlp():
             raise NotImplementedError("conv plans are built by ConvWorker")
         self.spec, self.master = spec, master
@@ -155,6 +155,9 @@ class DeviceWorker:
         if self.pull_mode == "direct" and self.lock_mode:
             self.pull_mode = "copy"            # a locked pull must be a private snapshot
         self.use_graphs = use_graphs and os.environ.get("SPARKFLOW_NO_GRAPHS") != "1"
+        self.use_branches = os.environ.get("SPARKFLOW_NO_BRANCHES") != "1"
+        self.fuse_loss = os.environ.get("SPARKFLOW_NO_FUSED_LOSS") != "1"
+        self.C.set_pdl(0 if os.environ.get("SPARKFLOW_NO_PDL") == "1" else 1)
         self.stream = torch.cuda.Stream(device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)
         dev = self.device
@@ -174,6 +177,11 @@ class DeviceWorker:
         self._keep: List[object] = []
         self.drop_next = 0
         self.launches_per_step = 0
+
+    @classmethod
+    def for_inference(cls, ir: GraphIR, plan: LayerPlan, spec: OptimizerSpec, master: MasterState) -> "DeviceWorker":
+        """Forward-only worker reading weights straight from ``master`` (no replica, no optimizer)."""
+        return cls(ir, plan.input_name, None, spec, master, acquire_lock=False, pull_mode="direct", use_graphs=False, plan=plan)
 
     # ------------------------------------------------------------------------------------------
     def _weight_src(self) -> torch.Tensor:
@@ -224,40 +232,59 @@ class DeviceWorker:
         wsrc = self._weight_src()
         plan = C.Plan()
         gemms = []
-        if with_pull and self.pull_mode != "direct":
+        branches = self.use_branches
+        do_pull = with_pull and self.pull_mode != "direct"
+        # ---------------- pull || input cast ----------------
+        if do_pull and branches:
+            plan.fork(1)
+            plan.branch(1)
+            plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
+            plan.branch(0)
+        elif do_pull:
             plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
         plan.add_cast_transpose(native.ptr(x_stage), D, 0, native.ptr(acts[0]), acts[0].shape[1], native.ptr(actsT[0]), ldB, B, D)
-        # ---------------- forward ----------------
+        if do_pull and branches:
+            plan.join(1)
+        # ---------------- forward (+ loss fused into the last epilogue) ----------------
+        last_bias = lay.by_name(dense[-1].bias) if dense[-1].bias else None
+        db_ptr = native.ptr(self.grads) + last_bias.offset * 4 if last_bias else 0
+        target = x_stage if lp.target_is_input else y_stage
+        fuse_loss = self.fuse_loss and (lp.loss == "mse" or widths[-1] <= 32)
         for i, l in enumerate(dense):
             ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
             last = i == L - 1
             d = dict(a=native.ptr(acts[i]), lda=acts[i].shape[1], b=native.ptr(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld,
                      M=B, N=ks.cols, K=ks.rows, bias=self._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
-            if last:
+            if last and fuse_loss:
+                d.update(loss_mode=1 if lp.loss == "softmax_xent" else 2, target=native.ptr(target), ld_target=target.shape[1],
+                         loss=native.ptr(self.loss_acc), out_bf16=native.ptr(dz[-1]), ld_bf16=dz[-1].shape[1],
+                         outT_bf16=native.ptr(dzT[-1]), ld_t=ldB, colsum=db_ptr)
+            elif last:
                 d.update(out_f32=native.ptr(out_f32), ld_f32=widths[-1])
             else:
                 d.update(out_bf16=native.ptr(acts[i + 1]), ld_bf16=acts[i + 1].shape[1], outT_bf16=native.ptr(actsT[i + 1]), ld_t=ldB)
             g = C.Gemm(d)
             gemms.append(g)
-            plan.add_gemm(g, f"fwd{i}")
-        # ---------------- loss ----------------
-        last_bias = lay.by_name(dense[-1].bias) if dense[-1].bias else None
-        db_ptr = native.ptr(self.grads) + last_bias.offset * 4 if last_bias else 0
-        target = x_stage if lp.target_is_input else y_stage
-        if lp.loss == "softmax_xent":
-            plan.add_softmax_xent(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], native.ptr(self.loss_acc),
-                                  native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
-        else:
-            plan.add_mse(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], ACT_IDS[dense[-1].act],
-                         native.ptr(self.loss_acc), native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
-        # ---------------- backward ----------------
+            plan.add_gemm(g, f"fwd{i}" + ("+loss" if last and fuse_loss else ""))
+        if not fuse_loss:
+            if lp.loss == "softmax_xent":
+                plan.add_softmax_xent(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], native.ptr(self.loss_acc),
+                                      native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
+            else:
+                plan.add_mse(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], ACT_IDS[dense[-1].act],
+                             native.ptr(self.loss_acc), native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
+        # ---------------- backward: dgrad chain on the main branch, wgrads on a side branch ----------------
         for i in range(L - 1, -1, -1):
             l = dense[i]
             ks = lay.by_name(l.kernel)
             wg = C.Gemm(dict(a=native.ptr(actsT[i]), lda=ldB, b=native.ptr(dzT[i]), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
                              out_f32=native.ptr(self.grads) + ks.offset * 4, ld_f32=ks.cols))
             gemms.append(wg)
+            if branches:
+                plan.fork(2)
+                plan.branch(2)
             plan.add_gemm(wg, f"wgrad{i}")
+            plan.branch(0)
             if i > 0:
                 prev = dense[i - 1]
                 pb = lay.by_name(prev.bias) if prev.bias else None
@@ -268,6 +295,8 @@ class DeviceWorker:
                                  colsum=native.ptr(self.grads) + pb.offset * 4 if pb else 0))
                 gemms.append(dg)
                 plan.add_gemm(dg, f"dgrad{i}")
+        if branches:
+            plan.join(2)
         if with_push:
             plan.add_push(self._push_args(loss_out), native.ptr(self.sync_push), 0)
         self._keep.extend([acts, actsT, out_f32, dz, dzT, gemms])
@@ -396,3 +425,22 @@ def plan_publish_needs(lp: LayerPlan) -> Tuple[Dict[str, bool], Dict[str, bool]]
             need_w[l.kernel] = not first
             first = False
     return need_w, need_wt
+
+
+def external_push(master: MasterState, layout: ParamLayout, spec: OptimizerSpec, grads: Sequence[np.ndarray], acquire_lock: bool) -> None:
+    """Apply one host-provided gradient list through the fused push kernel."""
+    C = native.cuda_ext()
+    dev = master.device
+    with torch.cuda.device(dev):
+        g = torch.from_numpy(layout.flatten(grads)).to(dev)
+        segs = torch.frombuffer(bytearray(C.pack_segs(layout.seg_rows())), dtype=torch.uint8).to(dev)
+        tmap = torch.from_numpy(layout.tile_map()).to(dev)
+        sync = torch.zeros(8, dtype=torch.int32, device=dev)
+        loss = torch.zeros(2, dtype=torch.float32, device=dev)
+        args = dict(p=native.ptr(master.p), s0=native.ptr(master.slots[0]), s1=native.ptr(master.slots[1]),
+                    s2=native.ptr(master.slots[2]), ctrl=native.ptr(master.ctrl), shadow_dst=[native.ptr(master.shadow)],
+                    grad=native.ptr(g), loss_acc=native.ptr(loss), loss_out=native.ptr(loss) + 4, segs=native.ptr(segs),
+                    tile_map=native.ptr(tmap), num_tiles=int(tmap.shape[0]), optimizer=spec.opt_id,
+                    lock_mode=1 if acquire_lock else 0, grad_scale=1.0, hyper=spec.native_hyper())
+        C.push(args, native.ptr(sync), 0, native.current_stream())
+        torch.cuda.synchronize(dev)

@@ -1,0 +1,243 @@
+"""TrainingSession: owns the master state and the workers for one ``HogwildSparkModel.train`` call.
+
+Execution modes (chosen automatically):
+
+=============================  =================================================================
+SPMD + GPUs (torchrun)          one rank per GPU; rank 0's GPU holds the master segment, exported
+                                to the other ranks through CUDA IPC; B200Engine everywhere.
+SPMD, CPU only (gloo)           rank 0 hosts the ParameterServer + GlooServer threads; every rank
+                                (0 included) runs a TorchEngine  (BASELINE.json config 1).
+single process + GPUs           one worker thread per GPU (peer access to the master on cuda:0).
+single process, CPU             worker threads + in-process ParameterServer (Spark local[N] analogue).
+=============================  =================================================================
+
+The reference's fixed costs are gone: no server process spawn, no 8 s sleep
+(/root/reference/sparkflow/HogwildSparkModel.py:118,135) – ``open`` returns once the master is ready.
+"""
+from __future__ import annotations
+
+import os
+import threading
+import warnings
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from ..graph.executor import GraphProgram
+from ..graph.ir import GraphIR
+from ..models.compiler import UnsupportedGraph, compile_graph
+from ..ops.layout import ParamLayout
+from ..ops.optimizers import OptimizerSpec
+from . import dist as D
+from .param_server import GlooServer, GlooTransport, LocalTransport, ParameterServer
+from .worker import B200Engine, Engine, TorchEngine, run_partition
+
+Partition = Tuple[np.ndarray, Optional[np.ndarray]]
+
+
+class TrainingSession:
+    def __init__(self, graph_json: str, tf_input: str, tf_label: Optional[str], optimizer: OptimizerSpec,
+                 acquire_lock: bool = False, iters: int = 1000, mini_batch: int = -1, mini_stochastic_iters: int = -1,
+                 shuffle: bool = True, verbose: int = 0, loss_callback: Optional[Callable] = None, engine: str = "auto",
+                 seed: Optional[int] = None, initial_weights: Optional[Sequence[np.ndarray]] = None,
+                 pull_mode: Optional[str] = None):
+        self.ir = GraphIR.from_metagraph(graph_json)
+        self.tf_input, self.tf_label, self.spec = tf_input, tf_label, optimizer
+        self.acquire_lock, self.iters = bool(acquire_lock), int(iters)
+        self.mini_batch, self.msi, self.shuffle = int(mini_batch), int(mini_stochastic_iters), bool(shuffle)
+        self.verbose, self.loss_callback, self.seed = verbose, loss_callback, seed
+        self.initial_weights = initial_weights
+        self.pull_mode = pull_mode
+        self.ctx = D.get_context()
+        self.use_cuda = torch.cuda.is_available() and engine != "torch" and os.environ.get("SPARKFLOW_ENGINE", "") != "torch"
+        self.engine_kind = "torch"
+        if self.use_cuda:
+            try:
+                lp = compile_graph(self.ir, tf_input, tf_label)
+                if not lp.is_mlp():
+                    raise UnsupportedGraph("conv plans are not compiled yet")
+                self.engine_kind = "b200"
+            except UnsupportedGraph as exc:
+                if engine == "b200":
+                    raise
+                warnings.warn(f"sparkflow_b200: graph is outside the compiled sm_100a plan family ({exc}); "
+                              "running the generic PyTorch interpreter engine on the GPU instead", RuntimeWarning)
+        elif engine == "b200":
+            raise RuntimeError("engine='b200' requested but no CUDA device is available")
+        self.master = None           # MasterState (GPU) or ParameterServer (host)
+        self.gloo_server: Optional[GlooServer] = None
+        self._workers: List[object] = []
+        self._opened = False
+
+    # -------------------------------------------------------------------------------------------
+    def _init_weights(self) -> List[np.ndarray]:
+        if self.initial_weights is not None:
+            return [np.asarray(w, dtype=np.float32) for w in self.initial_weights]
+        return GraphProgram(self.ir).init_weights(seed=self.seed)
+
+    def local_devices(self) -> List[torch.device]:
+        if not self.use_cuda:
+            return [torch.device("cpu")]
+        if self.ctx.world > 1:
+            return [torch.device("cuda", self.ctx.local_rank % torch.cuda.device_count())]
+        return [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
+
+    def open(self) -> "TrainingSession":
+        if self._opened:
+            return self
+        ctx = self.ctx
+        if self.engine_kind == "b200":
+            from .device_engine import MasterState, plan_publish_needs
+
+            lp = compile_graph(self.ir, self.tf_input, self.tf_label)
+            need_w, need_wt = plan_publish_needs(lp)
+            self.layout = ParamLayout.build(self.ir.param_shapes(), need_w, need_wt)
+            dev0 = self.local_devices()[0]
+            if ctx.world > 1:
+                if ctx.is_master:
+                    self.master = MasterState(self.layout, self.spec, dev0)
+                    self.master.load_weights(self._init_weights())
+                    handle = self.master.ipc_handle()
+                else:
+                    handle = None
+                handle = D.broadcast_object(ctx, handle, src=0)
+                if not ctx.is_master:
+                    self.master = MasterState.from_ipc(self.layout, self.spec, dev0, handle)
+                D.barrier(ctx)
+            else:
+                self.master = MasterState(self.layout, self.spec, dev0)
+                self.master.load_weights(self._init_weights())
+                from ..ops import native
+
+                for d in self.local_devices()[1:]:
+                    with torch.cuda.device(d):
+                        if not native.cuda_ext().enable_peer_access(dev0.index):
+                            raise RuntimeError(f"GPU {d.index} cannot access the master on GPU {dev0.index} (no P2P)")
+        else:
+            if ctx.world > 1:
+                if ctx.is_master:
+                    self.master = ParameterServer(self._init_weights(), self.spec, self.acquire_lock, max_errors=max(self.iters, 1))
+                    self.gloo_server = GlooServer(self.master, ctx.world, ctx.control_group)
+                D.barrier(ctx)
+            else:
+                self.master = ParameterServer(self._init_weights(), self.spec, self.acquire_lock, max_errors=max(self.iters, 1))
+        self._opened = True
+        return self
+
+    # -------------------------------------------------------------------------------------------
+    def make_engine(self, device: torch.device, partition_id: str = "") -> Engine:
+        if self.engine_kind == "b200":
+            from .device_engine import DeviceWorker, MasterState
+
+            master = self.master
+            if master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
+                master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base)
+            w = DeviceWorker(self.ir, self.tf_input, self.tf_label, self.spec, master, acquire_lock=self.acquire_lock,
+                             pull_mode=self.pull_mode, device=device)
+            self._workers.append(w)
+            return B200Engine(w)
+        if self.ctx.world > 1 and not self.ctx.is_master:
+            transport = GlooTransport(self.ctx.rank, [v.shape for v in self.ir.trainable], self.ctx.control_group)
+        else:
+            transport = LocalTransport(self.master)
+        eng = TorchEngine(self.ir, self.tf_input, self.tf_label, transport, device=str(device) if device.type == "cuda" else "cpu",
+                          partition_id=partition_id)
+        self._workers.append(eng)
+        return eng
+
+    def train_partitions(self, partitions: Sequence[Partition]) -> None:
+        """Train over ``partitions`` (global list; under SPMD every rank passes the same list and
+        takes the partitions ``i % world == rank``)."""
+        self.open()
+        ctx = self.ctx
+        mine = [(i, p) for i, p in enumerate(partitions) if i % ctx.world == ctx.rank]
+        devices = self.local_devices()
+        lanes: List[List[Tuple[int, Partition]]] = [[] for _ in devices]
+        n_lanes = len(devices) if self.use_cuda else max(1, len(mine))
+        if not self.use_cuda:
+            devices = [torch.device("cpu")] * n_lanes
+            lanes = [[] for _ in range(n_lanes)]
+        for j, item in enumerate(mine):
+            lanes[j % len(lanes)].append(item)
+        errors: List[BaseException] = []
+
+        def run_lane(lane_idx: int) -> None:
+            dev = devices[lane_idx]
+            if dev.type == "cuda":
+                torch.cuda.set_device(dev)
+            for pid, (feat, lab) in lanes[lane_idx]:
+                engine = self.make_engine(dev, partition_id=f"partition-{pid}")
+                run_partition(engine, feat, lab, iters=self.iters, mini_batch_size=self.mini_batch, shuffle=self.shuffle,
+                              mini_stochastic_iters=self.msi, verbose=self.verbose, loss_callback=self.loss_callback,
+                              partition_id=f"partition-{pid}", seed=None if self.seed is None else self.seed + pid)
+                if isinstance(engine, TorchEngine) and isinstance(engine.transport, GlooTransport):
+                    pass
+
+        active = [i for i, l in enumerate(lanes) if l]
+        if len(active) <= 1:
+            for i in active:
+                run_lane(i)
+        else:
+            with ThreadPoolExecutor(max_workers=len(active)) as ex:
+                futs = [ex.submit(run_lane, i) for i in active]
+                for f in futs:
+                    try:
+                        f.result()
+                    except BaseException as exc:  # noqa: BLE001
+                        errors.append(exc)
+        if errors:
+            raise errors[0]
+        D.barrier(ctx)
+
+    # -------------------------------------------------------------------------------------------
+    def weights(self) -> List[np.ndarray]:
+        ctx = self.ctx
+        if self.engine_kind == "b200":
+            for w in self._workers:
+                w.stream.synchronize()
+            D.barrier(ctx)
+            return self.master.weights()
+        if ctx.world > 1:
+            w = self.master.weights() if ctx.is_master else None
+            return D.broadcast_object(ctx, w, src=0)
+        return self.master.weights()
+
+    def push_external(self, grads) -> None:
+        """One optimizer step on the master from an externally computed gradient list."""
+        if self.engine_kind == "b200":
+            from .device_engine import external_push
+
+            external_push(self.master, self.layout, self.spec, [np.asarray(g, dtype=np.float32) for g in grads], self.acquire_lock)
+        else:
+            LocalTransport(self.master).push(grads)
+
+    def counters(self) -> dict:
+        if self.engine_kind == "b200":
+            return self.master.counters()
+        m = self.master
+        if m is None:
+            return {}
+        return {"pushes": m.pushes, "errors": m.errors, "dropped": m.dropped}
+
+    def close(self) -> None:
+        if not self._opened:
+            return
+        ctx = self.ctx
+        for w in self._workers:
+            if isinstance(w, TorchEngine) and isinstance(w.transport, GlooTransport):
+                w.transport.close()
+        D.barrier(ctx)
+        if self.gloo_server is not None:
+            self.gloo_server.join(timeout=10)
+            if self.gloo_server.failure:
+                raise self.gloo_server.failure
+        if self.engine_kind == "b200" and self.master is not None:
+            for w in self._workers:
+                w.stream.synchronize()
+            D.barrier(ctx)
+            self.master.close()
+        self._workers.clear()
+        self.master = None
+        self._opened = False

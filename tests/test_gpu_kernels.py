@@ -320,3 +320,81 @@ def test_plan_capture_replay(C):
         plan.replay(st.cuda_stream)
     st.synchronize()
     assert torch.equal(out, x.to(torch.bfloat16))
+
+
+def test_gemm_fused_softmax_xent_epilogue(C):
+    """Last dense layer + softmax-CE + gradient in one kernel (dz, dz^T, dbias, loss)."""
+    M, N, K = 300, 10, 256
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    y = torch.nn.functional.one_hot(torch.randint(0, N, (M,), device="cuda"), N).float()
+    ldn, ldt = round_up(N, 8), round_up(M, 8)
+    dz = torch.full((M, ldn), 3.0, dtype=torch.bfloat16, device="cuda")
+    dzT = torch.zeros(N, ldt, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    gm = C.Gemm(dict(a=native.ptr(a), b=native.ptr(w), M=M, N=N, K=K, lda=K, ldb=K, bias=native.ptr(bias), loss_mode=1,
+                     target=native.ptr(y), ld_target=N, loss=native.ptr(loss), out_bf16=native.ptr(dz), ld_bf16=ldn,
+                     outT_bf16=native.ptr(dzT), ld_t=ldt, colsum=native.ptr(db)))
+    gm.launch(native.current_stream())
+    torch.cuda.synchronize()
+    z = (a.float() @ w.float().t() + bias).requires_grad_(True)
+    ref = -(y * torch.log_softmax(z, 1)).sum(1).mean()
+    ref.backward()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(dz[:, :N].float(), z.grad, rtol=2e-2, atol=2e-5)
+    torch.testing.assert_close(dzT[:, :M].float().t(), z.grad, rtol=2e-2, atol=2e-5)
+    assert torch.all(dz[:, N:] == 0)
+    torch.testing.assert_close(db, z.grad.sum(0), rtol=1e-2, atol=1e-5)
+
+
+@pytest.mark.parametrize("act", [None, "sigmoid"])
+def test_gemm_fused_mse_epilogue(C, act):
+    M, N, K = 256, 784, 256
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g) * 0.1
+    tgt = torch.rand(M, N, device="cuda", generator=g)
+    ldn, ldt = round_up(N, 8), round_up(M, 8)
+    dz = torch.zeros(M, ldn, dtype=torch.bfloat16, device="cuda")
+    dzT = torch.zeros(N, ldt, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    gm = C.Gemm(dict(a=native.ptr(a), b=native.ptr(w), M=M, N=N, K=K, lda=K, ldb=K, bias=native.ptr(bias), act=ACT[act],
+                     loss_mode=2, target=native.ptr(tgt), ld_target=N, loss=native.ptr(loss), out_bf16=native.ptr(dz),
+                     ld_bf16=ldn, outT_bf16=native.ptr(dzT), ld_t=ldt, colsum=native.ptr(db)))
+    gm.launch(native.current_stream())
+    torch.cuda.synchronize()
+    z = (a.float() @ w.float().t() + bias).requires_grad_(True)
+    ref = ((_act(z, act) - tgt) ** 2).mean()
+    ref.backward()
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-3, atol=1e-6)
+    torch.testing.assert_close(dz[:, :N].float(), z.grad, rtol=2e-2, atol=1e-7)
+    torch.testing.assert_close(dzT[:, :M].float().t(), z.grad, rtol=2e-2, atol=1e-7)
+    torch.testing.assert_close(db, z.grad.sum(0), rtol=1e-2, atol=1e-6)
+
+
+def test_plan_branches_fork_join(C):
+    x = torch.randn(64, 32, device="cuda")
+    a = torch.zeros(64, 32, dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros(64, 32, dtype=torch.bfloat16, device="cuda")
+    plan = C.Plan()
+    plan.fork(1)
+    plan.branch(1)
+    plan.add_cast_transpose(native.ptr(x), 32, 0, native.ptr(a), 32, 0, 0, 64, 32)
+    plan.branch(0)
+    plan.add_cast_transpose(native.ptr(x), 32, 0, native.ptr(b), 32, 0, 0, 64, 32)
+    plan.join(1)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        plan.run(st.cuda_stream)
+        st.synchronize()
+        plan.capture(st.cuda_stream)
+        a.zero_(); b.zero_()
+        plan.replay(st.cuda_stream)
+    st.synchronize()
+    assert torch.equal(a, x.to(torch.bfloat16)) and torch.equal(b, x.to(torch.bfloat16))
+    assert plan.graph_nodes() >= 2 and plan.names() == ["cast_transpose@1", "cast_transpose"]

@@ -88,6 +88,13 @@ def bench_step(name, tf_in, tf_lab, B, lock, pull_mode, steps=200):
 if __name__ == "__main__":
     C = native.cuda_ext()
     out = {"gemm": [], "step": []}
+    if "--step-only" in sys.argv:
+        tag = sys.argv[sys.argv.index("--tag") + 1] if "--tag" in sys.argv else "step"
+        lock = "--lock" in sys.argv
+        r = bench_step("simple_dnn", "x:0", "y:0", 300, lock, "copy", steps=300)
+        r["tag"] = tag
+        print(json.dumps(r), flush=True)
+        sys.exit(0)
     for shp in [(300, 256, 784), (300, 256, 256), (300, 10, 256), (784, 256, 300), (256, 256, 300), (4096, 4096, 4096),
                 (8192, 8192, 8192), (4096, 1000, 4096), (1024, 4096, 4096)]:
         out["gemm"].append(bench_gemm(C, *shp))
