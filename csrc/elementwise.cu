@@ -37,8 +37,10 @@ cast_transpose_kernel(const float* __restrict__ in, int ld_in, const int32_t* __
                       __nv_bfloat16* __restrict__ out, int ld_out, __nv_bfloat16* __restrict__ outT,
                       int ld_t, int rows, int cols) {
   __shared__ float tile[32][33];
+  TraceScope trace;
   pdl_launch_dependents();
   pdl_wait();
+  trace.mark();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
 #pragma unroll
@@ -52,7 +54,10 @@ cast_transpose_kernel(const float* __restrict__ in, int ld_in, const int32_t* __
     tile[ty + 8 * i][tx] = v;
     if (out != nullptr && r < rows && c < ld_out) out[static_cast<size_t>(r) * ld_out + c] = __float2bfloat16(v);
   }
-  if (outT == nullptr) return;
+  if (outT == nullptr) {
+    trace.end(KID_CAST);
+    return;
+  }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -60,6 +65,7 @@ cast_transpose_kernel(const float* __restrict__ in, int ld_in, const int32_t* __
     if (c < cols && r < ld_t)
       outT[static_cast<size_t>(c) * ld_t + r] = __float2bfloat16(r < rows ? tile[tx][ty + 8 * i] : 0.f);
   }
+  trace.end(KID_CAST);
 }
 
 // ---------------------------------------------------------------------------
@@ -74,8 +80,10 @@ softmax_xent_kernel(const float* __restrict__ logits, int ld_logits, const float
                     __nv_bfloat16* __restrict__ dzT, int ld_t, float* __restrict__ dbias, int rows,
                     int cols) {
   extern __shared__ float s_db[];   // [cols]
+  TraceScope trace;
   pdl_launch_dependents();
   pdl_wait();
+  trace.mark();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   for (int c = threadIdx.x; c < cols; c += blockDim.x) s_db[c] = 0.f;
@@ -117,6 +125,7 @@ softmax_xent_kernel(const float* __restrict__ logits, int ld_logits, const float
   if (dbias)
     for (int c = threadIdx.x; c < cols; c += blockDim.x)
       if (s_db[c] != 0.f) atomicAdd(dbias + c, s_db[c]);
+  trace.end(KID_SOFTMAX);
 }
 
 // ---------------------------------------------------------------------------
@@ -129,8 +138,10 @@ mse_kernel(const float* __restrict__ out, int ld_out, const float* __restrict__ 
   __shared__ float tile[32][33];
   __shared__ float s_col[32];
   __shared__ float s_loss[8];
+  TraceScope trace;
   pdl_launch_dependents();
   pdl_wait();
+  trace.mark();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   if (threadIdx.x < 32) s_col[threadIdx.x] = 0.f;
@@ -170,12 +181,15 @@ mse_kernel(const float* __restrict__ out, int ld_out, const float* __restrict__ 
       if (c < cols && r < rows) dzT[static_cast<size_t>(c) * ld_t + r] = __float2bfloat16(tile[tx][ty + 8 * i]);
     }
   }
+  trace.end(KID_MSE);
 }
 
 __global__ void __launch_bounds__(256)
 argmax_rows_kernel(const float* __restrict__ in, int ld, float* __restrict__ out, int rows, int cols) {
+  TraceScope trace;
   pdl_launch_dependents();
   pdl_wait();
+  trace.mark();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= rows) return;
   const float* z = in + static_cast<size_t>(warp) * ld;
@@ -192,6 +206,7 @@ argmax_rows_kernel(const float* __restrict__ in, int ld, float* __restrict__ out
     if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
   }
   if (lane == 0) out[warp] = static_cast<float>(bi);
+  trace.end(KID_ARGMAX);
 }
 
 }  // namespace sf

@@ -73,6 +73,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + S::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
+  TraceScope trace;
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -100,6 +101,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();      // everything above overlapped the previous kernel; global memory is touched below
+  trace.mark();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -123,10 +125,13 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kBM, BN);
+      const bool tr = g_trace_buf != nullptr;
+      unsigned long long tm0 = tr ? trace_now() : 0, tm1 = 0;
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % S::kStages;
         const uint32_t ph = (i / S::kStages) & 1;
         mbar_wait(&full_bar[s], ph, 0x200 + s);
+        if (tr && i == 0) tm1 = trace_now();
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(stage_base + s * S::kStageBytes);
         const uint32_t b_addr = a_addr + S::kABytes;
@@ -140,12 +145,19 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&empty_bar[s]);      // smem slot reusable once these MMAs retire
       }
       umma_commit(tmem_full_bar);        // accumulator complete
+      if (tr) {                           // phase record: role start / first operands landed / last MMA issued
+        const unsigned int i = atomicAdd(&g_trace_n, 1u);
+        if (i < g_trace_cap) g_trace_buf[i] = TraceRec{tm0, tm1, trace_now(), 101u, blockIdx.x + gridDim.x * blockIdx.y};
+      }
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int e = warp - 4;              // == warp % 4 -> TMEM lane quarter this warp may touch
+    const bool tr = g_trace_buf != nullptr && e == 0 && lane == 0;
+    const unsigned long long te0 = tr ? trace_now() : 0;
     mbar_wait(tmem_full_bar, 0, 0x300);
     tc_fence_after_sync();
+    const unsigned long long te1 = tr ? trace_now() : 0;
     const int row = m0 + e * 32 + lane;
     const bool row_ok = row < M;
     const bool is_split0 = (blockIdx.z == 0);
@@ -295,6 +307,10 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ep.outT_bf16[static_cast<size_t>(col0 + j) * ep.ld_t + row] = __float2bfloat16(f[j]);
       }
     }
+    if (tr) {                             // phase record: wait start / accumulator ready / epilogue done
+      const unsigned int i = atomicAdd(&g_trace_n, 1u);
+      if (i < g_trace_cap) g_trace_buf[i] = TraceRec{te0, te1, trace_now(), 102u, blockIdx.x + gridDim.x * blockIdx.y};
+    }
     tc_fence_before_sync();
   }
 
@@ -303,6 +319,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after_sync();
     tmem_dealloc<S::kTmemCols>(tmem_base);
   }
+  trace.end(KID_GEMM);
 }
 
 // ---------------------------------------------------------------------------
@@ -409,6 +426,21 @@ extern "C" int sf_gemm_launch(const SfGemm* g, cudaStream_t st) {
 }
 
 extern "C" void sf_set_pdl(int enabled) { sf::pdl_enabled() = enabled ? 1 : 0; }
+
+// tracing: `buf` is a device buffer of `cap` 32-byte records (or nullptr to disable)
+extern "C" int sf_trace_enable(void* buf, unsigned int cap) {
+  sf::TraceRec* b = static_cast<sf::TraceRec*>(buf);
+  unsigned int zero = 0;
+  cudaError_t e = cudaMemcpyToSymbol(sf::g_trace_buf, &b, sizeof(b));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(sf::g_trace_cap, &cap, sizeof(cap));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(sf::g_trace_n, &zero, sizeof(zero));
+  return static_cast<int>(e);
+}
+extern "C" unsigned int sf_trace_count() {
+  unsigned int n = 0;
+  cudaMemcpyFromSymbol(&n, sf::g_trace_n, sizeof(n));
+  return n;
+}
 
 extern "C" unsigned int sf_read_error_code() {
   unsigned int v = 0;

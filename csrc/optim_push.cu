@@ -178,8 +178,10 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_t;
   __shared__ uint32_t s_epoch;
   __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
+  TraceScope trace;
   pdl_launch_dependents();
   pdl_wait();
+  trace.mark();
   const int tid = threadIdx.x;
   constexpr int NS = Slots<OPT>::n;
 
@@ -335,6 +337,7 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       }
     }
   }
+  trace.end(KID_PUSH);
 }
 
 // ---------------------------------------------------------------------------
@@ -343,8 +346,10 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
 __global__ void __launch_bounds__(256, 1)
 pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_epoch;
+  TraceScope trace;
   pdl_launch_dependents();
   pdl_wait();
+  trace.mark();
   const int tid = threadIdx.x;
   if (a.lock_mode == SF_LOCK_RW) {
     if (tid == 0) {
@@ -398,6 +403,7 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
       }
     }
   }
+  trace.end(KID_PULL);
 }
 
 // single-thread lock exerciser used by the GPU tests (op: 0 = acquire_read, 1 = release_read,

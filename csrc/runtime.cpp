@@ -459,6 +459,9 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("gemm_pick_bn", &sf_gemm_pick_bn);
   m.def("set_pdl", &sf_set_pdl);
+  m.def("trace_enable", [](uintptr_t buf, unsigned int cap) { ck_rc(sf_trace_enable(P<void>(buf), cap), "trace_enable"); });
+  m.def("trace_count", &sf_trace_count);
+  m.attr("TRACE_REC_BYTES") = 32;
   m.def("read_error_code", &sf_read_error_code);
   m.def("pack_segs", &pack_segs);
 

@@ -70,6 +70,8 @@ int sf_gemm_launch(const SfGemm* g, cudaStream_t st);
 int sf_gemm_pick_bn(int M, int N);
 unsigned int sf_read_error_code();
 void sf_set_pdl(int enabled);
+int sf_trace_enable(void* buf, unsigned int cap);
+unsigned int sf_trace_count();
 
 // ---------------------------------------------------------------------------
 // Elementwise / reduction kernels (elementwise.cu)

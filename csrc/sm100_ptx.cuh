@@ -26,6 +26,49 @@ __device__ __forceinline__ void sf_fail(unsigned int code) {
   asm volatile("trap;");
 }
 
+// ---------------------------------------------------------------------------
+// Device-side timeline tracer: when enabled, thread 0 of every CTA appends
+// (kernel id, block, t_entry, t_after_pdl_wait, t_exit) in %globaltimer ns.
+// ---------------------------------------------------------------------------
+struct TraceRec {
+  unsigned long long t0, t1, t2;
+  unsigned int kernel_id, block;
+};
+__device__ TraceRec* g_trace_buf = nullptr;
+__device__ unsigned int g_trace_cap = 0;
+__device__ unsigned int g_trace_n = 0;
+
+enum KernelId { KID_GEMM = 1, KID_CAST = 2, KID_SOFTMAX = 3, KID_MSE = 4, KID_ARGMAX = 5, KID_PUSH = 6, KID_PULL = 7,
+                KID_IM2COL = 8, KID_COL2IM = 9, KID_POOL_FWD = 10, KID_POOL_BWD = 11 };
+
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long t0, t1;
+  bool on;
+  __device__ __forceinline__ TraceScope() : t0(0), t1(0), on(false) {
+    if (threadIdx.x == 0 && g_trace_buf != nullptr) {
+      on = true;
+      t0 = trace_now();
+    }
+  }
+  __device__ __forceinline__ void mark() {
+    if (on) t1 = trace_now();
+  }
+  __device__ __forceinline__ void end(unsigned int kid) {
+    if (on) {
+      const unsigned int i = atomicAdd(&g_trace_n, 1u);
+      if (i < g_trace_cap) {
+        const unsigned int b = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        g_trace_buf[i] = TraceRec{t0, t1, trace_now(), kid, b};
+      }
+    }
+  }
+};
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

