@@ -95,9 +95,12 @@ def run_ours(args, ctx) -> dict:
     n_batches = rows // BATCH
 
     def e2e_steps(n, start):
-        for k in range(n):
-            r = ((start + k) % n_batches) * BATCH
-            eng.train(slice(r, r + BATCH), pull=True)
+        starts = [((start + k) % n_batches) * BATCH for k in range(n)]
+        if args.python_loop:
+            for r in starts:
+                eng.train(slice(r, r + BATCH), pull=True)
+        else:
+            eng.train_contiguous(starts, BATCH, pull=True)       # native StepDriver: H2D + graph replay + loss D2H per step
 
     # ---------------- e2e: public engine API, H2D of every minibatch + D2H of every loss ----------------
     e2e_steps(W, 0)
@@ -238,6 +241,7 @@ def main() -> int:
     ap.add_argument("--pull-mode", default=None, choices=[None, "copy", "direct"])
     ap.add_argument("--partition-rows", type=int, default=50_100, help="rows of the pinned per-rank partition (157 MiB > L2)")
     ap.add_argument("--with-nccl-baseline", action="store_true", help="also time the NCCL baseline in the same launch")
+    ap.add_argument("--python-loop", action="store_true", help="drive the e2e steps from Python instead of the native StepDriver")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -55,8 +55,9 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  // + barriers (full, empty per stage, tmem_full) + tmem slot, + 1024 alignment slack
-  static constexpr int kBytes = kStages * kStageBytes + 1024 + 256;
+  // + barriers (full, empty per stage, tmem_full) + tmem slot (256 B) + bias tile (BN floats) + 1024 alignment slack
+  static constexpr int kBarBytes = 256;
+  static constexpr int kBytes = kStages * kStageBytes + kBarBytes + BN * 4 + 1024;
 };
 
 template <int BN>
@@ -72,6 +73,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tmem_full_bar = empty_bar + S::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kBarBytes);
 
   TraceScope trace;
   pdl_launch_dependents();
@@ -155,12 +157,32 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int e = warp - 4;              // == warp % 4 -> TMEM lane quarter this warp may touch
     const bool tr = g_trace_buf != nullptr && e == 0 && lane == 0;
     const unsigned long long te0 = tr ? trace_now() : 0;
-    mbar_wait(tmem_full_bar, 0, 0x300);
-    tc_fence_after_sync();
-    const unsigned long long te1 = tr ? trace_now() : 0;
     const int row = m0 + e * 32 + lane;
     const bool row_ok = row < M;
     const bool is_split0 = (blockIdx.z == 0);
+    // ---- everything that does not depend on the accumulator is fetched while the main loop runs ----
+    {
+      const int et = threadIdx.x - 128;                        // 0..127
+      for (int j = et; j < BN; j += 128)
+        s_bias[j] = (ep.bias != nullptr && is_split0 && n0 + j < N) ? ep.bias[n0 + j] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");           // epilogue warps only
+    }
+    uint4 aux0[4] = {};
+    if (ep.aux != nullptr && row_ok) {
+      const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + n0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (n0 + g * 8 < ep.ld_aux) aux0[g] = *reinterpret_cast<const uint4*>(ap + g * 8);
+    }
+    float tgt0[32];
+    if (ep.loss_mode != SF_LOSS_NONE) {
+      const float* tp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target + n0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tgt0[j] = (row_ok && n0 + j < N) ? tp[j] : 0.f;
+    }
+    mbar_wait(tmem_full_bar, 0, 0x300);
+    tc_fence_after_sync();
+    const unsigned long long te1 = tr ? trace_now() : 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
@@ -170,27 +192,18 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (col0 >= ep.n_store_limit) break;   // whole chunk outside every output pitch
       float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha;
-
-      if (ep.bias != nullptr && is_split0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N) f[j] += ep.bias[col0 + j];   // may be peer memory: plain load
-      }
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha + s_bias[c * 32 + j];
       if (ep.act != SF_ACT_NONE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
       }
       if (ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
         // whole row lives in this thread (host guarantees N <= 32): softmax + CE + gradient in registers
-        float ysum = 0.f, zy = 0.f, mx = -INFINITY, yv[32];
-        const float* yp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target;
+        float ysum = 0.f, zy = 0.f, mx = -INFINITY;
+        float* yv = tgt0;                                   // N <= 32: the single chunk was prefetched
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool ok = row_ok && (col0 + j < N);
-          yv[j] = ok ? yp[col0 + j] : 0.f;
-          if (ok) mx = fmaxf(mx, f[j]);
-        }
+        for (int j = 0; j < 32; ++j)
+          if (row_ok && col0 + j < N) mx = fmaxf(mx, f[j]);
         float se = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -216,7 +229,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           if (row_ok && col0 + j < N) {
-            const float d = f[j] - tp[j];
+            const float d = f[j] - (c == 0 ? tgt0[j] : tp[j]);
             lrow += d * d;
             f[j] = d * scale * act_bwd_from_out(f[j], ep.act);
           } else {
@@ -232,7 +245,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (col0 + g * 8 < ep.ld_aux) {
-            const uint4 q = *reinterpret_cast<const uint4*>(ap + g * 8);
+            const uint4 q = (c == 0) ? aux0[g] : *reinterpret_cast<const uint4*>(ap + g * 8);
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {

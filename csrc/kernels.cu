@@ -2,3 +2,4 @@
 #include "gemm_sm100.cu"
 #include "elementwise.cu"
 #include "optim_push.cu"
+#include "conv.cu"

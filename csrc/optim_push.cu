@@ -30,38 +30,72 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
   return t;
 }
 
-// ---- writer-priority readers/writer lock on one 32-bit word (system scope, works over NVLink)
-__device__ void rw_acquire_write(uint32_t* lock) {
-  atom_add_acqrel_sys(lock, kLockWaitOne);                 // announce: blocks new readers
+// ---- writer-priority readers/writer lock on one 32-bit word -------------------------------------
+// Scope: .sys when more than one GPU shares the master (NVLink peers), .gpu for a single-GPU world
+// (every participant must use the same scope for the operations to be morally strong).
+// Uncontended acquires are ONE atomic round trip (optimistic add / cas); the slow paths keep the
+// writer-priority contract of the reference lock: a waiting writer blocks new readers.
+template <bool SYS> __device__ __forceinline__ uint32_t lk_ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  if (SYS) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+template <bool SYS> __device__ __forceinline__ uint32_t lk_add_acquire(uint32_t* p, uint32_t x) {
+  uint32_t old;
+  if (SYS) asm volatile("atom.acquire.sys.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  else asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  return old;
+}
+template <bool SYS> __device__ __forceinline__ uint32_t lk_add_release(uint32_t* p, uint32_t x) {
+  uint32_t old;
+  if (SYS) asm volatile("atom.release.sys.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  else asm volatile("atom.release.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  return old;
+}
+template <bool SYS> __device__ __forceinline__ uint32_t lk_add_relaxed(uint32_t* p, uint32_t x) {
+  uint32_t old;
+  if (SYS) asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  else asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+  return old;
+}
+template <bool SYS> __device__ __forceinline__ uint32_t lk_cas_acquire(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  if (SYS) asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  else asm volatile("atom.acquire.gpu.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+
+template <bool SYS> __device__ void rw_acquire_write(uint32_t* lock) {
+  if (lk_cas_acquire<SYS>(lock, 0u, kLockWriter) == 0u) return;          // uncontended: one round trip
+  lk_add_relaxed<SYS>(lock, kLockWaitOne);                               // announce: blocks new readers
   const unsigned long long t0 = gtime_ns();
   while (true) {
-    const uint32_t v = ld_acquire_sys(lock);
+    const uint32_t v = lk_ld_acquire<SYS>(lock);
     if ((v & (kLockReaders | kLockWriter)) == 0) {
-      if (atom_cas_acqrel_sys(lock, v, v - kLockWaitOne + kLockWriter) == v) return;
+      if (lk_cas_acquire<SYS>(lock, v, v - kLockWaitOne + kLockWriter) == v) return;
     } else {
-      __nanosleep(64);
+      __nanosleep(32);
     }
     if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x401);
   }
 }
-__device__ void rw_release_write(uint32_t* lock) {
-  atom_add_acqrel_sys(lock, 0u - kLockWriter);
-}
-__device__ void rw_acquire_read(uint32_t* lock) {
+template <bool SYS> __device__ void rw_release_write(uint32_t* lock) { lk_add_release<SYS>(lock, 0u - kLockWriter); }
+template <bool SYS> __device__ void rw_acquire_read(uint32_t* lock) {
   const unsigned long long t0 = gtime_ns();
   while (true) {
-    const uint32_t v = ld_acquire_sys(lock);
-    if ((v & kLockWriter) == 0 && (v >> 17) == 0) {        // no writer active, none waiting
-      if (atom_cas_acqrel_sys(lock, v, v + 1) == v) return;
-    } else {
-      __nanosleep(64);
+    const uint32_t old = lk_add_acquire<SYS>(lock, 1u);                 // optimistic: register as a reader
+    if ((old & kLockWriter) == 0 && (old >> 17) == 0) return;            // no writer active, none waiting
+    lk_add_relaxed<SYS>(lock, 0u - 1u);                                  // back out and wait our turn
+    while (true) {
+      const uint32_t v = lk_ld_acquire<SYS>(lock);
+      if ((v & kLockWriter) == 0 && (v >> 17) == 0) break;
+      __nanosleep(32);
+      if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x402);
     }
-    if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x402);
   }
 }
-__device__ void rw_release_read(uint32_t* lock) {
-  atom_add_acqrel_sys(lock, 0u - 1u);
-}
+template <bool SYS> __device__ void rw_release_read(uint32_t* lock) { lk_add_release<SYS>(lock, 0u - 1u); }
 
 // ---- in-grid coordination on the worker's own memory --------------------------------------
 // local_sync words: 0 = grant epoch, 1 = granted value (optimizer step t), 2 = done counter,
@@ -153,6 +187,17 @@ template <> struct Slots<SF_OPT_ADAGRAD_DA> { static constexpr int n = 2; };
 template <> struct Slots<SF_OPT_FTRL> { static constexpr int n = 2; };
 template <> struct Slots<SF_OPT_PROXIMAL_ADAGRAD> { static constexpr int n = 1; };
 
+// weak (non-atomic) 16-byte streaming accesses: L1 is invalidated at launch boundaries and every element is
+// touched once per kernel, so no stronger ordering than the end-of-push release is needed.
+__device__ __forceinline__ float4 ld_weak_f4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_weak_f4(float* p, float a, float b, float c, float d) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 constexpr int kTileR = 32;
 constexpr int kTileC = 64;
 constexpr int kPushThreads = 256;
@@ -163,16 +208,16 @@ __device__ __forceinline__ void st_shadow8(__nv_bfloat16* dst, uint2 q, bool mc)
                  "f"(__uint_as_float(q.x)), "f"(__uint_as_float(q.y))
                  : "memory");
   } else {
-    asm volatile("st.global.relaxed.sys.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(q.x),
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(q.x),
                  "r"(q.y)
                  : "memory");
   }
 }
 __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc) {
   if (mc) multimem_st_u4(reinterpret_cast<uint4*>(dst), q);
-  else st_stream_u4(reinterpret_cast<uint4*>(dst), q);
+  else asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
 }
-template <int OPT>
+template <int OPT, bool SYS>
 __global__ void __launch_bounds__(kPushThreads, 1)
 push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_t;
@@ -184,17 +229,17 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   trace.mark();
   const int tid = threadIdx.x;
   constexpr int NS = Slots<OPT>::n;
+  const bool locked = a.lock_mode == SF_LOCK_RW;
 
   // ---------------- acquire / step number ----------------
   if (tid == 0) {
     uint32_t t;
-    if (a.lock_mode == SF_LOCK_RW) {
+    if (locked) {
       const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
       if (blockIdx.x == 0) {
-        rw_acquire_write(a.ctrl + SF_CTRL_LOCK);
+        rw_acquire_write<SYS>(a.ctrl + SF_CTRL_LOCK);
         t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
         local_sync[1] = t;
-        __threadfence();
         st_release_gpu(local_sync + 0, epoch + 1);
       } else {
         const unsigned long long t0 = gtime_ns();
@@ -204,19 +249,10 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
         t = local_sync[1];
       }
       s_epoch = epoch;
-    } else {
-      // Hogwild: read the step count racily, exactly like unlocked TF beta-power variables
-      t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
-      s_epoch = 0;
+      s_t = t;
     }
-    s_t = t;
   }
-  __syncthreads();
-  const float t = static_cast<float>(s_t);
-  float lr_t = a.h.lr;
-  if constexpr (OPT == SF_OPT_ADAM) {
-    lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
-  }
+  if (locked) __syncthreads();      // Hogwild: nothing to wait for, loads below start immediately
   const bool mc = a.shadow_is_mc != 0;
 
   // ---------------- tiles ----------------
@@ -228,64 +264,85 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
     const bool vec = ((sg.cols & 3) == 0) && ((sg.offset & 3) == 0);
     const int tx = tid & 15, ty = tid >> 4;
     const int c = c0 + tx * 4;
+    // ---- phase 1: issue every load of both half-rows before anything depends on them ----
+    float g[2][4], p[2][4], x0[2][4], x1[2][4], x2[2][4];
+    int nv[2];
+    int64_t e[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = r0 + ty + 16 * half;
+      nv[half] = (r < sg.rows && c < sg.cols) ? ((sg.cols - c) >= 4 ? 4 : (sg.cols - c)) : 0;
+      e[half] = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { g[half][j] = 0.f; p[half][j] = 0.f; x0[half][j] = 0.f; x1[half][j] = 0.f; x2[half][j] = 0.f; }
+      if (nv[half] == 0) continue;
+      if (vec) {
+        const float4 gv = *reinterpret_cast<const float4*>(a.grad + e[half]);
+        g[half][0] = gv.x; g[half][1] = gv.y; g[half][2] = gv.z; g[half][3] = gv.w;
+        if (!a.drop) {
+          const float4 pv = ld_weak_f4(a.p + e[half]);
+          p[half][0] = pv.x; p[half][1] = pv.y; p[half][2] = pv.z; p[half][3] = pv.w;
+          if constexpr (NS >= 1) { const float4 q = ld_weak_f4(a.s0 + e[half]); x0[half][0] = q.x; x0[half][1] = q.y; x0[half][2] = q.z; x0[half][3] = q.w; }
+          if constexpr (NS >= 2) { const float4 q = ld_weak_f4(a.s1 + e[half]); x1[half][0] = q.x; x1[half][1] = q.y; x1[half][2] = q.z; x1[half][3] = q.w; }
+          if constexpr (NS >= 3) { const float4 q = ld_weak_f4(a.s2 + e[half]); x2[half][0] = q.x; x2[half][1] = q.y; x2[half][2] = q.z; x2[half][3] = q.w; }
+        }
+      } else {
+        for (int j = 0; j < nv[half]; ++j) {
+          g[half][j] = a.grad[e[half] + j];
+          if (!a.drop) {
+            p[half][j] = a.p[e[half] + j];
+            if constexpr (NS >= 1) x0[half][j] = a.s0[e[half] + j];
+            if constexpr (NS >= 2) x1[half][j] = a.s1[e[half] + j];
+            if constexpr (NS >= 3) x2[half][j] = a.s2[e[half] + j];
+          }
+        }
+      }
+    }
+    // ---- step number: under the lock it was granted above; Hogwild reads it racily (like unlocked TF
+    //      beta-power variables) while the loads are in flight ----
+    if (!locked && tile == static_cast<int>(blockIdx.x)) {
+      if (tid == 0) s_t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
+      __syncthreads();
+    }
+    const float t = static_cast<float>(s_t);
+    float lr_t = a.h.lr;
+    if constexpr (OPT == SF_OPT_ADAM) {
+      lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
+    }
+    // ---- phase 2: update + stores ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int rl = ty + 16 * half;
       const int r = r0 + rl;
       float w[4] = {0.f, 0.f, 0.f, 0.f};
-      if (r < sg.rows && c < sg.cols) {
-        const int64_t e = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
-        const int nv = (sg.cols - c) >= 4 ? 4 : (sg.cols - c);
-        float g[4] = {0, 0, 0, 0}, p[4] = {0, 0, 0, 0}, x0[4] = {0, 0, 0, 0}, x1[4] = {0, 0, 0, 0},
-              x2[4] = {0, 0, 0, 0};
-        if (vec) {
-          const float4 gv = *reinterpret_cast<const float4*>(a.grad + e);
-          g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
-          *reinterpret_cast<float4*>(a.grad + e) = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!a.drop) {
-            const float4 pv = ld_stream_f4(reinterpret_cast<const float4*>(a.p + e));
-            p[0] = pv.x; p[1] = pv.y; p[2] = pv.z; p[3] = pv.w;
-            if constexpr (NS >= 1) { const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(a.s0 + e)); x0[0] = q.x; x0[1] = q.y; x0[2] = q.z; x0[3] = q.w; }
-            if constexpr (NS >= 2) { const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(a.s1 + e)); x1[0] = q.x; x1[1] = q.y; x1[2] = q.z; x1[3] = q.w; }
-            if constexpr (NS >= 3) { const float4 q = ld_stream_f4(reinterpret_cast<const float4*>(a.s2 + e)); x2[0] = q.x; x2[1] = q.y; x2[2] = q.z; x2[3] = q.w; }
-          }
-        } else {
-          for (int j = 0; j < nv; ++j) {
-            g[j] = a.grad[e + j];
-            a.grad[e + j] = 0.f;
-            if (!a.drop) {
-              p[j] = a.p[e + j];
-              if constexpr (NS >= 1) x0[j] = a.s0[e + j];
-              if constexpr (NS >= 2) x1[j] = a.s1[e + j];
-              if constexpr (NS >= 3) x2[j] = a.s2[e + j];
-            }
-          }
-        }
+      if (nv[half] > 0) {
+        // the gradient is consumed: zero it for the next step's accumulating epilogues
+        if (vec) *reinterpret_cast<float4*>(a.grad + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else for (int j = 0; j < nv[half]; ++j) a.grad[e[half] + j] = 0.f;
         if (!a.drop) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            Upd u{p[j], x0[j], x1[j], x2[j]};
-            apply_rule<OPT>(u, g[j] * a.grad_scale, a.h, t, lr_t);
-            p[j] = u.p; x0[j] = u.s0; x1[j] = u.s1; x2[j] = u.s2;
-            w[j] = (j < nv) ? u.p : 0.f;      // lanes past the row end are padding: exact zeros
+            Upd u{p[half][j], x0[half][j], x1[half][j], x2[half][j]};
+            apply_rule<OPT>(u, g[half][j] * a.grad_scale, a.h, t, lr_t);
+            p[half][j] = u.p; x0[half][j] = u.s0; x1[half][j] = u.s1; x2[half][j] = u.s2;
+            w[j] = (j < nv[half]) ? u.p : 0.f;      // lanes past the row end are padding: exact zeros
           }
           if (vec) {
-            st_stream_f4(reinterpret_cast<float4*>(a.p + e), make_float4(p[0], p[1], p[2], p[3]));
-            if constexpr (NS >= 1) st_stream_f4(reinterpret_cast<float4*>(a.s0 + e), make_float4(x0[0], x0[1], x0[2], x0[3]));
-            if constexpr (NS >= 2) st_stream_f4(reinterpret_cast<float4*>(a.s1 + e), make_float4(x1[0], x1[1], x1[2], x1[3]));
-            if constexpr (NS >= 3) st_stream_f4(reinterpret_cast<float4*>(a.s2 + e), make_float4(x2[0], x2[1], x2[2], x2[3]));
+            st_weak_f4(a.p + e[half], p[half][0], p[half][1], p[half][2], p[half][3]);
+            if constexpr (NS >= 1) st_weak_f4(a.s0 + e[half], x0[half][0], x0[half][1], x0[half][2], x0[half][3]);
+            if constexpr (NS >= 2) st_weak_f4(a.s1 + e[half], x1[half][0], x1[half][1], x1[half][2], x1[half][3]);
+            if constexpr (NS >= 3) st_weak_f4(a.s2 + e[half], x2[half][0], x2[half][1], x2[half][2], x2[half][3]);
           } else {
-            for (int j = 0; j < nv; ++j) {
-              a.p[e + j] = p[j];
-              if constexpr (NS >= 1) a.s0[e + j] = x0[j];
-              if constexpr (NS >= 2) a.s1[e + j] = x1[j];
-              if constexpr (NS >= 3) a.s2[e + j] = x2[j];
+            for (int j = 0; j < nv[half]; ++j) {
+              a.p[e[half] + j] = p[half][j];
+              if constexpr (NS >= 1) a.s0[e[half] + j] = x0[half][j];
+              if constexpr (NS >= 2) a.s1[e[half] + j] = x1[half][j];
+              if constexpr (NS >= 3) a.s2[e[half] + j] = x2[half][j];
             }
           }
-          // row-major bf16 publish: [rows, w_ld]
+          // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
           if (sg.w_off >= 0) {
             const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
-            // w_ld is a multiple of 8 and c of 4: the 8-byte store always fits, pads carry zeros
             const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
             for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8(a.shadow_dst[d] + wo, q, mc && d == 0);
           }
@@ -303,7 +360,6 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       const int cc = c0 + cl, rr = r0 + part * 8;
       if (cc < sg.cols && rr < sg.rows) {
         const int64_t to = sg.wt_off + static_cast<int64_t>(cc) * sg.wt_ld + rr;
-        // wt_ld is a multiple of 8: the 16-byte store always fits, rows >= sg.rows carry zeros
         const uint4 q = *reinterpret_cast<const uint4*>(&s_tr[cl][part * 8]);
         for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16(a.shadow_dst[d] + to, q, mc && d == 0);
       }
@@ -314,25 +370,25 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   // ---------------- completion ----------------
   __syncthreads();
   if (tid == 0) {
-    __threadfence_system();                       // my remote stores are visible system-wide
-    const uint32_t prev = atomicAdd(local_sync + 2, 1u);
+    // lock mode: the release-add orders this CTA's stores (bar.sync is cumulative) before the lock release
+    // performed by the last CTA; Hogwild promises no ordering at all, so the counter is relaxed.
+    const uint32_t prev = locked ? lk_add_release<false>(local_sync + 2, 1u) : atomicAdd(local_sync + 2, 1u);
     if (prev == gridDim.x - 1) {                  // last CTA of this push
-      __threadfence_system();
+      if (locked) (void)ld_acquire_gpu(local_sync + 2);
       local_sync[2] = 0;
       if (a.loss_acc != nullptr) {
         *a.loss_out = *a.loss_acc;
         *a.loss_acc = 0.f;
       }
       if (a.drop) {
-        atom_add_relaxed_sys(a.ctrl + SF_CTRL_DROPPED, 1u);
+        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_DROPPED, 1u);
       } else {
-        atom_add_relaxed_sys(a.ctrl + SF_CTRL_STEP, 1u);
-        atom_add_relaxed_sys(a.ctrl + SF_CTRL_PUSHES, 1u);
-        atom_add_acqrel_sys(a.ctrl + SF_CTRL_VERSION, 1u);
+        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_STEP, 1u);
+        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_PUSHES, 1u);
+        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_VERSION, 1u);
       }
-      if (a.lock_mode == SF_LOCK_RW) {
-        rw_release_write(a.ctrl + SF_CTRL_LOCK);
-        __threadfence();
+      if (locked) {
+        rw_release_write<SYS>(a.ctrl + SF_CTRL_LOCK);
         st_release_gpu(local_sync + 3, s_epoch + 1);
       }
     }
@@ -343,6 +399,7 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
 // ---------------------------------------------------------------------------
 // pull: master publish buffer -> local replica (16-byte streaming copies over NVLink)
 // ---------------------------------------------------------------------------
+template <bool SYS>
 __global__ void __launch_bounds__(256, 1)
 pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_epoch;
@@ -351,12 +408,12 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
   pdl_wait();
   trace.mark();
   const int tid = threadIdx.x;
-  if (a.lock_mode == SF_LOCK_RW) {
+  const bool locked = a.lock_mode == SF_LOCK_RW;
+  if (locked) {
     if (tid == 0) {
       const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
       if (blockIdx.x == 0) {
-        rw_acquire_read(a.ctrl + SF_CTRL_LOCK);
-        __threadfence();
+        rw_acquire_read<SYS>(a.ctrl + SF_CTRL_LOCK);
         st_release_gpu(local_sync + 0, epoch + 1);
       } else {
         const unsigned long long t0 = gtime_ns();
@@ -390,15 +447,14 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
     for (size_t i = gid; i < n16; i += stride) d[i] = ld_stream_f4(s + i);
   }
   if (gid == 0 && a.seen_version != nullptr) *a.seen_version = ld_relaxed_sys(a.ctrl + SF_CTRL_VERSION);
-  if (a.lock_mode == SF_LOCK_RW) {
-    __syncthreads();
+  if (locked) {
+    __syncthreads();                 // every load of this CTA has returned (values were stored to the replica)
     if (tid == 0) {
-      __threadfence_system();
-      const uint32_t prev = atomicAdd(local_sync + 2, 1u);
+      const uint32_t prev = lk_add_release<false>(local_sync + 2, 1u);
       if (prev == gridDim.x - 1) {
+        (void)ld_acquire_gpu(local_sync + 2);
         local_sync[2] = 0;
-        rw_release_read(a.ctrl + SF_CTRL_LOCK);
-        __threadfence();
+        rw_release_read<SYS>(a.ctrl + SF_CTRL_LOCK);
         st_release_gpu(local_sync + 3, s_epoch + 1);
       }
     }
@@ -410,10 +466,10 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
 // 2 = acquire_write, 3 = release_write)
 __global__ void lock_test_kernel(uint32_t* ctrl, int op) {
   switch (op) {
-    case 0: rw_acquire_read(ctrl + SF_CTRL_LOCK); break;
-    case 1: rw_release_read(ctrl + SF_CTRL_LOCK); break;
-    case 2: rw_acquire_write(ctrl + SF_CTRL_LOCK); break;
-    case 3: rw_release_write(ctrl + SF_CTRL_LOCK); break;
+    case 0: rw_acquire_read<true>(ctrl + SF_CTRL_LOCK); break;
+    case 1: rw_release_read<true>(ctrl + SF_CTRL_LOCK); break;
+    case 2: rw_acquire_write<true>(ctrl + SF_CTRL_LOCK); break;
+    case 3: rw_release_write<true>(ctrl + SF_CTRL_LOCK); break;
   }
 }
 
@@ -421,7 +477,9 @@ __global__ void lock_test_kernel(uint32_t* ctrl, int op) {
 
 template <int OPT>
 static int launch_push(const SfPushArgs* a, uint32_t* ls, int grid, cudaStream_t st) {
-  return static_cast<int>(sf::launch(sf::push_kernel<OPT>, dim3(grid), dim3(sf::kPushThreads), 0, st, *a, ls));
+  if (a->scope_sys)
+    return static_cast<int>(sf::launch(sf::push_kernel<OPT, true>, dim3(grid), dim3(sf::kPushThreads), 0, st, *a, ls));
+  return static_cast<int>(sf::launch(sf::push_kernel<OPT, false>, dim3(grid), dim3(sf::kPushThreads), 0, st, *a, ls));
 }
 
 extern "C" int sf_push_launch(const SfPushArgs* a, uint32_t* local_sync, int grid, cudaStream_t st) {
@@ -450,7 +508,8 @@ extern "C" int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int gri
     if (grid > 148) grid = 148;
     if (grid < 1) grid = 1;
   }
-  return static_cast<int>(sf::launch(sf::pull_kernel, dim3(grid), dim3(256), 0, st, *a, local_sync));
+  if (a->scope_sys) return static_cast<int>(sf::launch(sf::pull_kernel<true>, dim3(grid), dim3(256), 0, st, *a, local_sync));
+  return static_cast<int>(sf::launch(sf::pull_kernel<false>, dim3(grid), dim3(256), 0, st, *a, local_sync));
 }
 
 extern "C" int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st) {

@@ -4,6 +4,7 @@
 // every kernel.  Python hands over raw device addresses (torch owns the allocations); nothing in
 // here depends on libtorch.
 #include <pybind11/pybind11.h>
+#include <pybind11/numpy.h>
 #include <pybind11/stl.h>
 
 #include <cstring>
@@ -136,6 +137,7 @@ SfPushArgs parse_push(const py::dict& d) {
   a.optimizer = getd<int>(d, "optimizer", SF_OPT_SGD);
   a.lock_mode = getd<int>(d, "lock_mode", 0);
   a.drop = getd<int>(d, "drop", 0);
+  a.scope_sys = getd<int>(d, "scope_sys", 1);
   a.grad_scale = getd<float>(d, "grad_scale", 1.0f);
   a.h = parse_hyper(getd<py::dict>(d, "hyper", py::dict()));
   if (!a.p || !a.ctrl || !a.grad || !a.segs || !a.tile_map || a.num_tiles <= 0)
@@ -155,6 +157,7 @@ SfPullArgs parse_pull(const py::dict& d) {
   a.ctrl = P<uint32_t>(getd<uintptr_t>(d, "ctrl", 0));
   a.seen_version = P<uint32_t>(getd<uintptr_t>(d, "seen_version", 0));
   a.lock_mode = getd<int>(d, "lock_mode", 0);
+  a.scope_sys = getd<int>(d, "scope_sys", 1);
   if ((a.n_bf16 % 8) || (a.n_f32 % 4)) throw std::runtime_error("pull: sizes must be 16-byte multiples");
   if (!a.ctrl) throw std::runtime_error("pull: ctrl is required");
   return a;
@@ -286,6 +289,88 @@ class Plan {
 };
 
 // ---------------------------------------------------------------------------
+// StepDriver: the native inner loop of a worker.  For every step it copies the minibatch rows from
+// the pinned host partition to the plan's staging buffers on the copy stream, makes the compute stream
+// wait for that copy, replays the step's CUDA graph and reads the step's loss back into a pinned ring.
+// Staging buffers are double-buffered by registering two plans (slot 0 / slot 1) per batch shape.
+// ---------------------------------------------------------------------------
+class StepDriver {
+ public:
+  StepDriver(uintptr_t compute_stream, uintptr_t copy_stream, uintptr_t x_host, size_t x_row_bytes, uintptr_t y_host,
+             size_t y_row_bytes, uintptr_t loss_ring, int ring_len)
+      : compute_(S(compute_stream)), copy_(S(copy_stream)), x_host_(P<const char>(x_host)), x_row_(x_row_bytes),
+        y_host_(P<const char>(y_host)), y_row_(y_row_bytes), ring_(P<float>(loss_ring)), ring_len_(ring_len) {}
+  ~StepDriver() {
+    for (auto& e : entries_) {
+      if (e.ready) cudaEventDestroy(e.ready);
+      if (e.free_) cudaEventDestroy(e.free_);
+    }
+  }
+  int add_plan(py::object plan, uintptr_t x_stage, uintptr_t y_stage, uintptr_t loss_out, int batch) {
+    Entry e;
+    e.keep = plan;
+    e.plan = plan.cast<Plan*>();
+    if (!e.plan->captured()) throw std::runtime_error("StepDriver: plan must be captured first");
+    e.x_stage = P<char>(x_stage);
+    e.y_stage = P<char>(y_stage);
+    e.loss_out = P<float>(loss_out);
+    e.batch = batch;
+    ck(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming), "cudaEventCreate");
+    ck(cudaEventCreateWithFlags(&e.free_, cudaEventDisableTiming), "cudaEventCreate");
+    entries_.push_back(e);
+    return static_cast<int>(entries_.size()) - 1;
+  }
+  // contiguous minibatches: step k uses plan ids[k] on rows [starts[k], starts[k] + batch)
+  void run(py::array_t<int32_t, py::array::c_style | py::array::forcecast> ids,
+           py::array_t<int64_t, py::array::c_style | py::array::forcecast> starts) {
+    const int n = static_cast<int>(ids.size());
+    if (starts.size() != n) throw std::runtime_error("StepDriver.run: ids/starts length mismatch");
+    const int32_t* ip = ids.data();
+    const int64_t* sp = starts.data();
+    py::gil_scoped_release nogil;
+    for (int k = 0; k < n; ++k) {
+      if (ip[k] < 0 || ip[k] >= static_cast<int>(entries_.size())) throw std::runtime_error("StepDriver.run: bad plan id");
+      Entry& e = entries_[ip[k]];
+      if (e.primed) ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(slot free)");
+      ck(cudaMemcpyAsync(e.x_stage, x_host_ + static_cast<size_t>(sp[k]) * x_row_, static_cast<size_t>(e.batch) * x_row_,
+                         cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(x)");
+      if (e.y_stage && y_host_)
+        ck(cudaMemcpyAsync(e.y_stage, y_host_ + static_cast<size_t>(sp[k]) * y_row_, static_cast<size_t>(e.batch) * y_row_,
+                           cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(y)");
+      ck(cudaEventRecord(e.ready, copy_), "cudaEventRecord(ready)");
+      ck(cudaStreamWaitEvent(compute_, e.ready, 0), "cudaStreamWaitEvent");
+      e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
+      ck(cudaMemcpyAsync(ring_ + (step_ % ring_len_), e.loss_out, sizeof(float), cudaMemcpyDeviceToHost, compute_), "cudaMemcpyAsync(loss)");
+      ck(cudaEventRecord(e.free_, compute_), "cudaEventRecord(free)");
+      e.primed = true;
+      ++step_;
+    }
+  }
+  long long steps() const { return step_; }
+
+ private:
+  struct Entry {
+    py::object keep;
+    Plan* plan = nullptr;
+    char* x_stage = nullptr;
+    char* y_stage = nullptr;
+    float* loss_out = nullptr;
+    int batch = 0;
+    cudaEvent_t ready = nullptr, free_ = nullptr;
+    bool primed = false;
+  };
+  cudaStream_t compute_, copy_;
+  const char* x_host_;
+  size_t x_row_;
+  const char* y_host_;
+  size_t y_row_;
+  float* ring_;
+  int ring_len_;
+  long long step_ = 0;
+  std::vector<Entry> entries_;
+};
+
+// ---------------------------------------------------------------------------
 // CUDA-IPC symmetric memory: cudaMalloc'ed segments exported to the peer processes of the box.
 // ---------------------------------------------------------------------------
 uintptr_t ipc_alloc(size_t bytes) {
@@ -408,6 +493,35 @@ PYBIND11_MODULE(_C, m) {
                return sf_argmax_rows(P<const float>(in), ld, P<float>(out), rows, cols, st);
              });
            })
+      .def("add_im2col",
+           [](Plan& p, uintptr_t in, int n, int h, int w, int c, int kh, int kw, uintptr_t out, int ld_out, uintptr_t outT, int ld_t) {
+             p.add("im2col", [=](cudaStream_t st) {
+               return sf_im2col_nhwc(P<const __nv_bfloat16>(in), n, h, w, c, kh, kw, P<__nv_bfloat16>(out), ld_out,
+                                     P<__nv_bfloat16>(outT), ld_t, st);
+             });
+           })
+      .def("add_col2im",
+           [](Plan& p, uintptr_t dcols, int ld_cols, int n, int h, int w, int c, int kh, int kw, uintptr_t din) {
+             p.add("col2im", [=](cudaStream_t st) {
+               return sf_col2im_nhwc(P<const __nv_bfloat16>(dcols), ld_cols, n, h, w, c, kh, kw, P<__nv_bfloat16>(din), st);
+             });
+           })
+      .def("add_maxpool_fwd",
+           [](Plan& p, uintptr_t in, int n, int h, int w, int c, uintptr_t out, uintptr_t argmax, uintptr_t outT, int ld_t) {
+             p.add("maxpool_fwd", [=](cudaStream_t st) {
+               return sf_maxpool2_fwd(P<const __nv_bfloat16>(in), n, h, w, c, P<__nv_bfloat16>(out), P<uint8_t>(argmax),
+                                      P<__nv_bfloat16>(outT), ld_t, st);
+             });
+           })
+      .def("add_maxpool_bwd",
+           [](Plan& p, uintptr_t dout, uintptr_t argmax, int n, int h, int w, int c, uintptr_t act_out, int act, uintptr_t dz,
+              int ld_dz, uintptr_t dzT, int ld_t, uintptr_t dbias) {
+             p.add("maxpool_bwd", [=](cudaStream_t st) {
+               return sf_maxpool2_bwd(P<const __nv_bfloat16>(dout), P<const uint8_t>(argmax), n, h, w, c,
+                                      P<const __nv_bfloat16>(act_out), act, P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT),
+                                      ld_t, P<float>(dbias), st);
+             });
+           })
       .def("add_push",
            [](Plan& p, const py::dict& d, uintptr_t local_sync, int grid) {
              const SfPushArgs a = parse_push(d);
@@ -417,6 +531,12 @@ PYBIND11_MODULE(_C, m) {
         const SfPullArgs a = parse_pull(d);
         p.add("pull", [=](cudaStream_t st) { return sf_pull_launch(&a, P<uint32_t>(local_sync), grid, st); });
       });
+
+  py::class_<StepDriver>(m, "StepDriver")
+      .def(py::init<uintptr_t, uintptr_t, uintptr_t, size_t, uintptr_t, size_t, uintptr_t, int>())
+      .def("add_plan", &StepDriver::add_plan)
+      .def("run", &StepDriver::run)
+      .def("steps", &StepDriver::steps);
 
   // direct (un-planned) entry points, used by tests and the eager paths
   m.def("cast_transpose", [](uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,
@@ -456,6 +576,20 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("lock_op", [](uintptr_t ctrl, int op, uintptr_t stream) {
     ck_rc(sf_lock_test(P<uint32_t>(ctrl), op, S(stream)), "lock_op");
+  });
+  m.def("im2col", [](uintptr_t in, int n, int h, int w, int c, int kh, int kw, uintptr_t out, int ld_out, uintptr_t outT, int ld_t, uintptr_t stream) {
+    ck_rc(sf_im2col_nhwc(P<const __nv_bfloat16>(in), n, h, w, c, kh, kw, P<__nv_bfloat16>(out), ld_out, P<__nv_bfloat16>(outT), ld_t, S(stream)), "im2col");
+  });
+  m.def("col2im", [](uintptr_t dcols, int ld_cols, int n, int h, int w, int c, int kh, int kw, uintptr_t din, uintptr_t stream) {
+    ck_rc(sf_col2im_nhwc(P<const __nv_bfloat16>(dcols), ld_cols, n, h, w, c, kh, kw, P<__nv_bfloat16>(din), S(stream)), "col2im");
+  });
+  m.def("maxpool_fwd", [](uintptr_t in, int n, int h, int w, int c, uintptr_t out, uintptr_t argmax, uintptr_t outT, int ld_t, uintptr_t stream) {
+    ck_rc(sf_maxpool2_fwd(P<const __nv_bfloat16>(in), n, h, w, c, P<__nv_bfloat16>(out), P<uint8_t>(argmax), P<__nv_bfloat16>(outT), ld_t, S(stream)), "maxpool_fwd");
+  });
+  m.def("maxpool_bwd", [](uintptr_t dout, uintptr_t argmax, int n, int h, int w, int c, uintptr_t act_out, int act, uintptr_t dz, int ld_dz,
+                          uintptr_t dzT, int ld_t, uintptr_t dbias, uintptr_t stream) {
+    ck_rc(sf_maxpool2_bwd(P<const __nv_bfloat16>(dout), P<const uint8_t>(argmax), n, h, w, c, P<const __nv_bfloat16>(act_out), act,
+                          P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT), ld_t, P<float>(dbias), S(stream)), "maxpool_bwd");
   });
   m.def("gemm_pick_bn", &sf_gemm_pick_bn);
   m.def("set_pdl", &sf_set_pdl);

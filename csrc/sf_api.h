@@ -95,15 +95,16 @@ int sf_mse_loss(const float* out, int ld_out, const float* target, int ld_target
 int sf_argmax_rows(const float* in, int ld, float* out, int rows, int cols, cudaStream_t st);
 int sf_fill_zero(void* p, size_t bytes, cudaStream_t st);
 
-// conv building blocks (NHWC, VALID, stride 1) and 2x2/s2 max-pool
+// conv building blocks (NHWC, VALID, stride 1) and 2x2/s2 max-pool (conv.cu)
 int sf_im2col_nhwc(const __nv_bfloat16* in, int n, int h, int w, int c, int kh, int kw,
                    __nv_bfloat16* out, int ld_out, __nv_bfloat16* outT, int ld_t, cudaStream_t st);
-int sf_col2im_nhwc(const float* cols, int ld_cols, int n, int h, int w, int c, int kh, int kw,
-                   float* out, cudaStream_t st);
+int sf_col2im_nhwc(const __nv_bfloat16* dcols, int ld_cols, int n, int h, int w, int c, int kh, int kw,
+                   __nv_bfloat16* din, cudaStream_t st);
 int sf_maxpool2_fwd(const __nv_bfloat16* in, int n, int h, int w, int c, __nv_bfloat16* out,
-                    uint8_t* argmax, cudaStream_t st);
-int sf_maxpool2_bwd(const float* dout, const uint8_t* argmax, int n, int h, int w, int c,
-                    const __nv_bfloat16* act_out, int act, __nv_bfloat16* din, cudaStream_t st);
+                    uint8_t* argmax, __nv_bfloat16* outT, int ld_t, cudaStream_t st);
+int sf_maxpool2_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, int n, int h, int w, int c,
+                    const __nv_bfloat16* act_out, int act, __nv_bfloat16* dz, int ld_dz,
+                    __nv_bfloat16* dzT, int ld_t, float* dbias, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // Fused push: optimizer step on the (possibly remote) master shard + bf16 publish (optim_push.cu)
@@ -141,6 +142,7 @@ struct SfPushArgs {
   int optimizer;
   int lock_mode;
   int drop;                       // fault injection: consume the gradient but do not apply it
+  int scope_sys;                  // 1: lock / counters use .sys scope (multi-GPU world); 0: .gpu (single GPU)
   float grad_scale;
   SfHyper h;
 };
@@ -169,6 +171,7 @@ struct SfPullArgs {
   uint32_t* ctrl;                 // master control block
   uint32_t* seen_version;         // local: version observed by this pull
   int lock_mode;
+  int scope_sys;
 };
 int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int grid, cudaStream_t st);
 

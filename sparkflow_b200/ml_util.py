@@ -107,8 +107,11 @@ def run_inference(graph_json: str, weights: Sequence[np.ndarray], features: np.n
         from .models.compiler import UnsupportedGraph, compile_graph
 
         try:
+            from .parallel.plan_builder import check_grammar
+
             lp = compile_graph(ir, tf_input, None, tf_output, need_loss=False)
-            if lp.is_mlp() and lp.output is not None and lp.output.layer >= 0:
+            check_grammar(lp)
+            if lp.output is not None and lp.output.layer >= 0 and lp.layers[lp.output.layer].kind == "dense":
                 from .ops.layout import ParamLayout
                 from .ops.optimizers import OptimizerSpec
                 from .parallel.device_engine import DeviceWorker, MasterState

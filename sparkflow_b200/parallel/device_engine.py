@@ -141,16 +141,18 @@ class DeviceWorker:
 
     def __init__(self, ir: GraphIR, tf_input: str, tf_label: Optional[str], spec: OptimizerSpec, master: MasterState,
                  acquire_lock: bool = False, pull_mode: Optional[str] = None, use_graphs: bool = True,
-                 device: Optional[torch.device] = None, plan: Optional[LayerPlan] = None):
+                 device: Optional[torch.device] = None, plan: Optional[LayerPlan] = None, shared: bool = True):
         self.C = native.cuda_ext()
         self.ir = ir
         self.plan: LayerPlan = plan if plan is not None else compile_graph(ir, tf_input, tf_label, None, need_loss=True)
-        if not self.plan.is_mlp():
-            raise NotImplementedError("conv plans are built by ConvWorker")
+        from .plan_builder import check_grammar
+
+        check_grammar(self.plan)
         self.spec, self.master = spec, master
         self.layout = master.layout
         self.device = device or master.device
         self.lock_mode = 1 if acquire_lock else 0
+        self.scope_sys = 1 if shared else 0        # more than one GPU touches the master -> system-scope lock
         self.pull_mode = pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")
         if self.pull_mode == "direct" and self.lock_mode:
             self.pull_mode = "copy"            # a locked pull must be a private snapshot
@@ -181,7 +183,8 @@ class DeviceWorker:
     @classmethod
     def for_inference(cls, ir: GraphIR, plan: LayerPlan, spec: OptimizerSpec, master: MasterState) -> "DeviceWorker":
         """Forward-only worker reading weights straight from ``master`` (no replica, no optimizer)."""
-        return cls(ir, plan.input_name, None, spec, master, acquire_lock=False, pull_mode="direct", use_graphs=False, plan=plan)
+        return cls(ir, plan.input_name, None, spec, master, acquire_lock=False, pull_mode="direct", use_graphs=False, plan=plan,
+                   shared=False)
 
     # ------------------------------------------------------------------------------------------
     def _weight_src(self) -> torch.Tensor:
@@ -200,167 +203,43 @@ class DeviceWorker:
                     ctrl=native.ptr(m.ctrl), shadow_dst=[native.ptr(m.shadow)], grad=native.ptr(self.grads),
                     loss_acc=native.ptr(self.loss_acc), loss_out=native.ptr(loss_out), segs=native.ptr(self.segs_dev),
                     tile_map=native.ptr(self.tile_map), num_tiles=int(self.tile_map.shape[0]), optimizer=self.spec.opt_id,
-                    lock_mode=self.lock_mode, drop=drop, grad_scale=1.0, hyper=self.spec.native_hyper())
+                    lock_mode=self.lock_mode, drop=drop, scope_sys=self.scope_sys, grad_scale=1.0, hyper=self.spec.native_hyper())
 
     def _pull_args(self) -> dict:
         lay, m = self.layout, self.master
         return dict(src=native.ptr(m.shadow), dst=native.ptr(self.replica), n_bf16=lay.shadow_total,
                     src_f32=native.ptr(m.p) + lay.vec_offset * 4 if lay.vec_count else 0,
                     dst_f32=native.ptr(self.vec_local) if lay.vec_count else 0, n_f32=lay.vec_count,
-                    ctrl=native.ptr(m.ctrl), seen_version=native.ptr(self.seen_version), lock_mode=self.lock_mode)
+                    ctrl=native.ptr(m.ctrl), seen_version=native.ptr(self.seen_version), lock_mode=self.lock_mode,
+                    scope_sys=self.scope_sys)
 
     # ------------------------------------------------------------------------------------------
     def build_plan(self, B: int, slot: int = 0, with_pull: bool = True, with_push: bool = True):
-        """Compile the step for batch size ``B`` reading from staging-buffer set ``slot``."""
-        key = (B, slot, with_pull, with_push)
-        if key in self._plans:
-            return self._plans[key], self._bufs[key]
-        C, dev, lay, lp = self.C, self.device, self.layout, self.plan
-        dense = [l for l in lp.layers if l.kind == "dense"]
-        L = len(dense)
-        ldB = round_up(B, 8)
-        D = lp.input_dim
-        x_stage = torch.zeros(B, D, dtype=torch.float32, device=dev)
-        y_stage = None if lp.target_is_input else torch.zeros(B, lp.label_dim, dtype=torch.float32, device=dev)
-        loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
-        widths = [D] + [l.out_features for l in dense]
-        acts = [torch.zeros(B, round_up(w, 8), dtype=torch.bfloat16, device=dev) for w in widths[:-1]]
-        actsT = [torch.zeros(w, ldB, dtype=torch.bfloat16, device=dev) for w in widths[:-1]]
-        out_f32 = torch.zeros(B, widths[-1], dtype=torch.float32, device=dev)
-        dz = [torch.zeros(B, round_up(w, 8), dtype=torch.bfloat16, device=dev) for w in widths[1:]]
-        dzT = [torch.zeros(w, ldB, dtype=torch.bfloat16, device=dev) for w in widths[1:]]
-        wsrc = self._weight_src()
-        plan = C.Plan()
-        gemms = []
-        branches = self.use_branches
-        do_pull = with_pull and self.pull_mode != "direct"
-        # ---------------- pull || input cast ----------------
-        if do_pull and branches:
-            plan.fork(1)
-            plan.branch(1)
-            plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
-            plan.branch(0)
-        elif do_pull:
-            plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
-        plan.add_cast_transpose(native.ptr(x_stage), D, 0, native.ptr(acts[0]), acts[0].shape[1], native.ptr(actsT[0]), ldB, B, D)
-        if do_pull and branches:
-            plan.join(1)
-        # ---------------- forward (+ loss fused into the last epilogue) ----------------
-        last_bias = lay.by_name(dense[-1].bias) if dense[-1].bias else None
-        db_ptr = native.ptr(self.grads) + last_bias.offset * 4 if last_bias else 0
-        target = x_stage if lp.target_is_input else y_stage
-        fuse_loss = self.fuse_loss and (lp.loss == "mse" or widths[-1] <= 32)
-        for i, l in enumerate(dense):
-            ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
-            last = i == L - 1
-            d = dict(a=native.ptr(acts[i]), lda=acts[i].shape[1], b=native.ptr(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld,
-                     M=B, N=ks.cols, K=ks.rows, bias=self._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
-            if last and fuse_loss:
-                d.update(loss_mode=1 if lp.loss == "softmax_xent" else 2, target=native.ptr(target), ld_target=target.shape[1],
-                         loss=native.ptr(self.loss_acc), out_bf16=native.ptr(dz[-1]), ld_bf16=dz[-1].shape[1],
-                         outT_bf16=native.ptr(dzT[-1]), ld_t=ldB, colsum=db_ptr)
-            elif last:
-                d.update(out_f32=native.ptr(out_f32), ld_f32=widths[-1])
-            else:
-                d.update(out_bf16=native.ptr(acts[i + 1]), ld_bf16=acts[i + 1].shape[1], outT_bf16=native.ptr(actsT[i + 1]), ld_t=ldB)
-            g = C.Gemm(d)
-            gemms.append(g)
-            plan.add_gemm(g, f"fwd{i}" + ("+loss" if last and fuse_loss else ""))
-        if not fuse_loss:
-            if lp.loss == "softmax_xent":
-                plan.add_softmax_xent(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], native.ptr(self.loss_acc),
-                                      native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
-            else:
-                plan.add_mse(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], ACT_IDS[dense[-1].act],
-                             native.ptr(self.loss_acc), native.ptr(dz[-1]), dz[-1].shape[1], native.ptr(dzT[-1]), ldB, db_ptr, B, widths[-1])
-        # ---------------- backward: dgrad chain on the main branch, wgrads on a side branch ----------------
-        for i in range(L - 1, -1, -1):
-            l = dense[i]
-            ks = lay.by_name(l.kernel)
-            wg = C.Gemm(dict(a=native.ptr(actsT[i]), lda=ldB, b=native.ptr(dzT[i]), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
-                             out_f32=native.ptr(self.grads) + ks.offset * 4, ld_f32=ks.cols))
-            gemms.append(wg)
-            if branches:
-                plan.fork(2)
-                plan.branch(2)
-            plan.add_gemm(wg, f"wgrad{i}")
-            plan.branch(0)
-            if i > 0:
-                prev = dense[i - 1]
-                pb = lay.by_name(prev.bias) if prev.bias else None
-                dg = C.Gemm(dict(a=native.ptr(dz[i]), lda=dz[i].shape[1], b=native.ptr(wsrc) + ks.w_off * 2, ldb=ks.w_ld,
-                                 M=B, N=ks.rows, K=ks.cols, aux=native.ptr(acts[i]), ld_aux=acts[i].shape[1],
-                                 aux_act=ACT_IDS[prev.act], out_bf16=native.ptr(dz[i - 1]), ld_bf16=dz[i - 1].shape[1],
-                                 outT_bf16=native.ptr(dzT[i - 1]), ld_t=ldB,
-                                 colsum=native.ptr(self.grads) + pb.offset * 4 if pb else 0))
-                gemms.append(dg)
-                plan.add_gemm(dg, f"dgrad{i}")
-        if branches:
-            plan.join(2)
-        if with_push:
-            plan.add_push(self._push_args(loss_out), native.ptr(self.sync_push), 0)
-        self._keep.extend([acts, actsT, out_f32, dz, dzT, gemms])
-        bufs = StepBuffers(x_stage, y_stage, loss_out)
-        self._plans[key], self._bufs[key] = plan, bufs
-        self.launches_per_step = len(plan)
-        return plan, bufs
+        """Compile the training step for batch size ``B`` reading from staging-buffer set ``slot``."""
+        from . import plan_builder
 
-    # ------------------------------------------------------------------------------------------
+        key = (B, slot, with_pull, with_push)
+        if key not in self._plans:
+            built = plan_builder.build(self, B, train=True, with_pull=with_pull, with_push=with_push)
+            self._plans[key] = built.plan
+            self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result)
+            self._keep.append(built.keep)
+            self.launches_per_step = len(built.plan)
+        return self._plans[key], self._bufs[key]
+
     def build_forward_plan(self, B: int, upto: Optional[int] = None, post: Optional[str] = None, with_loss: bool = False,
                            with_pull: bool = False):
         """Forward-only plan: up to dense layer ``upto`` (inclusive, default last) producing an fp32
         output (+ArgMax), or the full forward + loss kernel (no gradients) when ``with_loss``."""
+        from . import plan_builder
+
         key = ("fwd", B, upto, post, with_loss, with_pull)
-        if key in self._plans:
-            return self._plans[key], self._bufs[key]
-        C, dev, lay, lp = self.C, self.device, self.layout, self.plan
-        dense = [l for l in lp.layers if l.kind == "dense"]
-        if upto is None:
-            upto = len(dense) - 1
-        D = lp.input_dim
-        x_stage = torch.zeros(B, D, dtype=torch.float32, device=dev)
-        y_stage = None
-        if with_loss and not lp.target_is_input:
-            y_stage = torch.zeros(B, lp.label_dim, dtype=torch.float32, device=dev)
-        widths = [D] + [l.out_features for l in dense]
-        acts = [torch.zeros(B, round_up(w, 8), dtype=torch.bfloat16, device=dev) for w in widths[: upto + 1]]
-        out_f32 = torch.zeros(B, widths[upto + 1], dtype=torch.float32, device=dev)
-        result = torch.zeros(B, dtype=torch.float32, device=dev) if post == "ArgMax" else out_f32
-        loss_out = torch.zeros(1, dtype=torch.float32, device=dev)
-        wsrc = self._weight_src()
-        plan = C.Plan()
-        gemms = []
-        if with_pull and self.pull_mode != "direct":
-            plan.add_pull(self._pull_args(), native.ptr(self.sync_pull), 0)
-        if upto >= 0:
-            plan.add_cast_transpose(native.ptr(x_stage), D, 0, native.ptr(acts[0]), acts[0].shape[1], 0, 0, B, D)
-        for i in range(upto + 1):
-            l = dense[i]
-            ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
-            d = dict(a=native.ptr(acts[i]), lda=acts[i].shape[1], b=native.ptr(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld,
-                     M=B, N=ks.cols, K=ks.rows, bias=self._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
-            if i == upto:
-                d.update(out_f32=native.ptr(out_f32), ld_f32=widths[upto + 1])
-            else:
-                d.update(out_bf16=native.ptr(acts[i + 1]), ld_bf16=acts[i + 1].shape[1])
-            g = C.Gemm(d)
-            gemms.append(g)
-            plan.add_gemm(g, f"fwd{i}")
-        if with_loss:
-            target = x_stage if lp.target_is_input else y_stage
-            if lp.loss == "softmax_xent":
-                plan.add_softmax_xent(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], native.ptr(loss_out),
-                                      0, 0, 0, 0, 0, B, widths[-1])
-            else:
-                plan.add_mse(native.ptr(out_f32), widths[-1], native.ptr(target), target.shape[1], ACT_IDS[dense[-1].act],
-                             native.ptr(loss_out), 0, 0, 0, 0, 0, B, widths[-1])
-        elif post == "ArgMax":
-            plan.add_argmax(native.ptr(out_f32), widths[upto + 1], native.ptr(result), B, widths[upto + 1])
-        self._keep.extend([acts, out_f32, gemms, result])
-        bufs = StepBuffers(x_stage, y_stage, loss_out)
-        bufs.result = result
-        self._plans[key], self._bufs[key] = plan, bufs
-        return plan, bufs
+        if key not in self._plans:
+            built = plan_builder.build(self, B, train=False, with_pull=with_pull, upto=upto, post=post, with_loss=with_loss)
+            self._plans[key] = built.plan
+            self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result)
+            self._keep.append(built.keep)
+        return self._plans[key], self._bufs[key]
 
     EVAL_CHUNK = 4096
 

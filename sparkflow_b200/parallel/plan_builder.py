@@ -1,0 +1,316 @@
+"""LayerPlan -> native step plan (list of sm_100a kernel launches, later a CUDA graph).
+
+Supported layer grammar (anything else is reported as UnsupportedGraph and handled by the generic engine):
+
+    input -> [reshape] -> (conv pool)* -> [flatten] -> dense+ -> loss
+
+Data-flow conventions (all activations bf16, all accumulation fp32):
+
+* dense layer i consumes ``a_i`` [B, ld] (A operand) and the published ``W_i^T`` [out, ld] (B operand);
+  its epilogue adds bias, applies the activation and writes ``a_{i+1}`` plus ``a_{i+1}^T`` (the K-major
+  operand of the next layer's wgrad).  The last dense layer's epilogue also computes the loss and dL/dz.
+* conv is im2col (patches + patches^T) followed by the same GEMM; NHWC activations are exactly the
+  row-major GEMM output, so no layout conversion exists anywhere.
+* backward: ``dgrad`` GEMMs run on the main branch of the graph, ``wgrad`` GEMMs (which only feed the push)
+  on a side branch; bias gradients come out of epilogues / the pool-backward kernel; every gradient lands in
+  the flat fp32 buffer the push kernel consumes.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from ..models.compiler import ACT_IDS, Layer, LayerPlan, UnsupportedGraph
+from ..ops import native
+from ..ops.layout import round_up
+
+
+@dataclass
+class BuiltPlan:
+    plan: Any
+    x_stage: torch.Tensor
+    y_stage: Optional[torch.Tensor]
+    loss_out: torch.Tensor
+    result: Optional[torch.Tensor] = None
+    keep: List[Any] = field(default_factory=list)
+
+
+def check_grammar(lp: LayerPlan) -> None:
+    """Raise UnsupportedGraph unless the layer sequence matches the grammar above."""
+    kinds = [l.kind for l in lp.layers]
+    i = 0
+    if i < len(kinds) and kinds[i] == "reshape":
+        i += 1
+    saw_conv = False
+    while i + 1 < len(kinds) and kinds[i] == "conv" and kinds[i + 1] == "pool":
+        saw_conv = True
+        i += 2
+    if i < len(kinds) and kinds[i] == "reshape":
+        i += 1
+    n_dense = 0
+    while i < len(kinds) and kinds[i] == "dense":
+        n_dense += 1
+        i += 1
+    if i != len(kinds) or n_dense == 0:
+        raise UnsupportedGraph(f"layer sequence {kinds} is outside the compiled plan grammar "
+                               "(input -> [reshape] -> (conv pool)* -> [flatten] -> dense+)")
+    for l in lp.layers:
+        if l.kind == "conv":
+            if l.out_shape[2] % 8:
+                raise UnsupportedGraph("conv output channels must be a multiple of 8")
+            if l.act not in (None, "Relu", "Sigmoid", "Tanh"):
+                raise UnsupportedGraph(f"conv activation {l.act}")
+    if saw_conv and lp.input_dim % 8:
+        raise UnsupportedGraph("image inputs need a feature count that is a multiple of 8")
+
+
+def _split_k(tiles: int, kblocks: int) -> int:
+    if kblocks < 16:
+        return 1
+    return max(1, min(148 // max(tiles, 1), kblocks // 4))
+
+
+def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = True, upto: Optional[int] = None,
+          post: Optional[str] = None, with_loss: bool = False) -> BuiltPlan:
+    """``train``: full step (fwd + loss + bwd + push).  Otherwise forward up to dense index ``upto``
+    (None = last) producing an fp32 result (+ArgMax), or forward + loss only when ``with_loss``."""
+    C, dev, lay, lp = worker.C, worker.device, worker.layout, worker.plan
+    check_grammar(lp)
+    P = native.ptr
+    bf16, f32 = torch.bfloat16, torch.float32
+    keep: List[Any] = []
+
+    def zeros(*shape, dtype=bf16):
+        t = torch.zeros(*shape, dtype=dtype, device=dev)
+        keep.append(t)
+        return t
+
+    ldB = round_up(B, 8)
+    D = lp.input_dim
+    x_stage = zeros(B, D, dtype=f32)
+    need_labels = (train or with_loss) and not lp.target_is_input
+    y_stage = zeros(B, lp.label_dim, dtype=f32) if need_labels else None
+    loss_out = zeros(1, dtype=f32)
+    wsrc = worker._weight_src()
+    plan = C.Plan()
+    branches = worker.use_branches and train
+    do_pull = with_pull and worker.pull_mode != "direct"
+
+    layers = lp.layers
+    dense_ids = [i for i, l in enumerate(layers) if l.kind == "dense"]
+    last_dense_pos = len(dense_ids) - 1 if upto is None else upto
+    stop_layer = dense_ids[last_dense_pos]
+    trainable = [i for i, l in enumerate(layers) if l.kind in ("dense", "conv")]
+    first_trainable = trainable[0]
+
+    # ---------------- pull || input cast ----------------
+    if do_pull and branches:
+        plan.fork(1)
+        plan.branch(1)
+        plan.add_pull(worker._pull_args(), P(worker.sync_pull), 0)
+        plan.branch(0)
+    elif do_pull:
+        plan.add_pull(worker._pull_args(), P(worker.sync_pull), 0)
+    first_is_dense = layers[first_trainable].kind == "dense"
+    a0 = zeros(B, round_up(D, 8))
+    a0T = zeros(D, ldB) if (train and first_is_dense) else None
+    plan.add_cast_transpose(P(x_stage), D, 0, P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
+    if do_pull and branches:
+        plan.join(1)
+
+    # ---------------- forward ----------------
+    # `cur` describes the activation entering the next layer
+    cur: Dict[str, Any] = dict(kind="flat", buf=a0, bufT=a0T, feat=D, ld=a0.shape[1])
+    rec: Dict[int, Dict[str, Any]] = {}        # per-layer tensors needed by backward
+    gemms: List[Any] = []
+    out_f32 = None
+    dz_last = dzT_last = None
+    fuse_loss = False
+    target = x_stage if lp.target_is_input else y_stage
+    for i, l in enumerate(layers):
+        if i > stop_layer:
+            break
+        if l.kind == "reshape":
+            if len(l.out_shape) == 3:                              # flat -> image (NHWC view of the same memory)
+                if cur["ld"] != cur["feat"]:
+                    raise UnsupportedGraph("reshape to an image needs an unpadded feature row")
+                cur = dict(kind="img", buf=cur["buf"], shape=l.out_shape)
+            else:                                                   # flatten: image -> flat view
+                h, w, c = cur["shape"]
+                cur = dict(kind="flat", buf=cur["buf"], bufT=cur.get("flatT"), feat=h * w * c, ld=h * w * c)
+            continue
+        if l.kind == "conv":
+            h, w, cin = cur["shape"]
+            kh, kw = l.ksize
+            oh, ow, cout = l.out_shape
+            M, K = B * oh * ow, kh * kw * cin
+            ldK, ldM = round_up(K, 8), round_up(M, 8)
+            patches = zeros(M, ldK)
+            patchesT = zeros(K, ldM) if train else None
+            plan.add_im2col(P(cur["buf"]), B, h, w, cin, kh, kw, P(patches), ldK, P(patchesT), ldM if train else 0)
+            ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
+            act_out = zeros(M, cout)
+            g = C.Gemm(dict(a=P(patches), lda=ldK, b=P(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld, M=M, N=cout, K=K,
+                            bias=worker._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act], out_bf16=P(act_out), ld_bf16=cout,
+                            a_evict_first=1))
+            gemms.append(g)
+            plan.add_gemm(g, f"conv{i}")
+            rec[i] = dict(patches=patches, patchesT=patchesT, act_out=act_out, in_shape=(h, w, cin), M=M, K=K, ldM=ldM, ldK=ldK)
+            cur = dict(kind="img", buf=act_out, shape=(oh, ow, cout), conv=i)
+            continue
+        if l.kind == "pool":
+            h, w, c = cur["shape"]
+            oh, ow = h // 2, w // 2
+            pooled = zeros(B, oh * ow * c)
+            argmax = zeros(B, oh * ow * c, dtype=torch.uint8)
+            nxt_dense = (i + 2 < len(layers) and layers[i + 1].kind == "reshape" and layers[i + 2].kind == "dense")
+            flatT = zeros(oh * ow * c, ldB) if (train and nxt_dense) else None
+            plan.add_maxpool_fwd(P(cur["buf"]), B, h, w, c, P(pooled), P(argmax), P(flatT), ldB if flatT is not None else 0)
+            rec[i] = dict(argmax=argmax, in_shape=(h, w, c), conv=cur.get("conv"), pooled=pooled)
+            cur = dict(kind="img", buf=pooled, shape=(oh, ow, c), flatT=flatT)
+            continue
+        # ---- dense ----
+        ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
+        last = i == stop_layer
+        d = dict(a=P(cur["buf"]), lda=cur["ld"], b=P(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld, M=B, N=ks.cols, K=ks.rows,
+                 bias=worker._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
+        rec[i] = dict(a_in=cur["buf"], a_in_ld=cur["ld"], a_inT=cur.get("bufT"))
+        if last:
+            fuse_loss = train and worker.fuse_loss and (lp.loss == "mse" or ks.cols <= 32)
+            if fuse_loss:
+                dz_last, dzT_last = zeros(B, round_up(ks.cols, 8)), zeros(ks.cols, ldB)
+                db = P(worker.grads) + bs.offset * 4 if bs else 0
+                d.update(loss_mode=1 if lp.loss == "softmax_xent" else 2, target=P(target), ld_target=target.shape[1],
+                         loss=P(worker.loss_acc), out_bf16=P(dz_last), ld_bf16=dz_last.shape[1], outT_bf16=P(dzT_last), ld_t=ldB,
+                         colsum=db)
+            else:
+                out_f32 = zeros(B, ks.cols, dtype=f32)
+                d.update(out_f32=P(out_f32), ld_f32=ks.cols)
+            g = C.Gemm(d)
+            gemms.append(g)
+            plan.add_gemm(g, f"fwd{i}" + ("+loss" if fuse_loss else ""))
+            rec[i]["N"] = ks.cols
+            break
+        nxt = zeros(B, round_up(ks.cols, 8))
+        nxtT = zeros(ks.cols, ldB) if train else None
+        d.update(out_bf16=P(nxt), ld_bf16=nxt.shape[1], outT_bf16=P(nxtT), ld_t=ldB if train else 0)
+        g = C.Gemm(d)
+        gemms.append(g)
+        plan.add_gemm(g, f"fwd{i}")
+        cur = dict(kind="flat", buf=nxt, bufT=nxtT, feat=ks.cols, ld=nxt.shape[1])
+
+    result = None
+    last_l = layers[stop_layer]
+    n_out = lay.by_name(last_l.kernel).cols
+    if not train:
+        if with_loss:
+            if lp.loss == "softmax_xent":
+                plan.add_softmax_xent(P(out_f32), n_out, P(target), target.shape[1], P(loss_out), 0, 0, 0, 0, 0, B, n_out)
+            else:
+                plan.add_mse(P(out_f32), n_out, P(target), target.shape[1], ACT_IDS[last_l.act], P(loss_out), 0, 0, 0, 0, 0, B, n_out)
+        elif post == "ArgMax":
+            result = zeros(B, dtype=f32)
+            plan.add_argmax(P(out_f32), n_out, P(result), B, n_out)
+        else:
+            result = out_f32
+        keep.append(gemms)
+        return BuiltPlan(plan, x_stage, y_stage, loss_out, result, keep)
+
+    # ---------------- loss (when not fused) ----------------
+    bs_last = lay.by_name(last_l.bias) if last_l.bias else None
+    if not fuse_loss:
+        dz_last, dzT_last = zeros(B, round_up(n_out, 8)), zeros(n_out, ldB)
+        db = P(worker.grads) + bs_last.offset * 4 if bs_last else 0
+        if lp.loss == "softmax_xent":
+            plan.add_softmax_xent(P(out_f32), n_out, P(target), target.shape[1], P(worker.loss_acc), P(dz_last), dz_last.shape[1],
+                                  P(dzT_last), ldB, db, B, n_out)
+        else:
+            plan.add_mse(P(out_f32), n_out, P(target), target.shape[1], ACT_IDS[last_l.act], P(worker.loss_acc), P(dz_last),
+                         dz_last.shape[1], P(dzT_last), ldB, db, B, n_out)
+
+    # ---------------- backward ----------------
+    def side(fn):
+        """run `fn` (which adds ops) on the wgrad branch"""
+        if branches:
+            plan.fork(2)
+            plan.branch(2)
+        fn()
+        plan.branch(0)
+
+    # gradient flowing into the current layer from above
+    g_dz, g_dzT = dz_last, dzT_last              # wrt the pre-activation of the layer being processed (dense)
+    g_img = None                                  # wrt the pooled output (feeds maxpool_bwd)
+    for i in range(stop_layer, -1, -1):
+        l = layers[i]
+        if l.kind == "dense":
+            ks = lay.by_name(l.kernel)
+            r = rec[i]
+            if r["a_inT"] is None:
+                raise UnsupportedGraph("dense layer input has no transposed copy")
+            wg = C.Gemm(dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
+                             out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols))
+            gemms.append(wg)
+            side(lambda wg=wg, i=i: plan.add_gemm(wg, f"wgrad{i}"))
+            if i == first_trainable:
+                break
+            prev = layers[i - 1]
+            if prev.kind == "dense":
+                pb = lay.by_name(prev.bias) if prev.bias else None
+                ndz, ndzT = zeros(B, r["a_in_ld"]), zeros(ks.rows, ldB)
+                dg = C.Gemm(dict(a=P(g_dz), lda=g_dz.shape[1], b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=B, N=ks.rows, K=ks.cols,
+                                 aux=P(r["a_in"]), ld_aux=r["a_in_ld"], aux_act=ACT_IDS[prev.act], out_bf16=P(ndz),
+                                 ld_bf16=ndz.shape[1], outT_bf16=P(ndzT), ld_t=ldB,
+                                 colsum=P(worker.grads) + pb.offset * 4 if pb else 0))
+                gemms.append(dg)
+                plan.add_gemm(dg, f"dgrad{i}")
+                g_dz, g_dzT = ndz, ndzT
+            else:                                  # flatten over a pooled image: gradient wrt the pooled tensor
+                g_img = zeros(B, ks.rows)
+                dg = C.Gemm(dict(a=P(g_dz), lda=g_dz.shape[1], b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=B, N=ks.rows, K=ks.cols,
+                                 out_bf16=P(g_img), ld_bf16=ks.rows))
+                gemms.append(dg)
+                plan.add_gemm(dg, f"dgrad{i}")
+            continue
+        if l.kind == "reshape":
+            continue
+        if l.kind == "pool":
+            r = rec[i]
+            ci = r["conv"]
+            conv_l, cr = layers[ci], rec[ci]
+            h, w, c = r["in_shape"]
+            cb = lay.by_name(conv_l.bias) if conv_l.bias else None
+            need_dz = ci != first_trainable            # conv dgrad needs the row-major dz
+            dzc = zeros(cr["M"], c) if need_dz else None
+            dzcT = zeros(c, cr["ldM"])
+            plan.add_maxpool_bwd(P(g_img), P(r["argmax"]), B, h, w, c, P(cr["act_out"]), ACT_IDS[conv_l.act], P(dzc), c if need_dz else 0,
+                                 P(dzcT), cr["ldM"], P(worker.grads) + cb.offset * 4 if cb else 0)
+            rec[ci]["dz"], rec[ci]["dzT"] = dzc, dzcT
+            continue
+        if l.kind == "conv":
+            ks = lay.by_name(l.kernel)
+            r = rec[i]
+            kblocks = (r["M"] + 63) // 64
+            tiles = ((r["K"] + 127) // 128) * max(1, (ks.cols + 63) // 64)
+            wg = C.Gemm(dict(a=P(r["patchesT"]), lda=r["ldM"], b=P(r["dzT"]), ldb=r["ldM"], M=r["K"], N=ks.cols, K=r["M"],
+                             out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols, split_k=_split_k(tiles, kblocks), accumulate=1))
+            gemms.append(wg)
+            side(lambda wg=wg, i=i: plan.add_gemm(wg, f"wgrad{i}"))
+            if i == first_trainable:
+                break
+            h, w, cin = r["in_shape"]
+            dpatch = zeros(r["M"], r["ldK"])
+            dg = C.Gemm(dict(a=P(r["dz"]), lda=ks.cols, b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=r["M"], N=r["K"], K=ks.cols,
+                             out_bf16=P(dpatch), ld_bf16=r["ldK"], a_evict_first=1))
+            gemms.append(dg)
+            plan.add_gemm(dg, f"dgrad{i}")
+            g_img = zeros(B, h * w * cin)
+            plan.add_col2im(P(dpatch), r["ldK"], B, h, w, cin, l.ksize[0], l.ksize[1], P(g_img))
+            continue
+    if branches:
+        plan.join(2)
+    if with_push:
+        plan.add_push(worker._push_args(loss_out), P(worker.sync_push), 0)
+    keep.append(gemms)
+    return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep)

@@ -55,9 +55,9 @@ class TrainingSession:
         self.engine_kind = "torch"
         if self.use_cuda:
             try:
-                lp = compile_graph(self.ir, tf_input, tf_label)
-                if not lp.is_mlp():
-                    raise UnsupportedGraph("conv plans are not compiled yet")
+                from .plan_builder import check_grammar
+
+                check_grammar(compile_graph(self.ir, tf_input, tf_label))
                 self.engine_kind = "b200"
             except UnsupportedGraph as exc:
                 if engine == "b200":
@@ -134,8 +134,9 @@ class TrainingSession:
             master = self.master
             if master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
                 master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base)
+            shared = self.ctx.world > 1 or len(self.local_devices()) > 1
             w = DeviceWorker(self.ir, self.tf_input, self.tf_label, self.spec, master, acquire_lock=self.acquire_lock,
-                             pull_mode=self.pull_mode, device=device)
+                             pull_mode=self.pull_mode, device=device, shared=shared)
             self._workers.append(w)
             return B200Engine(w)
         if self.ctx.world > 1 and not self.ctx.is_master:

@@ -62,9 +62,14 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
     engine.load_partition(features, labels)
     rng = np.random.default_rng(seed)
     order: Optional[np.ndarray] = None
+    fast = hasattr(engine, "train_contiguous")
+    sweep = mini_stochastic_iters < 1 and mini_batch_size >= 1
     for i in range(iters):
         if shuffle:
             order = rng.permutation(n)
+            if fast and sweep:
+                engine.permute(order)          # physical shuffle (what the reference does), then contiguous batches
+                order = None
 
         def rows_of(sel: Rows) -> Rows:
             if order is None:
@@ -81,8 +86,14 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
                 engine.train(rows_of(sel), pull=(j == 0))
         elif mini_batch_size >= 1:
             mbs = max(clamp_batch(n, mini_batch_size), 1)
-            for r in range(0, n, mbs):
-                engine.train(rows_of(slice(r, min(r + mbs, n))), pull=True)
+            if fast and order is None:
+                full = n // mbs
+                engine.train_contiguous([k * mbs for k in range(full)], mbs, pull=True)
+                if full * mbs < n:
+                    engine.train(slice(full * mbs, n), pull=True)
+            else:
+                for r in range(0, n, mbs):
+                    engine.train(rows_of(slice(r, min(r + mbs, n))), pull=True)
         else:
             engine.train(rows_of(slice(0, n)), pull=True)
 
@@ -153,6 +164,10 @@ class B200Engine(Engine):
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._gather = [None, None]
+        self._driver = None
+        self._driver_plans = {}
+        self._driver_last = None
+        self._X2 = self._Y2 = None
 
     def load_partition(self, features, labels):
         self.X = torch.as_tensor(np.ascontiguousarray(features, dtype=np.float32)).pin_memory()
@@ -198,10 +213,71 @@ class B200Engine(Engine):
             self.d2h_bytes += 4
             self._slot_free[slot].record(w.stream)
         self._primed[slot] = True
+        self._driver_last = None
         self.step_idx += 1
+
+    def permute(self, order: np.ndarray) -> None:
+        """Physically shuffle the pinned partition (threaded native row gather into the spare buffers)."""
+        self.w.stream.synchronize()
+        self.w.copy_stream.synchronize()
+        from ..ops.native import host_ext
+
+        H = host_ext()
+        if self._X2 is None:
+            self._X2 = torch.empty_like(self.X).pin_memory()
+            self._Y2 = None if self.Y is None else torch.empty_like(self.Y).pin_memory()
+        idx = np.ascontiguousarray(order, dtype=np.int64)
+        H.gather_rows(self.X.data_ptr(), self._X2.data_ptr(), idx, self.X.shape[1] * 4, 8)
+        self.X, self._X2 = self._X2, self.X
+        if self.Y is not None:
+            H.gather_rows(self.Y.data_ptr(), self._Y2.data_ptr(), idx, self.Y.shape[1] * 4, 4)
+            self.Y, self._Y2 = self._Y2, self.Y
+        self._driver = None                     # host base pointers changed
+        self._driver_plans = {}
+
+    # ---- native inner loop -------------------------------------------------------------------------
+    def train_contiguous(self, starts: Sequence[int], batch: int, pull: bool = True) -> None:
+        """Run ``len(starts)`` steps on contiguous row blocks ``[s, s + batch)`` through the C++ StepDriver
+        (H2D of every minibatch, graph replay, loss D2H – no Python in the loop)."""
+        w = self.w
+        if not w.use_graphs or len(starts) == 0:
+            for s0 in starts:
+                self.train(slice(int(s0), int(s0) + batch), pull)
+            return
+        key = (batch, pull)
+        drv_ids = self._driver_plans.get(key)
+        if drv_ids is None:
+            if self._driver is None:
+                self._driver = w.C.StepDriver(w.stream.cuda_stream, w.copy_stream.cuda_stream, self.X.data_ptr(),
+                                              self.X.shape[1] * 4, 0 if self.Y is None else self.Y.data_ptr(),
+                                              0 if self.Y is None else self.Y.shape[1] * 4, self.loss_ring.data_ptr(), self.LOSS_RING)
+            drv_ids = []
+            for slot in (0, 1):
+                plan, bufs = w.build_plan(batch, slot, with_pull=pull)
+                while not plan.captured():              # first call runs eagerly, second captures
+                    bufs.x_stage.copy_(self.X[:batch], non_blocking=True)
+                    if bufs.y_stage is not None and self.Y is not None:
+                        bufs.y_stage.copy_(self.Y[:batch], non_blocking=True)
+                    torch.cuda.current_stream().synchronize()
+                    w.run_plan(plan)
+                    w.stream.synchronize()
+                    self.step_idx += 1
+                drv_ids.append(self._driver.add_plan(plan, bufs.x_stage.data_ptr(), 0 if bufs.y_stage is None else bufs.y_stage.data_ptr(),
+                                                     bufs.loss_out.data_ptr(), batch))
+            self._driver_plans[key] = drv_ids
+        self.w.stream.synchronize()       # python-path steps (if any) are done before the driver takes over the ring
+        ids = np.asarray([drv_ids[(self._driver.steps() + k) & 1] for k in range(len(starts))], dtype=np.int32)
+        self._driver.run(ids, np.asarray(starts, dtype=np.int64))
+        n = len(starts)
+        self.h2d_bytes += n * batch * (self.X.shape[1] + (0 if self.Y is None else self.Y.shape[1])) * 4
+        self.d2h_bytes += n * 4
+        self._driver_last = (self._driver.steps() - 1) % self.LOSS_RING
+        self.step_idx += n
 
     def last_loss(self) -> float:
         self.w.stream.synchronize()
+        if self._driver_last is not None:
+            return float(self.loss_ring[self._driver_last])
         return float(self.loss_ring[(self.step_idx - 1) % self.LOSS_RING])
 
     def partition_loss(self) -> float:

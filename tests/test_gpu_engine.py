@@ -17,6 +17,7 @@ from sparkflow_b200.parallel.param_server import LocalTransport, ParameterServer
 from sparkflow_b200.parallel.worker import B200Engine, TorchEngine
 
 CASES = {
+    "cnn": ("x:0", "y:0", 784, 10, "onehot"),
     "simple_dnn": ("x:0", "y:0", 784, 10, "onehot"),
     "autoencoder": ("x:0", None, 784, 0, None),
     "test_mlp": ("x:0", "y:0", 10, 1, "binary"),
