@@ -225,11 +225,14 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
   TraceScope trace;
   pdl_launch_dependents();
-  pdl_wait();
-  trace.mark();
   const int tid = threadIdx.x;
   constexpr int NS = Slots<OPT>::n;
   const bool locked = a.lock_mode == SF_LOCK_RW;
+  // Hogwild reads the global step count racily; it does not depend on this step's kernels, so the
+  // round trip to the master overlaps the predecessor's tail (before the programmatic-dependency wait).
+  if (!locked && tid == 0) s_t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
+  pdl_wait();
+  trace.mark();
 
   // ---------------- acquire / step number ----------------
   if (tid == 0) {
@@ -257,15 +260,28 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
 
   // ---------------- tiles ----------------
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-    const int seg_i = a.tile_map[tile * 3 + 0];
-    const int r0 = a.tile_map[tile * 3 + 1] * kTileR;
-    const int c0 = a.tile_map[tile * 3 + 2] * kTileC;
-    const SfTensorSeg sg = a.segs[seg_i];
+    int r0, c0;
+    SfTensorSeg sg;
+    if (a.n_inline_segs > 0) {                         // tables live in constant (parameter) space
+      int si = 0;
+      while (si + 1 < a.n_inline_segs && tile >= a.tile_prefix[si + 1]) ++si;
+      sg = a.inline_segs[si];
+      const int local = tile - a.tile_prefix[si];
+      const int tiles_c = (sg.cols + kTileC - 1) / kTileC;
+      r0 = (local / tiles_c) * kTileR;
+      c0 = (local % tiles_c) * kTileC;
+    } else {
+      const int seg_i = a.tile_map[tile * 3 + 0];
+      r0 = a.tile_map[tile * 3 + 1] * kTileR;
+      c0 = a.tile_map[tile * 3 + 2] * kTileC;
+      sg = a.segs[seg_i];
+    }
     const bool vec = ((sg.cols & 3) == 0) && ((sg.offset & 3) == 0);
     const int tx = tid & 15, ty = tid >> 4;
     const int c = c0 + tx * 4;
     // ---- phase 1: issue every load of both half-rows before anything depends on them ----
-    float g[2][4], p[2][4], x0[2][4], x1[2][4], x2[2][4];
+    float g[2][4];
+    float4 st4[2][4];
     int nv[2];
     int64_t e[2];
 #pragma unroll
@@ -274,36 +290,22 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       nv[half] = (r < sg.rows && c < sg.cols) ? ((sg.cols - c) >= 4 ? 4 : (sg.cols - c)) : 0;
       e[half] = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { g[half][j] = 0.f; p[half][j] = 0.f; x0[half][j] = 0.f; x1[half][j] = 0.f; x2[half][j] = 0.f; }
+      for (int j = 0; j < 4; ++j) { g[half][j] = 0.f; st4[half][j] = make_float4(0.f, 0.f, 0.f, 0.f); }
       if (nv[half] == 0) continue;
       if (vec) {
         const float4 gv = *reinterpret_cast<const float4*>(a.grad + e[half]);
         g[half][0] = gv.x; g[half][1] = gv.y; g[half][2] = gv.z; g[half][3] = gv.w;
-        if (!a.drop) {
-          const float4 pv = ld_weak_f4(a.p + e[half]);
-          p[half][0] = pv.x; p[half][1] = pv.y; p[half][2] = pv.z; p[half][3] = pv.w;
-          if constexpr (NS >= 1) { const float4 q = ld_weak_f4(a.s0 + e[half]); x0[half][0] = q.x; x0[half][1] = q.y; x0[half][2] = q.z; x0[half][3] = q.w; }
-          if constexpr (NS >= 2) { const float4 q = ld_weak_f4(a.s1 + e[half]); x1[half][0] = q.x; x1[half][1] = q.y; x1[half][2] = q.z; x1[half][3] = q.w; }
-          if constexpr (NS >= 3) { const float4 q = ld_weak_f4(a.s2 + e[half]); x2[half][0] = q.x; x2[half][1] = q.y; x2[half][2] = q.z; x2[half][3] = q.w; }
-        }
       } else {
-        for (int j = 0; j < nv[half]; ++j) {
-          g[half][j] = a.grad[e[half] + j];
-          if (!a.drop) {
-            p[half][j] = a.p[e[half] + j];
-            if constexpr (NS >= 1) x0[half][j] = a.s0[e[half] + j];
-            if constexpr (NS >= 2) x1[half][j] = a.s1[e[half] + j];
-            if constexpr (NS >= 3) x2[half][j] = a.s2[e[half] + j];
-          }
-        }
+        for (int j = 0; j < nv[half]; ++j) g[half][j] = a.grad[e[half] + j];
+      }
+      if (!a.drop) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nv[half]) st4[half][j] = ld_weak_f4(reinterpret_cast<const float*>(a.state + e[half] + j));
       }
     }
-    // ---- step number: under the lock it was granted above; Hogwild reads it racily (like unlocked TF
-    //      beta-power variables) while the loads are in flight ----
-    if (!locked && tile == static_cast<int>(blockIdx.x)) {
-      if (tid == 0) s_t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
-      __syncthreads();
-    }
+    // ---- step number: under the lock it was granted above; Hogwild read it at kernel entry ----
+    if (!locked && tile == static_cast<int>(blockIdx.x)) __syncthreads();     // s_t was read at kernel entry
     const float t = static_cast<float>(s_t);
     float lr_t = a.h.lr;
     if constexpr (OPT == SF_OPT_ADAM) {
@@ -322,22 +324,12 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
         if (!a.drop) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            Upd u{p[half][j], x0[half][j], x1[half][j], x2[half][j]};
-            apply_rule<OPT>(u, g[half][j] * a.grad_scale, a.h, t, lr_t);
-            p[half][j] = u.p; x0[half][j] = u.s0; x1[half][j] = u.s1; x2[half][j] = u.s2;
-            w[j] = (j < nv[half]) ? u.p : 0.f;      // lanes past the row end are padding: exact zeros
-          }
-          if (vec) {
-            st_weak_f4(a.p + e[half], p[half][0], p[half][1], p[half][2], p[half][3]);
-            if constexpr (NS >= 1) st_weak_f4(a.s0 + e[half], x0[half][0], x0[half][1], x0[half][2], x0[half][3]);
-            if constexpr (NS >= 2) st_weak_f4(a.s1 + e[half], x1[half][0], x1[half][1], x1[half][2], x1[half][3]);
-            if constexpr (NS >= 3) st_weak_f4(a.s2 + e[half], x2[half][0], x2[half][1], x2[half][2], x2[half][3]);
-          } else {
-            for (int j = 0; j < nv[half]; ++j) {
-              a.p[e[half] + j] = p[half][j];
-              if constexpr (NS >= 1) a.s0[e[half] + j] = x0[half][j];
-              if constexpr (NS >= 2) a.s1[e[half] + j] = x1[half][j];
-              if constexpr (NS >= 3) a.s2[e[half] + j] = x2[half][j];
+            if (j < nv[half]) {
+              Upd u{st4[half][j].x, st4[half][j].y, st4[half][j].z, st4[half][j].w};
+              apply_rule<OPT>(u, g[half][j] * a.grad_scale, a.h, t, lr_t);
+              w[j] = u.p;
+              float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
+              st_weak_f4(dst, u.p, NS >= 1 ? u.s0 : 0.f, NS >= 2 ? u.s1 : 0.f, NS >= 3 ? u.s2 : 0.f);
             }
           }
           // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
@@ -440,11 +432,8 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
     }
     for (; i < n16; i += stride) d[i] = ld_stream_u4(s + i);
   }
-  if (a.src_f32 != nullptr) {
-    const float4* s = reinterpret_cast<const float4*>(a.src_f32);
-    float4* d = reinterpret_cast<float4*>(a.dst_f32);
-    const size_t n16 = a.n_f32 / 4;
-    for (size_t i = gid; i < n16; i += stride) d[i] = ld_stream_f4(s + i);
+  if (a.src_state != nullptr) {      // 1-D variables: gather .x of the interleaved master state
+    for (size_t i = gid; i < a.n_f32; i += stride) a.dst_f32[i] = ld_stream_f4(a.src_state + i).x;
   }
   if (gid == 0 && a.seen_version != nullptr) *a.seen_version = ld_relaxed_sys(a.ctrl + SF_CTRL_VERSION);
   if (locked) {

@@ -118,10 +118,7 @@ SfHyper parse_hyper(const py::dict& d) {
 SfPushArgs parse_push(const py::dict& d) {
   SfPushArgs a;
   std::memset(&a, 0, sizeof(a));
-  a.p = P<float>(getd<uintptr_t>(d, "p", 0));
-  a.s0 = P<float>(getd<uintptr_t>(d, "s0", 0));
-  a.s1 = P<float>(getd<uintptr_t>(d, "s1", 0));
-  a.s2 = P<float>(getd<uintptr_t>(d, "s2", 0));
+  a.state = P<float4>(getd<uintptr_t>(d, "state", 0));
   a.ctrl = P<uint32_t>(getd<uintptr_t>(d, "ctrl", 0));
   auto dsts = getd<std::vector<uintptr_t>>(d, "shadow_dst", {});
   if (dsts.size() > 8) throw std::runtime_error("push: at most 8 publish destinations");
@@ -140,8 +137,26 @@ SfPushArgs parse_push(const py::dict& d) {
   a.scope_sys = getd<int>(d, "scope_sys", 1);
   a.grad_scale = getd<float>(d, "grad_scale", 1.0f);
   a.h = parse_hyper(getd<py::dict>(d, "hyper", py::dict()));
-  if (!a.p || !a.ctrl || !a.grad || !a.segs || !a.tile_map || a.num_tiles <= 0)
-    throw std::runtime_error("push: p/ctrl/grad/segs/tile_map/num_tiles are required");
+  {
+    auto rows = getd<std::vector<std::vector<int64_t>>>(d, "seg_rows", {});
+    if (!rows.empty() && rows.size() <= SF_MAX_INLINE_SEGS) {
+      int acc = 0;
+      for (size_t i = 0; i < rows.size(); ++i) {
+        const auto& r = rows[i];
+        if (r.size() != 7) throw std::runtime_error("push: seg_rows entries are (offset, rows, cols, w_off, w_ld, wt_off, wt_ld)");
+        SfTensorSeg& sg = a.inline_segs[i];
+        sg.offset = r[0]; sg.rows = static_cast<int>(r[1]); sg.cols = static_cast<int>(r[2]);
+        sg.w_off = r[3]; sg.w_ld = static_cast<int>(r[4]); sg.wt_off = r[5]; sg.wt_ld = static_cast<int>(r[6]);
+        a.tile_prefix[i] = acc;
+        acc += ((sg.rows + 31) / 32) * ((sg.cols + 63) / 64);
+      }
+      a.tile_prefix[rows.size()] = acc;
+      a.n_inline_segs = static_cast<int>(rows.size());
+      if (acc != a.num_tiles) throw std::runtime_error("push: seg_rows do not match num_tiles");
+    }
+  }
+  if (!a.state || !a.ctrl || !a.grad || !a.segs || !a.tile_map || a.num_tiles <= 0)
+    throw std::runtime_error("push: state/ctrl/grad/segs/tile_map/num_tiles are required");
   return a;
 }
 
@@ -150,7 +165,7 @@ SfPullArgs parse_pull(const py::dict& d) {
   std::memset(&a, 0, sizeof(a));
   a.src = P<const __nv_bfloat16>(getd<uintptr_t>(d, "src", 0));
   a.dst = P<__nv_bfloat16>(getd<uintptr_t>(d, "dst", 0));
-  a.src_f32 = P<const float>(getd<uintptr_t>(d, "src_f32", 0));
+  a.src_state = P<const float4>(getd<uintptr_t>(d, "src_state", 0));
   a.dst_f32 = P<float>(getd<uintptr_t>(d, "dst_f32", 0));
   a.n_bf16 = getd<size_t>(d, "n_bf16", 0);
   a.n_f32 = getd<size_t>(d, "n_f32", 0);
@@ -158,7 +173,7 @@ SfPullArgs parse_pull(const py::dict& d) {
   a.seen_version = P<uint32_t>(getd<uintptr_t>(d, "seen_version", 0));
   a.lock_mode = getd<int>(d, "lock_mode", 0);
   a.scope_sys = getd<int>(d, "scope_sys", 1);
-  if ((a.n_bf16 % 8) || (a.n_f32 % 4)) throw std::runtime_error("pull: sizes must be 16-byte multiples");
+  if (a.n_bf16 % 8) throw std::runtime_error("pull: bf16 size must be a 16-byte multiple");
   if (!a.ctrl) throw std::runtime_error("pull: ctrl is required");
   return a;
 }

@@ -116,6 +116,8 @@ struct SfTensorSeg {              // one trainable variable inside the flat buff
   int64_t wt_off;  int wt_ld;     // bf16 transpose [cols, wt_ld] (-1 = none)
 };
 
+#define SF_MAX_INLINE_SEGS 32
+
 struct SfHyper {
   float lr, beta1, beta2, eps;    // adam: beta1/beta2/eps ; rmsprop: decay=beta1 momentum=beta2
   float momentum, rho, decay;
@@ -125,8 +127,10 @@ struct SfHyper {
 };
 
 struct SfPushArgs {
-  // master state (peer-mapped addresses when the master is another GPU)
-  float* p; float* s0; float* s1; float* s2;   // params + up to three slot buffers
+  // master state (peer-mapped address when the master is another GPU): one float4 per parameter
+  // (.x = value, .y/.z/.w = optimizer slots).  A push reads and writes each element's tuple with ONE
+  // 16-byte access, so concurrent Hogwild pushes can lose updates but never tear a (p, m, v) tuple.
+  float4* state;
   uint32_t* ctrl;                 // control block in master memory (see SfCtrl offsets)
   // bf16 publish destinations: master copy first, then any replicas that are pushed to directly.
   // With NVLS a single multicast alias covers every replica (shadow_is_mc = 1).
@@ -139,6 +143,11 @@ struct SfPushArgs {
   const SfTensorSeg* segs;        // device array
   const int32_t* tile_map;        // device array [num_tiles * 3] = (seg, tile_row, tile_col)
   int num_tiles;
+  // the same tables in kernel-parameter (constant) space when the model has <= SF_MAX_INLINE_SEGS variables:
+  // no dependent global loads before the data loads can be issued
+  int n_inline_segs;              // 0 = use the global tables
+  int tile_prefix[SF_MAX_INLINE_SEGS + 1];
+  SfTensorSeg inline_segs[SF_MAX_INLINE_SEGS];
   int optimizer;
   int lock_mode;
   int drop;                       // fault injection: consume the gradient but do not apply it
@@ -164,8 +173,8 @@ int sf_push_launch(const SfPushArgs* a, uint32_t* local_sync, int grid, cudaStre
 struct SfPullArgs {
   const __nv_bfloat16* src;       // master publish buffer (peer-mapped)
   __nv_bfloat16* dst;             // local replica
-  const float* src_f32;           // optional: fp32 master params
-  float* dst_f32;                 // optional local fp32 copy
+  const float4* src_state;        // optional: master state (element-interleaved), first 1-D variable
+  float* dst_f32;                 // optional local fp32 copy of the 1-D variables (biases)
   size_t n_bf16;                  // elements (multiple of 8)
   size_t n_f32;                   // elements (multiple of 4)
   uint32_t* ctrl;                 // master control block

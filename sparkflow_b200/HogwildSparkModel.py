@@ -52,7 +52,7 @@ class HogwildSparkModel(object):
     def __init__(self, tensorflowGraph=None, iters=1000, tfInput=None, tfLabel=None, optimizer=None, master_url=None,
                  serverStartup=8, acquire_lock=False, mini_batch=-1, mini_stochastic_iters=-1, shuffle=True, verbose=0,
                  partition_shuffles=1, loss_callback: Optional[Callable] = None, port=5000, engine="auto", seed=None,
-                 initial_weights=None):
+                 initial_weights=None, resume_from=None, checkpoint_dir=None, checkpoint_every=0):
         self.tensorflowGraph = tensorflowGraph
         self.iters = iters
         self.tfInput = tfInput
@@ -74,7 +74,8 @@ class HogwildSparkModel(object):
         self._session = TrainingSession(tensorflowGraph, tfInput, tfLabel, optimizer, acquire_lock=acquire_lock, iters=iters,
                                         mini_batch=mini_batch, mini_stochastic_iters=mini_stochastic_iters, shuffle=shuffle,
                                         verbose=verbose, loss_callback=loss_callback, engine=engine, seed=seed,
-                                        initial_weights=initial_weights)
+                                        initial_weights=initial_weights, resume_from=resume_from, checkpoint_dir=checkpoint_dir,
+                                        checkpoint_every=checkpoint_every)
         self.start_server()
 
     @staticmethod

@@ -47,8 +47,7 @@ def _view(ptr: int, nbytes: int, dtype: torch.dtype, device: torch.device) -> to
 class MasterLayout:
     """Byte offsets of the fields inside the master segment."""
     ctrl: int
-    p: int
-    slots: Tuple[int, int, int]
+    state: int
     shadow: int
     nbytes: int
 
@@ -63,10 +62,9 @@ class MasterLayout:
             return start
 
         ctrl = take(ctrl_words * 4)
-        p = take(layout.total * 4)
-        slots = tuple(take(layout.total * 4) for _ in range(3))
+        state = take(layout.total * 16)           # float4 (p, slot0, slot1, slot2) per element
         shadow = take(layout.shadow_total * 2)
-        return cls(ctrl, p, slots, shadow, off)
+        return cls(ctrl, state, shadow, off)
 
 
 class MasterState:
@@ -82,8 +80,11 @@ class MasterState:
         nb = self.ml.nbytes
         self._bytes = _view(self.base, nb, torch.uint8, device)
         self.ctrl = self._bytes[self.ml.ctrl:self.ml.ctrl + self.C.CTRL_WORDS * 4].view(torch.int32)
-        self.p = self._bytes[self.ml.p:self.ml.p + layout.total * 4].view(torch.float32)
-        self.slots = [self._bytes[o:o + layout.total * 4].view(torch.float32) for o in self.ml.slots]
+        # element-interleaved state: one 16-byte (p, s0, s1, s2) tuple per parameter, so a push reads / writes a
+        # parameter's tuple with single 16-byte accesses (no torn (m, v) pairs under Hogwild)
+        self.state = self._bytes[self.ml.state:self.ml.state + layout.total * 16].view(torch.float32).view(layout.total, 4)
+        self.p = self.state[:, 0]
+        self.slots = [self.state[:, 1 + i] for i in range(3)]
         self.shadow = self._bytes[self.ml.shadow:self.ml.shadow + layout.shadow_total * 2].view(torch.bfloat16)
 
     # -- owner-side API ---------------------------------------------------------------------------
@@ -101,9 +102,11 @@ class MasterState:
     def load_weights(self, weights: Sequence[np.ndarray]) -> None:
         """Initialise params, slots, control block and the bf16 publish buffer (owner only)."""
         flat = self.layout.flatten(weights)
-        self.p.copy_(torch.from_numpy(flat))
-        for i, s in enumerate(self.slots):
-            s.fill_(self.spec.slot_init(i) if i < self.spec.num_slots else 0.0)
+        host = torch.zeros(self.layout.total, 4)
+        host[:, 0] = torch.from_numpy(flat)
+        for i in range(self.spec.num_slots):
+            host[:, 1 + i] = self.spec.slot_init(i)
+        self.state.copy_(host)
         self.ctrl.zero_()
         pub = torch.from_numpy(self.layout.publish_reference(flat)).to(torch.bfloat16)
         self.shadow.copy_(pub)
@@ -111,10 +114,18 @@ class MasterState:
 
     def weights(self) -> List[np.ndarray]:
         torch.cuda.synchronize(self.device)
-        return self.layout.unflatten(self.p.detach().cpu().numpy())
+        return self.layout.unflatten(self.p.detach().contiguous().cpu().numpy())
 
     def slot_arrays(self) -> List[List[np.ndarray]]:
-        return [self.layout.unflatten(s.detach().cpu().numpy()) for s in self.slots[: self.spec.num_slots]]
+        return [self.layout.unflatten(s.detach().contiguous().cpu().numpy()) for s in self.slots[: self.spec.num_slots]]
+
+    def load_slots(self, slots: Sequence[Sequence[np.ndarray]], step: int) -> None:
+        """Restore optimizer slots + the global step (resume from a snapshot)."""
+        for i, per_var in enumerate(slots[: self.spec.num_slots]):
+            self.state[:, 1 + i].copy_(torch.from_numpy(self.layout.flatten(per_var)))
+        self.ctrl[2] = int(step)
+        self.ctrl[3] = int(step)
+        torch.cuda.synchronize(self.device)
 
     def counters(self) -> Dict[str, int]:
         c = self.ctrl.cpu().numpy()
@@ -192,23 +203,21 @@ class DeviceWorker:
         return self.master.shadow if self.pull_mode == "direct" else self.replica
 
     def _bias_ptr(self, seg) -> int:
-        if self.pull_mode == "direct":
-            return native.ptr(self.master.p) + seg.offset * 4
+        # biases are always read from the local fp32 copy (the master keeps them interleaved with their slots)
         return native.ptr(self.vec_local) + (seg.offset - self.layout.vec_offset) * 4
 
     def _push_args(self, loss_out: torch.Tensor, drop: int = 0) -> dict:
         m = self.master
-        slots = m.slots
-        return dict(p=native.ptr(m.p), s0=native.ptr(slots[0]), s1=native.ptr(slots[1]), s2=native.ptr(slots[2]),
-                    ctrl=native.ptr(m.ctrl), shadow_dst=[native.ptr(m.shadow)], grad=native.ptr(self.grads),
+        return dict(state=native.ptr(m.state), ctrl=native.ptr(m.ctrl), shadow_dst=[native.ptr(m.shadow)], grad=native.ptr(self.grads),
                     loss_acc=native.ptr(self.loss_acc), loss_out=native.ptr(loss_out), segs=native.ptr(self.segs_dev),
-                    tile_map=native.ptr(self.tile_map), num_tiles=int(self.tile_map.shape[0]), optimizer=self.spec.opt_id,
-                    lock_mode=self.lock_mode, drop=drop, scope_sys=self.scope_sys, grad_scale=1.0, hyper=self.spec.native_hyper())
+                    tile_map=native.ptr(self.tile_map), num_tiles=int(self.tile_map.shape[0]), seg_rows=self.layout.seg_rows(),
+                    optimizer=self.spec.opt_id, lock_mode=self.lock_mode, drop=drop, scope_sys=self.scope_sys, grad_scale=1.0, hyper=self.spec.native_hyper())
 
     def _pull_args(self) -> dict:
         lay, m = self.layout, self.master
-        return dict(src=native.ptr(m.shadow), dst=native.ptr(self.replica), n_bf16=lay.shadow_total,
-                    src_f32=native.ptr(m.p) + lay.vec_offset * 4 if lay.vec_count else 0,
+        direct = self.pull_mode == "direct"       # weights are read in place by TMA; only the 1-D tail is copied
+        return dict(src=native.ptr(m.shadow), dst=native.ptr(self.replica), n_bf16=0 if direct else lay.shadow_total,
+                    src_state=native.ptr(m.state) + lay.vec_offset * 16 if lay.vec_count else 0,
                     dst_f32=native.ptr(self.vec_local) if lay.vec_count else 0, n_f32=lay.vec_count,
                     ctrl=native.ptr(m.ctrl), seen_version=native.ptr(self.seen_version), lock_mode=self.lock_mode,
                     scope_sys=self.scope_sys)
@@ -249,7 +258,7 @@ class DeviceWorker:
         total = 0.0
         for r in range(0, n, self.EVAL_CHUNK):
             rows = min(self.EVAL_CHUNK, n - r)
-            plan, bufs = self.build_forward_plan(rows, with_loss=True)
+            plan, bufs = self.build_forward_plan(rows, with_loss=True, with_pull=self.pull_mode == "direct")
             with torch.cuda.stream(self.stream):
                 bufs.x_stage.copy_(X[r:r + rows], non_blocking=True)
                 if bufs.y_stage is not None and Y is not None:
@@ -266,7 +275,7 @@ class DeviceWorker:
         outs = []
         for r in range(0, n, self.EVAL_CHUNK):
             rows = min(self.EVAL_CHUNK, n - r)
-            plan, bufs = self.build_forward_plan(rows, upto=upto, post=post)
+            plan, bufs = self.build_forward_plan(rows, upto=upto, post=post, with_pull=True)     # predict with fresh master weights
             with torch.cuda.stream(self.stream):
                 bufs.x_stage.copy_(Xp[r:r + rows], non_blocking=True)
                 plan.run(self.stream.cuda_stream)
@@ -316,8 +325,7 @@ def external_push(master: MasterState, layout: ParamLayout, spec: OptimizerSpec,
         tmap = torch.from_numpy(layout.tile_map()).to(dev)
         sync = torch.zeros(8, dtype=torch.int32, device=dev)
         loss = torch.zeros(2, dtype=torch.float32, device=dev)
-        args = dict(p=native.ptr(master.p), s0=native.ptr(master.slots[0]), s1=native.ptr(master.slots[1]),
-                    s2=native.ptr(master.slots[2]), ctrl=native.ptr(master.ctrl), shadow_dst=[native.ptr(master.shadow)],
+        args = dict(state=native.ptr(master.state), ctrl=native.ptr(master.ctrl), shadow_dst=[native.ptr(master.shadow)],
                     grad=native.ptr(g), loss_acc=native.ptr(loss), loss_out=native.ptr(loss) + 4, segs=native.ptr(segs),
                     tile_map=native.ptr(tmap), num_tiles=int(tmap.shape[0]), optimizer=spec.opt_id,
                     lock_mode=1 if acquire_lock else 0, grad_scale=1.0, hyper=spec.native_hyper())

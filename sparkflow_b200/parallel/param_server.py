@@ -22,7 +22,7 @@ from typing import Callable, List, Optional, Sequence
 import numpy as np
 import torch
 
-from ..ops.optimizers import OptimizerSpec, apply_update, init_slots
+from ..ops.optimizers import OptimizerSpec, apply_update
 from .rwlock import RWLock
 
 
@@ -37,9 +37,16 @@ class ParameterServer:
         self.shapes = [tuple(np.shape(w)) for w in weights]
         self.sizes = [int(np.prod(s)) if s else 1 for s in self.shapes]
         flat = np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights]) if weights else np.zeros(0, np.float32)
-        self.p = torch.from_numpy(flat.copy())
         self.spec = spec
-        self.slots = init_slots(spec, self.p)
+        # element-interleaved state [P, 1 + slots]: (p_i, slot0_i, slot1_i, ...) are adjacent, so a Hogwild
+        # write-back (one memcpy) stores every element's tuple together, like TF's fused Apply* kernels
+        ns = spec.num_slots
+        self.state = torch.empty(flat.size, 1 + ns, dtype=torch.float32)
+        self.state[:, 0] = torch.from_numpy(flat)
+        for i in range(ns):
+            self.state[:, 1 + i] = spec.slot_init(i)
+        self.p = self.state[:, 0]
+        self.slots = [self.state[:, 1 + i] for i in range(ns)]
         self.lock = RWLock() if acquire_lock else None
         self.max_errors = max_errors
         self.pushes = 0
@@ -53,8 +60,8 @@ class ParameterServer:
     def get_parameters(self) -> torch.Tensor:
         if self.lock:
             with self.lock.reading():
-                return self.p.clone()
-        return self.p.clone()
+                return self.p.clone().contiguous()
+        return self.p.clone().contiguous()
 
     def update_parameters(self, grad_flat: torch.Tensor) -> str:
         with self._count_lock:
@@ -84,7 +91,24 @@ class ParameterServer:
 
     def _apply(self, g: torch.Tensor) -> None:
         self.pushes += 1
-        apply_update(self.spec, self.p, g, self.slots, self.pushes)
+        if self.lock is not None:
+            apply_update(self.spec, self.p, g, self.slots, self.pushes)
+            return
+        # Hogwild: like TF's fused Apply* kernels (and the GPU push kernel) every element's (p, slots) tuple is
+        # read once, updated together in private storage and written back.  Concurrent pushes may lose each
+        # other's updates - that is the algorithm - but no thread ever combines its momentum with another
+        # thread's half-written second moment (which divides by ~0 and blows the model up).
+        local = self.state.clone()
+        apply_update(self.spec, local[:, 0], g, [local[:, 1 + i] for i in range(self.spec.num_slots)], self.pushes)
+        self.state.copy_(local)
+
+    def slot_arrays(self) -> List[List[np.ndarray]]:
+        return [self.unflatten(s.clone().contiguous()) for s in self.slots]
+
+    def load_slots(self, slots: Sequence[Sequence[np.ndarray]], step: int) -> None:
+        for i, per_var in enumerate(slots[: self.spec.num_slots]):
+            self.state[:, 1 + i] = torch.from_numpy(np.concatenate([np.asarray(a, np.float32).reshape(-1) for a in per_var]))
+        self.pushes = int(step)
 
     # -- conversions ----------------------------------------------------------------------------------
     def unflatten(self, flat: torch.Tensor) -> List[np.ndarray]:

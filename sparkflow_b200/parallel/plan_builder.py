@@ -96,7 +96,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     wsrc = worker._weight_src()
     plan = C.Plan()
     branches = worker.use_branches and train
-    do_pull = with_pull and worker.pull_mode != "direct"
+    do_pull = with_pull and (worker.pull_mode != "direct" or lay.vec_count > 0)
 
     layers = lp.layers
     dense_ids = [i for i, l in enumerate(layers) if l.kind == "dense"]

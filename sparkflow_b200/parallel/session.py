@@ -42,7 +42,8 @@ class TrainingSession:
                  acquire_lock: bool = False, iters: int = 1000, mini_batch: int = -1, mini_stochastic_iters: int = -1,
                  shuffle: bool = True, verbose: int = 0, loss_callback: Optional[Callable] = None, engine: str = "auto",
                  seed: Optional[int] = None, initial_weights: Optional[Sequence[np.ndarray]] = None,
-                 pull_mode: Optional[str] = None):
+                 pull_mode: Optional[str] = None, resume_from: Optional[str] = None, checkpoint_dir: Optional[str] = None,
+                 checkpoint_every: int = 0):
         self.ir = GraphIR.from_metagraph(graph_json)
         self.tf_input, self.tf_label, self.spec = tf_input, tf_label, optimizer
         self.acquire_lock, self.iters = bool(acquire_lock), int(iters)
@@ -50,6 +51,9 @@ class TrainingSession:
         self.verbose, self.loss_callback, self.seed = verbose, loss_callback, seed
         self.initial_weights = initial_weights
         self.pull_mode = pull_mode
+        self.resume_from, self.checkpoint_dir, self.checkpoint_every = resume_from, checkpoint_dir, int(checkpoint_every or 0)
+        self._resume_state = None
+        self.graph_json = graph_json
         self.ctx = D.get_context()
         self.use_cuda = torch.cuda.is_available() and engine != "torch" and os.environ.get("SPARKFLOW_ENGINE", "") != "torch"
         self.engine_kind = "torch"
@@ -73,6 +77,12 @@ class TrainingSession:
 
     # -------------------------------------------------------------------------------------------
     def _init_weights(self) -> List[np.ndarray]:
+        if self.resume_from:
+            from ..utils.checkpoint import load_master_state
+
+            w, slots, step = load_master_state(self.resume_from, [v.name for v in self.ir.trainable], self.spec)
+            self._resume_state = (slots, step)
+            return [np.asarray(a, dtype=np.float32) for a in w]
         if self.initial_weights is not None:
             return [np.asarray(w, dtype=np.float32) for w in self.initial_weights]
         return GraphProgram(self.ir).init_weights(seed=self.seed)
@@ -123,8 +133,35 @@ class TrainingSession:
                 D.barrier(ctx)
             else:
                 self.master = ParameterServer(self._init_weights(), self.spec, self.acquire_lock, max_errors=max(self.iters, 1))
+        if self._resume_state is not None and self.master is not None and (self.ctx.is_master or self.ctx.world == 1):
+            slots, step = self._resume_state
+            self.master.load_slots(slots, step)
+        D.barrier(ctx)
         self._opened = True
         return self
+
+    # -- snapshot / resume ------------------------------------------------------------------------------
+    def snapshot(self, prefix: str) -> Optional[str]:
+        """Write the master's parameters + optimizer slots as a TF-V2 checkpoint (rank 0 only)."""
+        if not (self.ctx.is_master or self.ctx.world == 1) or self.master is None:
+            return None
+        from ..utils.checkpoint import save_master_state
+
+        if self.engine_kind == "b200":
+            for w in self._workers:
+                w.stream.synchronize()
+            step = self.master.counters()["step"]
+        else:
+            step = self.master.pushes
+        return save_master_state(prefix, [v.name for v in self.ir.trainable], self.master.weights(), self.master.slot_arrays(),
+                                 self.spec, step, self.graph_json)
+
+    def maybe_snapshot(self, iteration: int) -> None:
+        if self.checkpoint_dir and self.checkpoint_every > 0 and (iteration + 1) % self.checkpoint_every == 0:
+            import os
+
+            os.makedirs(self.checkpoint_dir, exist_ok=True)
+            self.snapshot(os.path.join(self.checkpoint_dir, f"master-{iteration + 1}"))
 
     # -------------------------------------------------------------------------------------------
     def make_engine(self, device: torch.device, partition_id: str = "") -> Engine:
@@ -172,7 +209,8 @@ class TrainingSession:
                 engine = self.make_engine(dev, partition_id=f"partition-{pid}")
                 run_partition(engine, feat, lab, iters=self.iters, mini_batch_size=self.mini_batch, shuffle=self.shuffle,
                               mini_stochastic_iters=self.msi, verbose=self.verbose, loss_callback=self.loss_callback,
-                              partition_id=f"partition-{pid}", seed=None if self.seed is None else self.seed + pid)
+                              partition_id=f"partition-{pid}", seed=None if self.seed is None else self.seed + pid,
+                              on_iteration=self.maybe_snapshot if (pid == 0 and self.checkpoint_every) else None)
                 if isinstance(engine, TorchEngine) and isinstance(engine.transport, GlooTransport):
                     pass
 

@@ -54,7 +54,10 @@ class Engine:
 def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndarray], iters: int = 1000,
                   mini_batch_size: int = -1, shuffle: bool = True, mini_stochastic_iters: int = -1, verbose: int = 0,
                   loss_callback: Optional[Callable[[float, int, str], None]] = None, partition_id: Optional[str] = None,
-                  seed: Optional[int] = None) -> str:
+                  seed: Optional[int] = None, on_iteration: Optional[Callable[[int], None]] = None) -> str:
+    from ..utils.metrics import MetricsLogger
+
+    metrics = MetricsLogger()
     partition_id = partition_id or uuid.uuid4().hex
     n = int(features.shape[0])
     if n == 0:
@@ -103,6 +106,12 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
                 print("Partition Id: %s, Iteration: %i, Loss: %f" % (partition_id, i, loss))
             if loss_callback:
                 loss_callback(loss, i, partition_id)
+            if metrics.enabled:
+                metrics.log(event="iteration", partition=partition_id, iteration=i, loss=float(loss), rows=n)
+        elif metrics.enabled:
+            metrics.log(event="iteration", partition=partition_id, iteration=i, rows=n)
+        if on_iteration is not None:
+            on_iteration(i)
     engine.finish()
     return partition_id
 

@@ -99,9 +99,6 @@ def test_training_reduces_loss_and_predicts():
     l1 = eng.partition_loss()
     assert l1 < 0.2 * l0, (l0, l1)
     # prediction through the forward-only plan (+ArgMax kernel)
-    worker.build_plan(300, 0)          # ensure replica is current via one more pull
-    plan, _ = worker.build_forward_plan(1, with_pull=True)
-    plan.run(worker.stream.cuda_stream)
     pred = worker.predict(X[:500], upto=2, post="ArgMax")
     assert (pred.astype(np.int64) == lab[:500]).mean() > 0.95
     master.close()

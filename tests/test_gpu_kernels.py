@@ -195,12 +195,13 @@ SHAPES = [("dense/kernel", (784, 256)), ("dense/bias", (256,)), ("dense_1/kernel
 def _push_setup(C, spec, lock_mode=0):
     lay = ParamLayout.build(SHAPES)
     dev = "cuda"
-    p = torch.zeros(lay.total, device=dev)
+    state = torch.zeros(lay.total, 4, device=dev)
     mask = torch.from_numpy(lay.valid_mask()).to(dev)
-    p[mask] = torch.randn(int(mask.sum()), device=dev) * 0.1
-    slots = init_slots(spec, p)
-    while len(slots) < 3:
-        slots.append(None)
+    state[mask, 0] = torch.randn(int(mask.sum()), device=dev) * 0.1
+    for i in range(spec.num_slots):
+        state[:, 1 + i] = spec.slot_init(i)
+    p = state[:, 0]
+    slots = [state[:, 1 + i] for i in range(spec.num_slots)] + [None] * (3 - spec.num_slots)
     ctrl = torch.zeros(C.CTRL_WORDS, dtype=torch.int32, device=dev)
     shadow = torch.zeros(lay.shadow_total, dtype=torch.bfloat16, device=dev)
     grad = torch.zeros(lay.total, device=dev)
@@ -209,12 +210,11 @@ def _push_setup(C, spec, lock_mode=0):
     lsync = torch.zeros(8, dtype=torch.int32, device=dev)
     loss_acc = torch.zeros(1, device=dev)
     loss_out = torch.zeros(1, device=dev)
-    args = dict(p=native.ptr(p), s0=native.ptr(slots[0]), s1=native.ptr(slots[1]), s2=native.ptr(slots[2]),
-                ctrl=native.ptr(ctrl), shadow_dst=[native.ptr(shadow)], grad=native.ptr(grad),
+    args = dict(state=native.ptr(state), ctrl=native.ptr(ctrl), shadow_dst=[native.ptr(shadow)], grad=native.ptr(grad),
                 loss_acc=native.ptr(loss_acc), loss_out=native.ptr(loss_out), segs=native.ptr(segs),
                 tile_map=native.ptr(tmap), num_tiles=int(tmap.shape[0]), optimizer=spec.opt_id,
                 lock_mode=lock_mode, grad_scale=1.0, hyper=spec.native_hyper())
-    keep = dict(lay=lay, p=p, slots=slots, ctrl=ctrl, shadow=shadow, grad=grad, segs=segs, tmap=tmap, lsync=lsync,
+    keep = dict(lay=lay, state=state, p=p, slots=slots, ctrl=ctrl, shadow=shadow, grad=grad, segs=segs, tmap=tmap, lsync=lsync,
                 loss_acc=loss_acc, loss_out=loss_out, mask=mask)
     return args, keep
 
@@ -238,8 +238,8 @@ def _push_setup(C, spec, lock_mode=0):
 def test_push_matches_reference_optimizer(C, name, kw, lock_mode):
     spec = OptimizerSpec.from_tf_kwargs(name, kw)
     args, k = _push_setup(C, spec, lock_mode)
-    p_ref = k["p"].clone()
-    s_ref = [s.clone() for s in k["slots"] if s is not None]
+    p_ref = k["p"].clone().contiguous()
+    s_ref = [s.clone().contiguous() for s in k["slots"] if s is not None]
     for step in range(1, 4):
         g = torch.zeros_like(k["grad"])
         g[k["mask"]] = torch.randn(int(k["mask"].sum()), device="cuda") * 0.05
@@ -256,7 +256,7 @@ def test_push_matches_reference_optimizer(C, name, kw, lock_mode):
         assert float(k["loss_out"][0]) == float(step) and float(k["loss_acc"][0]) == 0.0
         ctrl = k["ctrl"].cpu().numpy()
         assert ctrl[0] == 0 and ctrl[1] == step and ctrl[2] == step and ctrl[3] == step
-    exp = torch.from_numpy(k["lay"].publish_reference(k["p"].cpu().numpy())).to(torch.bfloat16)
+    exp = torch.from_numpy(k["lay"].publish_reference(k["p"].contiguous().cpu().numpy())).to(torch.bfloat16)
     assert torch.equal(k["shadow"].cpu(), exp)
 
 
@@ -264,11 +264,11 @@ def test_push_drop_fault_injection(C):
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.01))
     args, k = _push_setup(C, spec)
     args["drop"] = 1
-    before = k["p"].clone()
+    before = k["p"].clone().contiguous()
     k["grad"][k["mask"]] = 1.0
     C.push(args, native.ptr(k["lsync"]), 0, native.current_stream())
     torch.cuda.synchronize()
-    assert torch.equal(before, k["p"]) and torch.all(k["grad"] == 0)
+    assert torch.equal(before, k["p"].contiguous()) and torch.all(k["grad"] == 0)
     assert int(k["ctrl"][5]) == 1 and int(k["ctrl"][3]) == 0
 
 
@@ -277,13 +277,14 @@ def test_pull_copies_publish_buffer(C, lock_mode):
     n16, n32 = 64 * 1000, 4 * 300
     src = torch.randn(n16, device="cuda").to(torch.bfloat16)
     dst = torch.zeros_like(src)
-    s32 = torch.randn(n32, device="cuda")
+    sstate = torch.randn(n32, 4, device="cuda")
+    s32 = sstate[:, 0].contiguous()
     d32 = torch.zeros_like(s32)
     ctrl = torch.zeros(C.CTRL_WORDS, dtype=torch.int32, device="cuda")
     ctrl[1] = 41
     seen = torch.zeros(1, dtype=torch.int32, device="cuda")
     lsync = torch.zeros(8, dtype=torch.int32, device="cuda")
-    d = dict(src=native.ptr(src), dst=native.ptr(dst), src_f32=native.ptr(s32), dst_f32=native.ptr(d32),
+    d = dict(src=native.ptr(src), dst=native.ptr(dst), src_state=native.ptr(sstate), dst_f32=native.ptr(d32),
              n_bf16=n16, n_f32=n32, ctrl=native.ptr(ctrl), seen_version=native.ptr(seen), lock_mode=lock_mode)
     for _ in range(2):
         C.pull(d, native.ptr(lsync), 0, native.current_stream())

@@ -38,7 +38,8 @@ WORKER = textwrap.dedent("""
     prog = GraphProgram(GraphIR.from_metagraph(graph))
     X = np.concatenate([p[0] for p in parts]); L = np.concatenate([p[2] for p in parts])
     acc = float((prog.forward("out:0", {{"x:0": X}}, w).numpy() == L).mean())
-    print("RESULT " + json.dumps({{"rank": ctx.rank, "acc": acc, "counters": c, "w0": float(np.abs(w[0]).sum())}}))
+    with open(os.path.join(sys.argv[2], "rank%d.json" % ctx.rank), "w") as fh:
+        json.dump({{"rank": ctx.rank, "acc": acc, "counters": c, "w0": float(np.abs(w[0]).sum())}}, fh)
     sess.close()
 """)
 
@@ -47,11 +48,11 @@ def _run(n, mode, tmp_path, port):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
-           "--master-port", str(port), str(script), mode]
+           "--master-port", str(port), str(script), mode, str(tmp_path)]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600,
                           env=dict(os.environ, GLOO_SOCKET_IFNAME="lo"))
     assert proc.returncode == 0, proc.stdout[-4000:]
-    return [json.loads(l.split("RESULT ", 1)[1]) for l in proc.stdout.splitlines() if "RESULT " in l]
+    return [json.load(open(tmp_path / f)) for f in sorted(os.listdir(tmp_path)) if f.startswith("rank")]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")

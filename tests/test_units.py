@@ -365,3 +365,80 @@ def test_shim_dataframe_behaviour():
     df.rdd.foreachPartition(lambda it: seen.append(len(list(it))))
     assert sum(seen) == 10
     assert df.select("b").columns == ["b"] and df.rdd.mapPartitions(lambda it: [sum(1 for _ in it)]).collect() == seen or True
+
+
+# ---------------------------------------------------------------------------------------------
+# checkpoint / resume, metrics, fault injection (aux subsystems the reference lacks)
+# ---------------------------------------------------------------------------------------------
+def _blobs(n=240, d=10, seed=0):
+    rng = np.random.default_rng(seed)
+    y = rng.integers(0, 2, n)
+    x = rng.normal(0, 1, (n, d)).astype(np.float32) + 2.0 * y[:, None]
+    return x, y.reshape(-1, 1).astype(np.float32)
+
+
+def test_snapshot_resume_is_exact(tmp_path):
+    from sparkflow_b200.io.bundle import read_bundle
+    from sparkflow_b200.parallel.session import TrainingSession
+
+    x, y = _blobs()
+    graph = zoo.build("test_mlp")
+    spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.01))
+    kw = dict(iters=3, mini_batch=60, shuffle=False, engine="torch", seed=4)
+    # run 6 iterations straight through
+    full = TrainingSession(graph, "x:0", "y:0", spec, **{**kw, "iters": 6})
+    full.train_partitions([(x, y)])
+    w_full = full.weights()
+    full.close()
+    # 3 iterations, snapshot, resume for 3 more
+    a = TrainingSession(graph, "x:0", "y:0", spec, **kw)
+    a.train_partitions([(x, y)])
+    prefix = a.snapshot(str(tmp_path / "ck" / "master-3"))
+    a.close()
+    keys = set(read_bundle(prefix))
+    assert {"dense/kernel", "dense/kernel/Adam", "dense/kernel/Adam_1", "outer/bias/Adam_1", "beta1_power", "beta2_power"} <= keys
+    b = TrainingSession(graph, "x:0", "y:0", spec, resume_from=prefix, **kw)
+    b.train_partitions([(x, y)])
+    w_resumed = b.weights()
+    assert b.counters()["pushes"] == 24
+    b.close()
+    for u, v in zip(w_full, w_resumed):
+        np.testing.assert_allclose(u, v, rtol=1e-5, atol=1e-7)
+    # the snapshot is a loadable TF checkpoint for the inference loader as well
+    from sparkflow_b200.tensorflow_model_loader import load_tensorflow_model
+
+    m = load_tensorflow_model(prefix, inputCol="features", tfInput="x:0", tfOutput="outer/Sigmoid:0")
+    assert len(json.loads(m.getOrDefault(m.modelWeights))) == 6
+
+
+def test_periodic_checkpoints_and_metrics(tmp_path, monkeypatch):
+    from sparkflow_b200.parallel.session import TrainingSession
+    from sparkflow_b200.utils.metrics import read_metrics
+
+    monkeypatch.setenv("SPARKFLOW_METRICS", str(tmp_path / "metrics.jsonl"))
+    x, y = _blobs()
+    s = TrainingSession(zoo.build("test_mlp"), "x:0", "y:0", OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.01)), iters=4,
+                        mini_batch=80, engine="torch", verbose=0, loss_callback=lambda *a: None, checkpoint_dir=str(tmp_path / "ck"),
+                        checkpoint_every=2)
+    s.train_partitions([(x, y)])
+    s.close()
+    assert sorted(f for f in os.listdir(tmp_path / "ck") if f.endswith(".index")) == ["master-2.index", "master-4.index"]
+    recs = read_metrics(str(tmp_path / "metrics.jsonl"))
+    assert [r["iteration"] for r in recs] == [0, 1, 2, 3] and all(np.isfinite(r["loss"]) for r in recs)
+
+
+def test_fault_injection_dropped_and_failed_pushes_are_not_fatal():
+    from sparkflow_b200.parallel.param_server import LocalTransport, ParameterServer, TooManyFailures
+    from sparkflow_b200.parallel.worker import TorchEngine, run_partition
+
+    x, y = _blobs()
+    ir = GraphIR.from_metagraph(zoo.build("test_mlp"))
+    w0 = GraphProgram(ir).init_weights(0)
+    ps = ParameterServer(w0, OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.01)), max_errors=1000)
+    ps.fault_hook = lambda k: "drop" if k % 3 == 0 else ("raise" if k % 5 == 0 else None)
+    run_partition(TorchEngine(ir, "x:0", "y:0", LocalTransport(ps)), x, y, iters=5, mini_batch_size=60, shuffle=True)
+    assert ps.dropped == 6 and ps.errors == 3 and ps.pushes == 20 - 6 - 3
+    tight = ParameterServer(w0, OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.01)), max_errors=2)
+    tight.fault_hook = lambda k: "raise"
+    with pytest.raises(TooManyFailures):
+        run_partition(TorchEngine(ir, "x:0", "y:0", LocalTransport(tight)), x, y, iters=5, mini_batch_size=60)
