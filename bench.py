@@ -86,7 +86,8 @@ def run_ours(args, ctx) -> dict:
     lock = args.mode == "lock"
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001, beta1=0.9, beta2=0.999))
     sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock=lock, iters=1, mini_batch=BATCH,
-                           mini_stochastic_iters=1, shuffle=True, engine="b200", seed=1234, pull_mode=args.pull_mode).open()
+                           mini_stochastic_iters=1, shuffle=True, engine="b200", seed=1234, pull_mode=args.pull_mode,
+                           push_mode=args.push_mode).open()
     eng = sess.make_engine(dev)
     rows = max(args.partition_rows, BATCH * 2)
     x, y = _synthetic_partition(rows, seed=100 + ctx.rank)
@@ -164,7 +165,7 @@ def run_ours(args, ctx) -> dict:
         "dtype": "bf16", "data": "synthetic", "impl": "sparkflow_b200",
         "config": {"model": "simple_dnn 784-256-256-10", "global_batch": ctx.world * BATCH, "seq_len": 1,
                    "parallelism": f"async-ps dp{ctx.world} ({'rw-lock' if lock else 'hogwild'}, master on gpu0)",
-                   "optimizer": "adam(1e-3), one step per push on the master", "pull_mode": w.pull_mode,
+                   "optimizer": "adam(1e-3), one step per push on the master", "pull_mode": w.pull_mode, "push_mode": sess.push_mode,
                    "l2": "device-timed value: 256 MiB flush between steps (outside the event pairs); e2e: pinned partition "
                          f"{rows * DIMS[0] * 4 >> 20} MiB > L2, a fresh minibatch H2D every step",
                    "kernels_per_step": plan.names(), "cuda_graph": bool(w.use_graphs)},
@@ -239,6 +240,9 @@ def main() -> int:
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
     ap.add_argument("--mode", default="lock", choices=["lock", "hogwild"], help="acquire_lock=True (BASELINE config 2) or Hogwild")
     ap.add_argument("--pull-mode", default=None, choices=[None, "copy", "direct"])
+    ap.add_argument("--push-mode", default=None, choices=[None, "direct", "served"],
+                    help="direct: worker applies the optimizer on master memory over NVLink; served: mailbox + applier kernel "
+                         "on the master GPU (default: served when more than one GPU shares the master)")
     ap.add_argument("--partition-rows", type=int, default=50_100, help="rows of the pinned per-rank partition (157 MiB > L2)")
     ap.add_argument("--with-nccl-baseline", action="store_true", help="also time the NCCL baseline in the same launch")
     ap.add_argument("--python-loop", action="store_true", help="drive the e2e steps from Python instead of the native StepDriver")

@@ -59,6 +59,15 @@ template <bool SYS> __device__ __forceinline__ uint32_t lk_add_relaxed(uint32_t*
   else asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
   return old;
 }
+// fire-and-forget counter bump (no return value -> no NVLink round trip on the critical path)
+template <bool SYS> __device__ __forceinline__ void lk_red_relaxed(uint32_t* p, uint32_t x) {
+  if (SYS) asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+  else asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+}
+template <bool SYS> __device__ __forceinline__ void lk_red_release(uint32_t* p, uint32_t x) {
+  if (SYS) asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+  else asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(x) : "memory");
+}
 template <bool SYS> __device__ __forceinline__ uint32_t lk_cas_acquire(uint32_t* p, uint32_t cmp, uint32_t val) {
   uint32_t old;
   if (SYS) asm volatile("atom.acquire.sys.global.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
@@ -80,7 +89,7 @@ template <bool SYS> __device__ void rw_acquire_write(uint32_t* lock) {
     if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x401);
   }
 }
-template <bool SYS> __device__ void rw_release_write(uint32_t* lock) { lk_add_release<SYS>(lock, 0u - kLockWriter); }
+template <bool SYS> __device__ void rw_release_write(uint32_t* lock) { lk_red_release<SYS>(lock, 0u - kLockWriter); }
 template <bool SYS> __device__ void rw_acquire_read(uint32_t* lock) {
   const unsigned long long t0 = gtime_ns();
   while (true) {
@@ -95,7 +104,7 @@ template <bool SYS> __device__ void rw_acquire_read(uint32_t* lock) {
     }
   }
 }
-template <bool SYS> __device__ void rw_release_read(uint32_t* lock) { lk_add_release<SYS>(lock, 0u - 1u); }
+template <bool SYS> __device__ void rw_release_read(uint32_t* lock) { lk_red_release<SYS>(lock, 0u - 1u); }
 
 // ---- in-grid coordination on the worker's own memory --------------------------------------
 // local_sync words: 0 = grant epoch, 1 = granted value (optimizer step t), 2 = done counter,
@@ -217,49 +226,16 @@ __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc
   if (mc) multimem_st_u4(reinterpret_cast<uint4*>(dst), q);
   else asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
 }
-template <int OPT, bool SYS>
-__global__ void __launch_bounds__(kPushThreads, 1)
-push_kernel(const SfPushArgs a, uint32_t* local_sync) {
-  __shared__ uint32_t s_t;
-  __shared__ uint32_t s_epoch;
-  __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
-  TraceScope trace;
-  pdl_launch_dependents();
-  const int tid = threadIdx.x;
+// One 32x64 parameter tile: load the gradient + the master tuples, apply the optimizer rule in registers, store
+// the tuples back, publish bf16 W / W^T, zero the consumed gradient.  Shared by the worker-side push kernel
+// (master tuples over NVLink) and the master-resident applier (gradient from a worker's mailbox).
+template <int OPT>
+__device__ __forceinline__ void push_tile(const SfPushArgs& a, float* grad, int tile, const uint32_t* s_t_ptr, bool sync_for_t,
+                                          __nv_bfloat16 (*s_tr)[kTileR + 8]) {
   constexpr int NS = Slots<OPT>::n;
-  const bool locked = a.lock_mode == SF_LOCK_RW;
-  // Hogwild reads the global step count racily; it does not depend on this step's kernels, so the
-  // round trip to the master overlaps the predecessor's tail (before the programmatic-dependency wait).
-  if (!locked && tid == 0) s_t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
-  pdl_wait();
-  trace.mark();
-
-  // ---------------- acquire / step number ----------------
-  if (tid == 0) {
-    uint32_t t;
-    if (locked) {
-      const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
-      if (blockIdx.x == 0) {
-        rw_acquire_write<SYS>(a.ctrl + SF_CTRL_LOCK);
-        t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
-        local_sync[1] = t;
-        st_release_gpu(local_sync + 0, epoch + 1);
-      } else {
-        const unsigned long long t0 = gtime_ns();
-        while (ld_acquire_gpu(local_sync + 0) != epoch + 1) {
-          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x403);
-        }
-        t = local_sync[1];
-      }
-      s_epoch = epoch;
-      s_t = t;
-    }
-  }
-  if (locked) __syncthreads();      // Hogwild: nothing to wait for, loads below start immediately
+  const int tid = threadIdx.x;
   const bool mc = a.shadow_is_mc != 0;
-
-  // ---------------- tiles ----------------
-  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+  {
     int r0, c0;
     SfTensorSeg sg;
     if (a.n_inline_segs > 0) {                         // tables live in constant (parameter) space
@@ -293,10 +269,10 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       for (int j = 0; j < 4; ++j) { g[half][j] = 0.f; st4[half][j] = make_float4(0.f, 0.f, 0.f, 0.f); }
       if (nv[half] == 0) continue;
       if (vec) {
-        const float4 gv = *reinterpret_cast<const float4*>(a.grad + e[half]);
+        const float4 gv = *reinterpret_cast<const float4*>(grad + e[half]);
         g[half][0] = gv.x; g[half][1] = gv.y; g[half][2] = gv.z; g[half][3] = gv.w;
       } else {
-        for (int j = 0; j < nv[half]; ++j) g[half][j] = a.grad[e[half] + j];
+        for (int j = 0; j < nv[half]; ++j) g[half][j] = grad[e[half] + j];
       }
       if (!a.drop) {
 #pragma unroll
@@ -305,8 +281,8 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       }
     }
     // ---- step number: under the lock it was granted above; Hogwild read it at kernel entry ----
-    if (!locked && tile == static_cast<int>(blockIdx.x)) __syncthreads();     // s_t was read at kernel entry
-    const float t = static_cast<float>(s_t);
+    if (sync_for_t) __syncthreads();     // the step count was written to shared memory by thread 0
+    const float t = static_cast<float>(*s_t_ptr);
     float lr_t = a.h.lr;
     if constexpr (OPT == SF_OPT_ADAM) {
       lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
@@ -319,8 +295,8 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       float w[4] = {0.f, 0.f, 0.f, 0.f};
       if (nv[half] > 0) {
         // the gradient is consumed: zero it for the next step's accumulating epilogues
-        if (vec) *reinterpret_cast<float4*>(a.grad + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
-        else for (int j = 0; j < nv[half]; ++j) a.grad[e[half] + j] = 0.f;
+        if (vec) *reinterpret_cast<float4*>(grad + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else for (int j = 0; j < nv[half]; ++j) grad[e[half] + j] = 0.f;
         if (!a.drop) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -358,6 +334,50 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
       __syncthreads();
     }
   }
+}
+
+template <int OPT, bool SYS>
+__global__ void __launch_bounds__(kPushThreads, 1)
+push_kernel(const SfPushArgs a, uint32_t* local_sync) {
+  __shared__ uint32_t s_t;
+  __shared__ uint32_t s_epoch;
+  __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
+  TraceScope trace;
+  pdl_launch_dependents();
+  const int tid = threadIdx.x;
+  const bool locked = a.lock_mode == SF_LOCK_RW;
+  // Hogwild reads the global step count racily; it does not depend on this step's kernels, so the
+  // round trip to the master overlaps the predecessor's tail (before the programmatic-dependency wait).
+  if (!locked && tid == 0) s_t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
+  pdl_wait();
+  trace.mark();
+
+  // ---------------- acquire / step number ----------------
+  if (tid == 0) {
+    uint32_t t;
+    if (locked) {
+      const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
+      if (blockIdx.x == 0) {
+        rw_acquire_write<SYS>(a.ctrl + SF_CTRL_LOCK);
+        t = ld_relaxed_sys(a.ctrl + SF_CTRL_STEP) + 1;
+        local_sync[1] = t;
+        st_release_gpu(local_sync + 0, epoch + 1);
+      } else {
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_gpu(local_sync + 0) != epoch + 1) {
+          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x403);
+        }
+        t = local_sync[1];
+      }
+      s_epoch = epoch;
+      s_t = t;
+    }
+  }
+  if (locked) __syncthreads();      // Hogwild: nothing to wait for, loads below start immediately
+
+  // ---------------- tiles ----------------
+  for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
+    push_tile<OPT>(a, a.grad, tile, &s_t, !locked && tile == static_cast<int>(blockIdx.x), s_tr);
 
   // ---------------- completion ----------------
   __syncthreads();
@@ -373,11 +393,11 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
         *a.loss_acc = 0.f;
       }
       if (a.drop) {
-        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_DROPPED, 1u);
+        lk_red_relaxed<SYS>(a.ctrl + SF_CTRL_DROPPED, 1u);
       } else {
-        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_STEP, 1u);
-        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_PUSHES, 1u);
-        lk_add_relaxed<SYS>(a.ctrl + SF_CTRL_VERSION, 1u);
+        lk_red_relaxed<SYS>(a.ctrl + SF_CTRL_STEP, 1u);
+        lk_red_relaxed<SYS>(a.ctrl + SF_CTRL_PUSHES, 1u);
+        lk_red_relaxed<SYS>(a.ctrl + SF_CTRL_VERSION, 1u);
       }
       if (locked) {
         rw_release_write<SYS>(a.ctrl + SF_CTRL_LOCK);
@@ -401,6 +421,17 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
   trace.mark();
   const int tid = threadIdx.x;
   const bool locked = a.lock_mode == SF_LOCK_RW;
+  if (a.wait_applied != nullptr) {
+    if (tid == 0) {
+      const uint32_t want = *a.my_posted;
+      const unsigned long long t0 = gtime_ns();
+      while (static_cast<int32_t>(ld_acquire_sys(a.wait_applied) - want) < 0) {
+        __nanosleep(64);
+        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x405);
+      }
+    }
+    __syncthreads();
+  }
   if (locked) {
     if (tid == 0) {
       const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
@@ -451,6 +482,145 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
   trace.end(KID_PULL);
 }
 
+// ---------------------------------------------------------------------------
+// post: worker-side half of a served push.  local_sync[4] holds this worker's posted sequence number.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1)
+post_kernel(const SfPostArgs a, uint32_t* local_sync) {
+  __shared__ uint32_t s_seq;
+  TraceScope trace;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.mark();
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    // the mailbox may only be overwritten once the applier has consumed the previous post
+    const uint32_t posted = ld_acquire_gpu(local_sync + 4);
+    if (!a.drop) {
+      const unsigned long long t0 = gtime_ns();
+      while (static_cast<int32_t>(ld_acquire_sys(a.flags + SF_MB_APPLIED) - posted) < 0) {
+        __nanosleep(64);
+        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x406);
+      }
+    }
+    s_seq = posted;
+  }
+  __syncthreads();
+  const size_t n4 = a.n / 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  float4* g = reinterpret_cast<float4*>(a.grad);
+  float4* mb = reinterpret_cast<float4*>(a.mailbox);
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + tid; i < n4; i += stride) {
+    const float4 v = g[i];
+    g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!a.drop) st_weak_f4(reinterpret_cast<float*>(mb + i), v.x, v.y, v.z, v.w);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // release: this CTA's mailbox stores (ordered by bar.sync) become visible before the last CTA posts
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    const uint32_t prev = lk_add_release<false>(local_sync + 2, 1u);
+    if (prev == gridDim.x - 1) {
+      (void)ld_acquire_gpu(local_sync + 2);
+      local_sync[2] = 0;
+      if (a.loss_acc != nullptr) {
+        *a.loss_out = *a.loss_acc;
+        *a.loss_acc = 0.f;
+      }
+      if (!a.drop) {
+        st_release_gpu(local_sync + 4, s_seq + 1);
+        st_release_sys(a.flags + SF_MB_POSTED, s_seq + 1);
+      }
+    }
+  }
+  trace.end(KID_PUSH);
+}
+
+// ---------------------------------------------------------------------------
+// applier: persistent kernel on the master GPU.  CTA 0 is the leader: it scans the workers' POSTED flags
+// round-robin, (lock mode) takes the write lock, publishes (epoch, worker, step) to the other CTAs through
+// master-local memory, everybody updates its share of the tiles from that worker's mailbox, and the leader
+// then bumps the counters, releases the lock and acknowledges through the APPLIED flag.  Updates are applied
+// strictly one push at a time - one optimizer step per push, exactly the reference's parameter server.
+// sync words: 0 = epoch, 1 = worker (-1: exit), 2 = step, 3 = cumulative done count.
+// ---------------------------------------------------------------------------
+template <int OPT, bool SYS>
+__global__ void __launch_bounds__(kPushThreads, 1)
+applier_kernel(const SfApplierArgs a) {
+  __shared__ uint32_t s_t;
+  __shared__ int s_w;
+  __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
+  __shared__ uint32_t s_applied[8];
+  const int tid = threadIdx.x;
+  const bool leader = blockIdx.x == 0;
+  const bool locked = a.push.lock_mode == SF_LOCK_RW;
+  uint32_t epoch = 0;
+  int rr = 0;
+  if (leader && tid < 8) s_applied[tid] = (tid < a.n_workers) ? ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED) : 0u;
+  __syncthreads();
+  while (true) {
+    if (tid == 0) {
+      if (leader) {
+        int found = -1;
+        const unsigned long long t_idle = gtime_ns();
+        while (found < 0) {
+          if (*a.host_stop != 0) { found = -2; break; }
+          for (int k = 0; k < a.n_workers; ++k) {
+            const int w = (rr + k) % a.n_workers;
+            if (ld_acquire_sys(a.flags + w * SF_MB_WORDS + SF_MB_POSTED) != s_applied[w]) { found = w; break; }
+          }
+          if (found >= 0) break;
+          if (gtime_ns() - t_idle > a.idle_timeout_ns) { found = -2; break; }
+          __nanosleep(100);
+        }
+        uint32_t t = 0;
+        if (found >= 0) {
+          if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+          t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
+        }
+        a.sync[1] = static_cast<uint32_t>(found);
+        a.sync[2] = t;
+        st_release_gpu(a.sync + 0, epoch + 1);
+        s_w = found;
+        s_t = t;
+      } else {
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_gpu(a.sync + 0) != epoch + 1) {
+          __nanosleep(40);
+          if (gtime_ns() - t0 > a.idle_timeout_ns + kLockTimeoutNs) { a.sync[1] = 0xFFFFFFFEu; break; }
+        }
+        s_w = static_cast<int>(a.sync[1]);
+        s_t = a.sync[2];
+      }
+    }
+    __syncthreads();
+    ++epoch;
+    const int w = s_w;
+    if (w < 0) return;                                  // stop requested / idle timeout
+    float* grad = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
+    for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x) push_tile<OPT>(a.push, grad, tile, &s_t, false, s_tr);
+    __syncthreads();
+    if (tid == 0) {
+      lk_red_release<false>(a.sync + 3, 1u);
+      if (leader) {
+        const uint32_t want = epoch * gridDim.x;
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_gpu(a.sync + 3) != want) {
+          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
+        }
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, 1u);
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, 1u);
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, 1u);
+        if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+        s_applied[w] += 1;
+        st_release_sys(a.flags + w * SF_MB_WORDS + SF_MB_APPLIED, s_applied[w]);
+        rr = (w + 1) % a.n_workers;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // single-thread lock exerciser used by the GPU tests (op: 0 = acquire_read, 1 = release_read,
 // 2 = acquire_write, 3 = release_write)
 __global__ void lock_test_kernel(uint32_t* ctrl, int op) {
@@ -499,6 +669,42 @@ extern "C" int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int gri
   }
   if (a->scope_sys) return static_cast<int>(sf::launch(sf::pull_kernel<true>, dim3(grid), dim3(256), 0, st, *a, local_sync));
   return static_cast<int>(sf::launch(sf::pull_kernel<false>, dim3(grid), dim3(256), 0, st, *a, local_sync));
+}
+
+extern "C" int sf_post_launch(const SfPostArgs* a, uint32_t* local_sync, int grid, cudaStream_t st) {
+  if (grid <= 0) {
+    grid = static_cast<int>((a->n / 4 + 256 * 8 - 1) / (256 * 8));
+    if (grid > 148) grid = 148;
+    if (grid < 1) grid = 1;
+  }
+  return static_cast<int>(sf::launch(sf::post_kernel, dim3(grid), dim3(256), 0, st, *a, local_sync));
+}
+
+template <int OPT>
+static int launch_applier(const SfApplierArgs* a, int grid, cudaStream_t st) {
+  // a persistent kernel: never a programmatic-dependent launch
+  if (a->push.scope_sys) sf::applier_kernel<OPT, true><<<grid, sf::kPushThreads, 0, st>>>(*a);
+  else sf::applier_kernel<OPT, false><<<grid, sf::kPushThreads, 0, st>>>(*a);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int sf_applier_launch(const SfApplierArgs* a, int grid, cudaStream_t st) {
+  if (grid <= 0) grid = 32;
+  if (grid > 64) grid = 64;
+  if (a->n_workers < 1 || a->n_workers > 8) return -6;
+  switch (a->push.optimizer) {
+    case SF_OPT_SGD: return launch_applier<SF_OPT_SGD>(a, grid, st);
+    case SF_OPT_MOMENTUM: return launch_applier<SF_OPT_MOMENTUM>(a, grid, st);
+    case SF_OPT_ADAM: return launch_applier<SF_OPT_ADAM>(a, grid, st);
+    case SF_OPT_RMSPROP: return launch_applier<SF_OPT_RMSPROP>(a, grid, st);
+    case SF_OPT_ADAGRAD: return launch_applier<SF_OPT_ADAGRAD>(a, grid, st);
+    case SF_OPT_ADADELTA: return launch_applier<SF_OPT_ADADELTA>(a, grid, st);
+    case SF_OPT_ADAGRAD_DA: return launch_applier<SF_OPT_ADAGRAD_DA>(a, grid, st);
+    case SF_OPT_FTRL: return launch_applier<SF_OPT_FTRL>(a, grid, st);
+    case SF_OPT_PROXIMAL_ADAGRAD: return launch_applier<SF_OPT_PROXIMAL_ADAGRAD>(a, grid, st);
+    case SF_OPT_PROXIMAL_SGD: return launch_applier<SF_OPT_PROXIMAL_SGD>(a, grid, st);
+  }
+  return -4;
 }
 
 extern "C" int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st) {

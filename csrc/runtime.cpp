@@ -155,8 +155,23 @@ SfPushArgs parse_push(const py::dict& d) {
       if (acc != a.num_tiles) throw std::runtime_error("push: seg_rows do not match num_tiles");
     }
   }
+  if (!a.grad && getd<int>(d, "applier", 0)) a.grad = reinterpret_cast<float*>(16);   // never dereferenced by the applier
   if (!a.state || !a.ctrl || !a.grad || !a.segs || !a.tile_map || a.num_tiles <= 0)
     throw std::runtime_error("push: state/ctrl/grad/segs/tile_map/num_tiles are required");
+  return a;
+}
+
+SfPostArgs parse_post(const py::dict& d) {
+  SfPostArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
+  a.mailbox = P<float>(getd<uintptr_t>(d, "mailbox", 0));
+  a.flags = P<uint32_t>(getd<uintptr_t>(d, "flags", 0));
+  a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
+  a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
+  a.n = getd<size_t>(d, "n", 0);
+  a.drop = getd<int>(d, "drop", 0);
+  if (!a.grad || !a.mailbox || !a.flags || a.n == 0 || (a.n % 4)) throw std::runtime_error("post: grad/mailbox/flags/n (multiple of 4) are required");
   return a;
 }
 
@@ -173,6 +188,9 @@ SfPullArgs parse_pull(const py::dict& d) {
   a.seen_version = P<uint32_t>(getd<uintptr_t>(d, "seen_version", 0));
   a.lock_mode = getd<int>(d, "lock_mode", 0);
   a.scope_sys = getd<int>(d, "scope_sys", 1);
+  a.wait_applied = P<const uint32_t>(getd<uintptr_t>(d, "wait_applied", 0));
+  a.my_posted = P<const uint32_t>(getd<uintptr_t>(d, "my_posted", 0));
+  if (a.wait_applied && !a.my_posted) throw std::runtime_error("pull: wait_applied needs my_posted");
   if (a.n_bf16 % 8) throw std::runtime_error("pull: bf16 size must be a 16-byte multiple");
   if (!a.ctrl) throw std::runtime_error("pull: ctrl is required");
   return a;
@@ -386,6 +404,66 @@ class StepDriver {
 };
 
 // ---------------------------------------------------------------------------
+// Applier: owns the persistent master-side kernel of the served push mode.
+// ---------------------------------------------------------------------------
+class Applier {
+ public:
+  Applier(const py::dict& push, uintptr_t mailboxes, size_t mailbox_stride, uintptr_t flags, int n_workers, uintptr_t sync,
+          double idle_timeout_s, int grid) {
+    py::dict d(push);
+    std::memset(&args_, 0, sizeof(args_));
+    args_.push = parse_push(d);
+    args_.mailboxes = P<float>(mailboxes);
+    args_.mailbox_stride = mailbox_stride;
+    args_.flags = P<uint32_t>(flags);
+    args_.n_workers = n_workers;
+    args_.sync = P<uint32_t>(sync);
+    args_.idle_timeout_ns = static_cast<unsigned long long>(idle_timeout_s * 1e9);
+    void* raw = nullptr;
+    ck(cudaHostAlloc(&raw, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc(stop flag)");
+    stop_host_ = static_cast<volatile int*>(raw);
+    *stop_host_ = 0;
+    int* dev_ptr = nullptr;
+    ck(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_ptr), const_cast<int*>(stop_host_), 0), "cudaHostGetDevicePointer");
+    args_.host_stop = dev_ptr;
+    int lo = 0, hi = 0;
+    ck(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
+    ck(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi), "cudaStreamCreate(applier)");
+    ck(cudaMemsetAsync(args_.sync, 0, 8 * sizeof(uint32_t), stream_), "cudaMemsetAsync(applier sync)");
+    ck_rc(sf_applier_launch(&args_, grid, stream_), "applier launch");
+    running_ = true;
+  }
+  ~Applier() {
+    try { stop(); } catch (...) {}
+    if (stream_) cudaStreamDestroy(stream_);
+    if (stop_host_) cudaFreeHost(const_cast<int*>(stop_host_));
+  }
+  bool alive() {
+    if (!running_) return false;
+    const cudaError_t e = cudaStreamQuery(stream_);
+    if (e == cudaErrorNotReady) return true;
+    running_ = false;
+    if (e != cudaSuccess) ck(e, "applier kernel");
+    return false;
+  }
+  void stop() {
+    if (!running_) return;
+    *stop_host_ = 1;
+    {
+      py::gil_scoped_release nogil;
+      ck(cudaStreamSynchronize(stream_), "applier stop");
+    }
+    running_ = false;
+  }
+
+ private:
+  SfApplierArgs args_;
+  volatile int* stop_host_ = nullptr;
+  cudaStream_t stream_ = nullptr;
+  bool running_ = false;
+};
+
+// ---------------------------------------------------------------------------
 // CUDA-IPC symmetric memory: cudaMalloc'ed segments exported to the peer processes of the box.
 // ---------------------------------------------------------------------------
 uintptr_t ipc_alloc(size_t bytes) {
@@ -542,10 +620,28 @@ PYBIND11_MODULE(_C, m) {
              const SfPushArgs a = parse_push(d);
              p.add("push", [=](cudaStream_t st) { return sf_push_launch(&a, P<uint32_t>(local_sync), grid, st); });
            })
+      .def("add_post",
+           [](Plan& p, const py::dict& d, uintptr_t local_sync, int grid) {
+             const SfPostArgs a = parse_post(d);
+             p.add("post", [=](cudaStream_t st) { return sf_post_launch(&a, P<uint32_t>(local_sync), grid, st); });
+           })
       .def("add_pull", [](Plan& p, const py::dict& d, uintptr_t local_sync, int grid) {
         const SfPullArgs a = parse_pull(d);
         p.add("pull", [=](cudaStream_t st) { return sf_pull_launch(&a, P<uint32_t>(local_sync), grid, st); });
       });
+
+  py::class_<Applier>(m, "Applier")
+      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int>(), py::arg("push"), py::arg("mailboxes"),
+           py::arg("mailbox_stride"), py::arg("flags"), py::arg("n_workers"), py::arg("sync"), py::arg("idle_timeout_s") = 30.0,
+           py::arg("grid") = 32)
+      .def("alive", &Applier::alive)
+      .def("stop", &Applier::stop);
+  m.attr("MB_WORDS") = static_cast<int>(SF_MB_WORDS);
+  m.attr("MB_APPLIED") = static_cast<int>(SF_MB_APPLIED);
+  m.def("post", [](const py::dict& d, uintptr_t local_sync, int grid, uintptr_t stream) {
+    const SfPostArgs a = parse_post(d);
+    ck_rc(sf_post_launch(&a, P<uint32_t>(local_sync), grid, S(stream)), "post");
+  });
 
   py::class_<StepDriver>(m, "StepDriver")
       .def(py::init<uintptr_t, uintptr_t, uintptr_t, size_t, uintptr_t, size_t, uintptr_t, int>())

@@ -181,8 +181,41 @@ struct SfPullArgs {
   uint32_t* seen_version;         // local: version observed by this pull
   int lock_mode;
   int scope_sys;
+  // served push: wait until the applier has consumed this worker's last posted gradient, so a pull after a
+  // push always observes the worker's own update (the reference's POST /update is synchronous)
+  const uint32_t* wait_applied;   // master flag word (peer mapped) or nullptr
+  const uint32_t* my_posted;      // local word holding the sequence number of my last post
 };
 int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int grid, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// Served push ("mailbox + master-resident applier"): the worker's push kernel only streams its gradient
+// into its mailbox in master memory (4 B / parameter over NVLink instead of 36 B) and posts a sequence
+// number; a persistent applier kernel on the master GPU applies the mailboxes one at a time at HBM speed.
+// ---------------------------------------------------------------------------
+enum SfMailFlag { SF_MB_POSTED = 0, SF_MB_APPLIED = 16, SF_MB_WORDS = 32 };   // uint32 words per worker, 64 B apart
+
+struct SfPostArgs {
+  float* grad;                    // local gradient (consumed + zeroed)
+  float* mailbox;                 // this worker's mailbox in master memory (peer mapped)
+  uint32_t* flags;                // this worker's flag words in master memory
+  float* loss_acc; float* loss_out;
+  size_t n;                       // floats (multiple of 4)
+  int drop;                       // fault injection: consume the gradient, post nothing
+};
+int sf_post_launch(const SfPostArgs* a, uint32_t* local_sync, int grid, cudaStream_t st);
+
+struct SfApplierArgs {
+  SfPushArgs push;                // master-local pointers; push.grad is ignored
+  float* mailboxes;               // [n_workers][mailbox_stride]
+  size_t mailbox_stride;          // floats
+  uint32_t* flags;                // [n_workers][SF_MB_WORDS]
+  int n_workers;
+  volatile int* host_stop;        // mapped pinned host word: != 0 -> exit
+  uint32_t* sync;                 // 8 words of master-local memory for the in-grid protocol
+  unsigned long long idle_timeout_ns;
+};
+int sf_applier_launch(const SfApplierArgs* a, int grid, cudaStream_t st);
 
 // host-visible lock helpers for tests (single-thread kernels)
 int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st);

@@ -50,9 +50,14 @@ class MasterLayout:
     state: int
     shadow: int
     nbytes: int
+    mailboxes: int = 0
+    mailbox_stride: int = 0        # floats
+    flags: int = 0
+    applier_sync: int = 0
+    n_mailboxes: int = 0
 
     @classmethod
-    def build(cls, layout: ParamLayout, ctrl_words: int) -> "MasterLayout":
+    def build(cls, layout: ParamLayout, ctrl_words: int, n_mailboxes: int = 0, mb_words: int = 32) -> "MasterLayout":
         off = 0
 
         def take(n):
@@ -64,16 +69,24 @@ class MasterLayout:
         ctrl = take(ctrl_words * 4)
         state = take(layout.total * 16)           # float4 (p, slot0, slot1, slot2) per element
         shadow = take(layout.shadow_total * 2)
-        return cls(ctrl, state, shadow, off)
+        if n_mailboxes <= 0:
+            return cls(ctrl, state, shadow, off)
+        stride = round_up(layout.total, 64)
+        flags = take(n_mailboxes * mb_words * 4)
+        sync = take(64)
+        boxes = take(n_mailboxes * stride * 4)
+        return cls(ctrl, state, shadow, off, boxes, stride, flags, sync, n_mailboxes)
 
 
 class MasterState:
     """The parameter server's state on the driver GPU (or a mapping of it in a worker process)."""
 
-    def __init__(self, layout: ParamLayout, spec: OptimizerSpec, device: torch.device, base_ptr: Optional[int] = None):
+    def __init__(self, layout: ParamLayout, spec: OptimizerSpec, device: torch.device, base_ptr: Optional[int] = None,
+                 n_mailboxes: int = 0):
         self.C = native.cuda_ext()
         self.layout, self.spec, self.device = layout, spec, device
-        self.ml = MasterLayout.build(layout, self.C.CTRL_WORDS)
+        self.ml = MasterLayout.build(layout, self.C.CTRL_WORDS, n_mailboxes, self.C.MB_WORDS)
+        self.applier = None
         self.owner = base_ptr is None
         with torch.cuda.device(device):
             self.base = self.C.ipc_alloc(self.ml.nbytes) if self.owner else int(base_ptr)
@@ -93,11 +106,43 @@ class MasterState:
             return bytes(self.C.ipc_get_handle(self.base))
 
     @classmethod
-    def from_ipc(cls, layout: ParamLayout, spec: OptimizerSpec, device: torch.device, handle: bytes) -> "MasterState":
+    def from_ipc(cls, layout: ParamLayout, spec: OptimizerSpec, device: torch.device, handle: bytes, n_mailboxes: int = 0) -> "MasterState":
         C = native.cuda_ext()
         with torch.cuda.device(device):
             base = C.ipc_open_handle(handle)
-        return cls(layout, spec, device, base_ptr=base)
+        return cls(layout, spec, device, base_ptr=base, n_mailboxes=n_mailboxes)
+
+    # -- served push (mailboxes + master-resident applier) ------------------------------------------
+    @property
+    def served(self) -> bool:
+        return self.ml.n_mailboxes > 0
+
+    def mailbox_ptr(self, worker: int) -> int:
+        return self.base + self.ml.mailboxes + worker * self.ml.mailbox_stride * 4
+
+    def flags_ptr(self, worker: int) -> int:
+        return self.base + self.ml.flags + worker * self.C.MB_WORDS * 4
+
+    def start_applier(self, acquire_lock: bool, scope_sys: bool, grid: int = 0, idle_timeout_s: float = 300.0) -> None:
+        """Launch the persistent applier kernel on the master GPU (owner process only)."""
+        assert self.owner and self.served
+        lay = self.layout
+        with torch.cuda.device(self.device):
+            self._segs_dev = torch.frombuffer(bytearray(self.C.pack_segs(lay.seg_rows())), dtype=torch.uint8).to(self.device)
+            self._tile_map = torch.from_numpy(lay.tile_map()).to(self.device)
+            torch.cuda.synchronize(self.device)
+            push = dict(state=native.ptr(self.state), ctrl=native.ptr(self.ctrl), shadow_dst=[native.ptr(self.shadow)], grad=0, applier=1,
+                        segs=native.ptr(self._segs_dev), tile_map=native.ptr(self._tile_map), num_tiles=int(self._tile_map.shape[0]),
+                        seg_rows=lay.seg_rows(), optimizer=self.spec.opt_id, lock_mode=1 if acquire_lock else 0, drop=0,
+                        scope_sys=1 if scope_sys else 0, grad_scale=1.0, hyper=self.spec.native_hyper())
+            grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "48"))
+            self.applier = self.C.Applier(push, self.base + self.ml.mailboxes, self.ml.mailbox_stride, self.base + self.ml.flags,
+                                          self.ml.n_mailboxes, self.base + self.ml.applier_sync, idle_timeout_s, grid)
+
+    def stop_applier(self) -> None:
+        if self.applier is not None:
+            self.applier.stop()
+            self.applier = None
 
     def load_weights(self, weights: Sequence[np.ndarray]) -> None:
         """Initialise params, slots, control block and the bf16 publish buffer (owner only)."""
@@ -133,6 +178,7 @@ class MasterState:
                 "dropped": int(c[5])}
 
     def close(self) -> None:
+        self.stop_applier()
         if self.base:
             with torch.cuda.device(self.device):
                 (self.C.ipc_free if self.owner else self.C.ipc_close_handle)(self.base)
@@ -152,7 +198,8 @@ class DeviceWorker:
 
     def __init__(self, ir: GraphIR, tf_input: str, tf_label: Optional[str], spec: OptimizerSpec, master: MasterState,
                  acquire_lock: bool = False, pull_mode: Optional[str] = None, use_graphs: bool = True,
-                 device: Optional[torch.device] = None, plan: Optional[LayerPlan] = None, shared: bool = True):
+                 device: Optional[torch.device] = None, plan: Optional[LayerPlan] = None, shared: bool = True,
+                 worker_index: int = 0):
         self.C = native.cuda_ext()
         self.ir = ir
         self.plan: LayerPlan = plan if plan is not None else compile_graph(ir, tf_input, tf_label, None, need_loss=True)
@@ -164,6 +211,8 @@ class DeviceWorker:
         self.device = device or master.device
         self.lock_mode = 1 if acquire_lock else 0
         self.scope_sys = 1 if shared else 0        # more than one GPU touches the master -> system-scope lock
+        self.worker_index = worker_index
+        self.served = bool(master.served)          # push = post to my mailbox, the master-resident applier applies it
         self.pull_mode = pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")
         if self.pull_mode == "direct" and self.lock_mode:
             self.pull_mode = "copy"            # a locked pull must be a private snapshot
@@ -213,6 +262,11 @@ class DeviceWorker:
                     tile_map=native.ptr(self.tile_map), num_tiles=int(self.tile_map.shape[0]), seg_rows=self.layout.seg_rows(),
                     optimizer=self.spec.opt_id, lock_mode=self.lock_mode, drop=drop, scope_sys=self.scope_sys, grad_scale=1.0, hyper=self.spec.native_hyper())
 
+    def _post_args(self, loss_out: torch.Tensor, drop: int = 0) -> dict:
+        m = self.master
+        return dict(grad=native.ptr(self.grads), mailbox=m.mailbox_ptr(self.worker_index), flags=m.flags_ptr(self.worker_index),
+                    loss_acc=native.ptr(self.loss_acc), loss_out=native.ptr(loss_out), n=self.layout.total, drop=drop)
+
     def _pull_args(self) -> dict:
         lay, m = self.layout, self.master
         direct = self.pull_mode == "direct"       # weights are read in place by TMA; only the 1-D tail is copied
@@ -220,7 +274,9 @@ class DeviceWorker:
                     src_state=native.ptr(m.state) + lay.vec_offset * 16 if lay.vec_count else 0,
                     dst_f32=native.ptr(self.vec_local) if lay.vec_count else 0, n_f32=lay.vec_count,
                     ctrl=native.ptr(m.ctrl), seen_version=native.ptr(self.seen_version), lock_mode=self.lock_mode,
-                    scope_sys=self.scope_sys)
+                    scope_sys=self.scope_sys,
+                    wait_applied=(m.flags_ptr(self.worker_index) + self.C.MB_APPLIED * 4) if self.served else 0,
+                    my_posted=(native.ptr(self.sync_push) + 16) if self.served else 0)
 
     # ------------------------------------------------------------------------------------------
     def build_plan(self, B: int, slot: int = 0, with_pull: bool = True, with_push: bool = True):
@@ -282,6 +338,24 @@ class DeviceWorker:
             self.stream.synchronize()
             outs.append(bufs.result.detach().cpu().numpy().copy())
         return np.concatenate(outs, axis=0) if outs else np.zeros((0,), np.float32)
+
+    def drain(self, timeout_s: float = 30.0) -> None:
+        """Served push: block until the applier has consumed every gradient this worker posted."""
+        self.stream.synchronize()
+        if not self.served:
+            return
+        import time
+
+        posted = int(self.sync_push[4])
+        flags = _view(self.master.flags_ptr(self.worker_index), self.C.MB_WORDS * 4, torch.int32, self.device)
+        t0 = time.time()
+        while True:
+            applied = int(flags[self.C.MB_APPLIED])
+            if ((applied - posted) & 0xFFFFFFFF) < 0x80000000:
+                return
+            if time.time() - t0 > timeout_s:
+                raise TimeoutError(f"applier did not consume post {posted} of worker {self.worker_index} (applied={applied})")
+            time.sleep(0.0005)
 
     def need_w_map(self) -> Tuple[Dict[str, bool], Dict[str, bool]]:
         return plan_publish_needs(self.plan)

@@ -311,6 +311,9 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     if branches:
         plan.join(2)
     if with_push:
-        plan.add_push(worker._push_args(loss_out), P(worker.sync_push), 0)
+        if worker.served:
+            plan.add_post(worker._post_args(loss_out), P(worker.sync_push), 0)
+        else:
+            plan.add_push(worker._push_args(loss_out), P(worker.sync_push), 0)
     keep.append(gemms)
     return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep)

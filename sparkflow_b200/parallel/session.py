@@ -43,7 +43,7 @@ class TrainingSession:
                  shuffle: bool = True, verbose: int = 0, loss_callback: Optional[Callable] = None, engine: str = "auto",
                  seed: Optional[int] = None, initial_weights: Optional[Sequence[np.ndarray]] = None,
                  pull_mode: Optional[str] = None, resume_from: Optional[str] = None, checkpoint_dir: Optional[str] = None,
-                 checkpoint_every: int = 0):
+                 checkpoint_every: int = 0, push_mode: Optional[str] = None):
         self.ir = GraphIR.from_metagraph(graph_json)
         self.tf_input, self.tf_label, self.spec = tf_input, tf_label, optimizer
         self.acquire_lock, self.iters = bool(acquire_lock), int(iters)
@@ -54,6 +54,10 @@ class TrainingSession:
         self.resume_from, self.checkpoint_dir, self.checkpoint_every = resume_from, checkpoint_dir, int(checkpoint_every or 0)
         self._resume_state = None
         self.graph_json = graph_json
+        # push_mode: 'direct' = the worker applies the optimizer on the master's memory over NVLink;
+        #            'served' = the worker posts its gradient to a mailbox and a persistent applier kernel on the
+        #                       master GPU applies it (4 B/param over NVLink instead of 36 B, no remote round trips)
+        self.push_mode = push_mode or os.environ.get("SPARKFLOW_PUSH_MODE") or "auto"
         self.ctx = D.get_context()
         self.use_cuda = torch.cuda.is_available() and engine != "torch" and os.environ.get("SPARKFLOW_ENGINE", "") != "torch"
         self.engine_kind = "torch"
@@ -105,19 +109,24 @@ class TrainingSession:
             need_w, need_wt = plan_publish_needs(lp)
             self.layout = ParamLayout.build(self.ir.param_shapes(), need_w, need_wt)
             dev0 = self.local_devices()[0]
+            n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
+            shared = n_workers > 1
+            if self.push_mode == "auto":
+                self.push_mode = "served" if shared else "direct"
+            n_mb = n_workers if self.push_mode == "served" else 0
             if ctx.world > 1:
                 if ctx.is_master:
-                    self.master = MasterState(self.layout, self.spec, dev0)
+                    self.master = MasterState(self.layout, self.spec, dev0, n_mailboxes=n_mb)
                     self.master.load_weights(self._init_weights())
                     handle = self.master.ipc_handle()
                 else:
                     handle = None
                 handle = D.broadcast_object(ctx, handle, src=0)
                 if not ctx.is_master:
-                    self.master = MasterState.from_ipc(self.layout, self.spec, dev0, handle)
+                    self.master = MasterState.from_ipc(self.layout, self.spec, dev0, handle, n_mailboxes=n_mb)
                 D.barrier(ctx)
             else:
-                self.master = MasterState(self.layout, self.spec, dev0)
+                self.master = MasterState(self.layout, self.spec, dev0, n_mailboxes=n_mb)
                 self.master.load_weights(self._init_weights())
                 from ..ops import native
 
@@ -136,6 +145,9 @@ class TrainingSession:
         if self._resume_state is not None and self.master is not None and (self.ctx.is_master or self.ctx.world == 1):
             slots, step = self._resume_state
             self.master.load_slots(slots, step)
+        if self.engine_kind == "b200" and self.push_mode == "served" and self.master.owner:
+            n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
+            self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1)
         D.barrier(ctx)
         self._opened = True
         return self
@@ -170,10 +182,11 @@ class TrainingSession:
 
             master = self.master
             if master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
-                master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base)
+                master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base, n_mailboxes=self.master.ml.n_mailboxes)
             shared = self.ctx.world > 1 or len(self.local_devices()) > 1
+            widx = self.ctx.rank if self.ctx.world > 1 else (device.index or 0)
             w = DeviceWorker(self.ir, self.tf_input, self.tf_label, self.spec, master, acquire_lock=self.acquire_lock,
-                             pull_mode=self.pull_mode, device=device, shared=shared)
+                             pull_mode=self.pull_mode, device=device, shared=shared, worker_index=widx)
             self._workers.append(w)
             return B200Engine(w)
         if self.ctx.world > 1 and not self.ctx.is_master:
@@ -190,6 +203,11 @@ class TrainingSession:
         takes the partitions ``i % world == rank``)."""
         self.open()
         ctx = self.ctx
+        if self.engine_kind == "b200" and self.push_mode == "served" and self.master.owner:
+            if self.master.applier is None or not self.master.applier.alive():      # idle timeout between rounds
+                n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
+                self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1)
+        D.barrier(ctx)
         mine = [(i, p) for i, p in enumerate(partitions) if i % ctx.world == ctx.rank]
         devices = self.local_devices()
         lanes: List[List[Tuple[int, Partition]]] = [[] for _ in devices]
@@ -235,7 +253,7 @@ class TrainingSession:
         ctx = self.ctx
         if self.engine_kind == "b200":
             for w in self._workers:
-                w.stream.synchronize()
+                w.drain()
             D.barrier(ctx)
             return self.master.weights()
         if ctx.world > 1:
@@ -274,7 +292,10 @@ class TrainingSession:
                 raise self.gloo_server.failure
         if self.engine_kind == "b200" and self.master is not None:
             for w in self._workers:
-                w.stream.synchronize()
+                try:
+                    w.drain()
+                except TimeoutError:
+                    pass
             D.barrier(ctx)
             self.master.close()
         self._workers.clear()

@@ -200,9 +200,9 @@ class B200Engine(Engine):
             torch.index_select(self.Y, 0, idx, out=g[1])
         return g
 
-    def train(self, rows, pull):
+    def train(self, rows, pull, slot=None):
         w = self.w
-        slot = self.step_idx & 1
+        slot = (self.step_idx & 1) if slot is None else slot
         B = (rows.stop - rows.start) if isinstance(rows, slice) else len(rows)
         plan, bufs = w.build_plan(B, slot, with_pull=pull)
         if self._primed[slot]:
@@ -253,6 +253,7 @@ class B200Engine(Engine):
             for s0 in starts:
                 self.train(slice(int(s0), int(s0) + batch), pull)
             return
+        starts = [int(v) for v in starts]
         key = (batch, pull)
         drv_ids = self._driver_plans.get(key)
         if drv_ids is None:
@@ -263,17 +264,19 @@ class B200Engine(Engine):
             drv_ids = []
             for slot in (0, 1):
                 plan, bufs = w.build_plan(batch, slot, with_pull=pull)
-                while not plan.captured():              # first call runs eagerly, second captures
-                    bufs.x_stage.copy_(self.X[:batch], non_blocking=True)
-                    if bufs.y_stage is not None and self.Y is not None:
-                        bufs.y_stage.copy_(self.Y[:batch], non_blocking=True)
-                    torch.cuda.current_stream().synchronize()
-                    w.run_plan(plan)
-                    w.stream.synchronize()
-                    self.step_idx += 1
+                if not plan.captured():
+                    # the first use of a plan runs it eagerly (a REAL step on the next scheduled minibatch) and
+                    # captures the graph; step counts therefore stay exactly iters x batches
+                    if not starts:
+                        self._driver_plans.pop(key, None)
+                        return
+                    self.train(slice(starts[0], starts[0] + batch), pull, slot=slot)
+                    starts = starts[1:]
                 drv_ids.append(self._driver.add_plan(plan, bufs.x_stage.data_ptr(), 0 if bufs.y_stage is None else bufs.y_stage.data_ptr(),
                                                      bufs.loss_out.data_ptr(), batch))
             self._driver_plans[key] = drv_ids
+        if not starts:
+            return
         self.w.stream.synchronize()       # python-path steps (if any) are done before the driver takes over the ring
         ids = np.asarray([drv_ids[(self._driver.steps() + k) & 1] for k in range(len(starts))], dtype=np.int32)
         self._driver.run(ids, np.asarray(starts, dtype=np.int64))
@@ -293,4 +296,4 @@ class B200Engine(Engine):
         return self.w.partition_loss(self.X, self.Y)
 
     def finish(self):
-        self.w.stream.synchronize()
+        self.w.drain()

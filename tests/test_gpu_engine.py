@@ -37,17 +37,19 @@ def _data(n, d, c, kind, seed=0):
     return X, Y
 
 
-def _setup(name, spec, lock=False, pull_mode="copy"):
+def _setup(name, spec, lock=False, pull_mode="copy", served=False):
     tf_in, tf_lab, d, c, kind = CASES[name]
     ir = GraphIR.from_metagraph(zoo.build(name))
     lp = compile_graph(ir, tf_in, tf_lab)
     need_w, need_wt = plan_publish_needs(lp)
     lay = ParamLayout.build(ir.param_shapes(), need_w, need_wt)
     dev = torch.device("cuda:0")
-    master = MasterState(lay, spec, dev)
+    master = MasterState(lay, spec, dev, n_mailboxes=1 if served else 0)
     w0 = GraphProgram(ir).init_weights(seed=1)
     master.load_weights(w0)
-    worker = DeviceWorker(ir, tf_in, tf_lab, spec, master, acquire_lock=lock, pull_mode=pull_mode)
+    if served:
+        master.start_applier(lock, scope_sys=False, grid=16, idle_timeout_s=20.0)
+    worker = DeviceWorker(ir, tf_in, tf_lab, spec, master, acquire_lock=lock, pull_mode=pull_mode, shared=False)
     return ir, master, worker, w0, (tf_in, tf_lab, d, c, kind)
 
 
@@ -121,3 +123,34 @@ def test_graph_replay_equals_eager(pull_mode):
         master.close()
     for a, b in zip(*outs):
         np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("lock", [False, True])
+def test_served_push_mailbox_applier_tracks_oracle(lock):
+    """push = post to the mailbox + persistent applier kernel on the master GPU; same numbers as direct mode."""
+    spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
+    ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, lock, served=True)
+    assert worker.served and master.applier.alive()
+    X, Y = _data(256, d, c, kind)
+    eng = B200Engine(worker)
+    eng.load_partition(X, Y)
+    ps = ParameterServer(w0, spec, acquire_lock=lock)
+    ref = TorchEngine(ir, tf_in, tf_lab, LocalTransport(ps))
+    ref.load_partition(X, Y)
+    rows = [slice(0, 64), slice(64, 128), slice(128, 192), slice(192, 256)] * 3
+    for r in rows:
+        eng.train(r, pull=True)          # each pull waits until the applier has consumed this worker's previous post
+        ref.train(r, pull=True)
+    eng.finish()
+    import time
+    t0 = time.time()
+    while master.counters()["pushes"] < len(rows) and time.time() - t0 < 10:
+        time.sleep(0.01)
+    cnt = master.counters()
+    assert cnt["pushes"] == len(rows) and cnt["lock"] == 0, cnt
+    for a, b, v in zip(master.weights(), ps.weights(), ir.trainable):
+        assert np.abs(a - b).max() < 5 * 0.001 * len(rows), v.name
+        assert np.mean(np.abs(a - b)) < 0.35 * 0.001 * len(rows), v.name
+    assert master.applier.alive()
+    master.close()
+    assert master.applier is None

@@ -21,7 +21,8 @@ WORKER = textwrap.dedent("""
     from sparkflow_b200.ops.optimizers import OptimizerSpec
     from sparkflow_b200.parallel import dist as D
     from sparkflow_b200.parallel.session import TrainingSession
-    lock = sys.argv[1] == "lock"
+    lock = sys.argv[1].startswith("lock")
+    push_mode = "direct" if sys.argv[1].endswith("direct") else "served"
     ctx = D.get_context()
     rng = np.random.default_rng(11)
     centers = rng.normal(0, 1, (10, 784)).astype(np.float32)
@@ -31,8 +32,13 @@ WORKER = textwrap.dedent("""
         parts.append((centers[lab] + 0.3 * rng.normal(0, 1, (1500, 784)).astype(np.float32), np.eye(10, dtype=np.float32)[lab], lab))
     graph = zoo.build("simple_dnn")
     sess = TrainingSession(graph, "x:0", "y:0", OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.002)), acquire_lock=lock,
-                           iters=6, mini_batch=300, shuffle=False, engine="b200", seed=3)
+                           iters=6, mini_batch=300, shuffle=False, engine="b200", seed=3, push_mode=push_mode)
     sess.train_partitions([(x, y) for x, y, _ in parts])
+    import time
+    t0 = time.time()
+    while sess.counters()["pushes"] < ctx.world * 30 and time.time() - t0 < 20:
+        time.sleep(0.02)            # served mode: the applier may still be draining the last mailboxes
+    D.barrier(ctx)
     w = sess.weights()
     c = sess.counters()
     prog = GraphProgram(GraphIR.from_metagraph(graph))
@@ -56,10 +62,10 @@ def _run(n, mode, tmp_path, port):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("mode", ["hogwild", "lock"])
+@pytest.mark.parametrize("mode", ["hogwild", "lock", "hogwild-direct", "lock-direct"])
 def test_two_gpu_async_parameter_server(mode, tmp_path):
     n = min(torch.cuda.device_count(), 8)
-    res = _run(n, mode, tmp_path, 29541 if mode == "lock" else 29542)
+    res = _run(n, mode, tmp_path, 29541 + ["hogwild", "lock", "hogwild-direct", "lock-direct"].index(mode))
     assert len(res) == n
     total = n * 6 * 5                       # ranks x iters x batches
     for r in res:
