@@ -107,18 +107,16 @@ def run_ours(args, ctx) -> dict:
     e2e_steps(W, 0)
     eng.finish()
     h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
-    D.barrier(ctx)
-    torch.cuda.synchronize(dev)
+    sess.quiesce()                       # barrier + device-wide torch.cuda.synchronize() (applier paused around it)
     sampler = ClockSampler(dev.index or 0).start() if ctx.rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e0.record(eng.w.stream)
     e2e_steps(K, W)
     e1.record(eng.w.stream)
-    eng.finish()
-    torch.cuda.synchronize(dev)
+    eng.finish()                         # stream sync + wait until the master has applied this rank's last push
     t_wall = time.perf_counter() - t_wall0
-    D.barrier(ctx)
+    sess.quiesce()
     e2e_ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
     wall_ms = _max_over_ranks(ctx, t_wall * 1e3)
     last_loss = eng.last_loss()
@@ -135,16 +133,14 @@ def run_ours(args, ctx) -> dict:
         for _ in range(max(W, 3)):
             w.run_plan(plan)
         st.synchronize()
-        D.barrier(ctx)
-        torch.cuda.synchronize(dev)
+        sess.quiesce()
         for a, b in evs:
             flush.zero_()
             a.record(st)
             w.run_plan(plan)
             b.record(st)
         st.synchronize()
-    torch.cuda.synchronize(dev)
-    D.barrier(ctx)
+    sess.quiesce()
     dev_ms = _max_over_ranks(ctx, sum(a.elapsed_time(b) for a, b in evs))
     # back-to-back replays without the flush (what the training loop actually sees)
     with torch.cuda.stream(st):

@@ -50,7 +50,9 @@ __device__ __forceinline__ float act_bwd_from_out(float a, int act) {
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int kStages = (BN >= 256) ? 4 : 6;
+  // ~200 KB of operand ring per CTA: small-N tiles are latency bound, so they get the deepest ring
+  // (all 13 k-blocks of the flagship's 784-wide layer are in flight at once)
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128) ? 6 : (BN >= 64) ? 8 : 10;
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBBytes = BN * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -454,6 +456,24 @@ extern "C" unsigned int sf_trace_count() {
   cudaMemcpyFromSymbol(&n, sf::g_trace_n, sizeof(n));
   return n;
 }
+
+static unsigned int* g_err_host_ptr = nullptr;
+
+// allocate the host-visible error word for the current device and point the device symbol at it
+extern "C" int sf_init_error_channel() {
+  if (g_err_host_ptr == nullptr) {
+    void* raw = nullptr;
+    cudaError_t e = cudaHostAlloc(&raw, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    g_err_host_ptr = static_cast<unsigned int*>(raw);
+    *g_err_host_ptr = 0;
+  }
+  unsigned int* dptr = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&dptr), g_err_host_ptr, 0);
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(sf::g_sf_error_host, &dptr, sizeof(dptr));
+  return static_cast<int>(e);
+}
+extern "C" unsigned int sf_read_host_error_code() { return g_err_host_ptr ? *g_err_host_ptr : 0u; }
 
 extern "C" unsigned int sf_read_error_code() {
   unsigned int v = 0;

@@ -537,42 +537,55 @@ post_kernel(const SfPostArgs a, uint32_t* local_sync) {
 }
 
 // ---------------------------------------------------------------------------
-// applier: persistent kernel on the master GPU.  CTA 0 is the leader: it scans the workers' POSTED flags
-// round-robin, (lock mode) takes the write lock, publishes (epoch, worker, step) to the other CTAs through
-// master-local memory, everybody updates its share of the tiles from that worker's mailbox, and the leader
-// then bumps the counters, releases the lock and acknowledges through the APPLIED flag.  Updates are applied
-// strictly one push at a time - one optimizer step per push, exactly the reference's parameter server.
-// sync words: 0 = epoch, 1 = worker (-1: exit), 2 = step, 3 = cumulative done count.
+// applier: master-GPU side of a served push.  A host thread keeps a few of these *finite* kernels queued on a
+// dedicated stream; each one listens for posted mailboxes for at most `poll_ns`, applies AT MOST ONE push and
+// exits.  (A truly persistent kernel is not an option inside a PyTorch process: CUDA's lazy module loading
+// needs a context-wide synchronisation the first time any kernel is used, which would stall behind it.)
+// CTA 0 is the leader: its first warp scans every worker's POSTED / APPLIED words in one round trip
+// (lane = worker), (lock mode) takes the write lock, and publishes (launch seq, worker, step) to the other CTAs
+// through master-local memory; everybody updates its share of the tiles from that worker's mailbox; the leader
+// bumps the counters, releases the lock and acknowledges through the APPLIED word.  Updates are applied strictly
+// one push at a time: one optimizer step per push, exactly the reference's parameter server.
+// sync words: 0 = launch seq of the published decision, 1 = worker (or -1), 2 = step, 3 = done counter,
+//             4 = round-robin cursor.
 // ---------------------------------------------------------------------------
 template <int OPT, bool SYS>
 __global__ void __launch_bounds__(kPushThreads, 1)
-applier_kernel(const SfApplierArgs a) {
+applier_kernel(const SfApplierArgs a, const uint32_t seq) {
   __shared__ uint32_t s_t;
   __shared__ int s_w;
+  __shared__ uint32_t s_ack;
   __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
-  __shared__ uint32_t s_applied[8];
   const int tid = threadIdx.x;
   const bool leader = blockIdx.x == 0;
   const bool locked = a.push.lock_mode == SF_LOCK_RW;
-  uint32_t epoch = 0;
-  int rr = 0;
-  if (leader && tid < 8) s_applied[tid] = (tid < a.n_workers) ? ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED) : 0u;
-  __syncthreads();
-  while (true) {
-    if (tid == 0) {
-      if (leader) {
-        int found = -1;
-        const unsigned long long t_idle = gtime_ns();
-        while (found < 0) {
-          if (*a.host_stop != 0) { found = -2; break; }
-          for (int k = 0; k < a.n_workers; ++k) {
-            const int w = (rr + k) % a.n_workers;
-            if (ld_acquire_sys(a.flags + w * SF_MB_WORDS + SF_MB_POSTED) != s_applied[w]) { found = w; break; }
-          }
-          if (found >= 0) break;
-          if (gtime_ns() - t_idle > a.idle_timeout_ns) { found = -2; break; }
-          __nanosleep(100);
+  if (leader) {
+    if (tid < 32) {
+      int found = -1;
+      uint32_t posted = 0;
+      const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
+      const unsigned long long t0 = gtime_ns();
+      while (true) {
+        uint32_t ap = 0;
+        bool ready = false;
+        if (tid < a.n_workers) {
+          posted = ld_acquire_sys(a.flags + tid * SF_MB_WORDS + SF_MB_POSTED);
+          ap = ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED);
+          ready = posted != ap;
         }
+        const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
+        if (m_ready) {
+          // round-robin fairness: first ready worker at or after the cursor
+          const unsigned rot = (m_ready >> rr) | (m_ready << ((32 - rr) & 31));
+          found = (rr + __ffs(rot) - 1) & 31;
+          break;
+        }
+        // listening window over: let the next launch take over (lane 0 decides for the whole warp)
+        if (__ballot_sync(0xffffffffu, gtime_ns() - t0 > a.idle_timeout_ns) & 1u) break;
+        __nanosleep(40);
+      }
+      const uint32_t posted_w = __shfl_sync(0xffffffffu, posted, found < 0 ? 0 : found);
+      if (tid == 0) {
         uint32_t t = 0;
         if (found >= 0) {
           if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
@@ -580,44 +593,42 @@ applier_kernel(const SfApplierArgs a) {
         }
         a.sync[1] = static_cast<uint32_t>(found);
         a.sync[2] = t;
-        st_release_gpu(a.sync + 0, epoch + 1);
+        st_release_gpu(a.sync + 0, seq);
         s_w = found;
         s_t = t;
-      } else {
-        const unsigned long long t0 = gtime_ns();
-        while (ld_acquire_gpu(a.sync + 0) != epoch + 1) {
-          __nanosleep(40);
-          if (gtime_ns() - t0 > a.idle_timeout_ns + kLockTimeoutNs) { a.sync[1] = 0xFFFFFFFEu; break; }
-        }
-        s_w = static_cast<int>(a.sync[1]);
-        s_t = a.sync[2];
+        s_ack = posted_w;
       }
     }
-    __syncthreads();
-    ++epoch;
-    const int w = s_w;
-    if (w < 0) return;                                  // stop requested / idle timeout
-    float* grad = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
-    for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x) push_tile<OPT>(a.push, grad, tile, &s_t, false, s_tr);
-    __syncthreads();
-    if (tid == 0) {
-      lk_red_release<false>(a.sync + 3, 1u);
-      if (leader) {
-        const uint32_t want = epoch * gridDim.x;
-        const unsigned long long t0 = gtime_ns();
-        while (ld_acquire_gpu(a.sync + 3) != want) {
-          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
-        }
-        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, 1u);
-        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, 1u);
-        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, 1u);
-        if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
-        s_applied[w] += 1;
-        st_release_sys(a.flags + w * SF_MB_WORDS + SF_MB_APPLIED, s_applied[w]);
-        rr = (w + 1) % a.n_workers;
-      }
+  } else if (tid == 0) {
+    const unsigned long long t0 = gtime_ns();
+    while (ld_acquire_gpu(a.sync + 0) != seq) {
+      __nanosleep(20);
+      if (gtime_ns() - t0 > a.idle_timeout_ns + kLockTimeoutNs) sf_fail(0x408);
     }
-    __syncthreads();
+    s_w = static_cast<int>(a.sync[1]);
+    s_t = a.sync[2];
+  }
+  __syncthreads();
+  const int w = s_w;
+  if (w < 0) return;                                    // nothing was posted during this listening window
+  float* grad = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
+  for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x) push_tile<OPT>(a.push, grad, tile, &s_t, false, s_tr);
+  __syncthreads();
+  if (tid == 0) {
+    lk_red_release<false>(a.sync + 3, 1u);
+    if (leader) {
+      const unsigned long long t0 = gtime_ns();
+      while (ld_acquire_gpu(a.sync + 3) != gridDim.x) {
+        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
+      }
+      a.sync[3] = 0;                                    // the next launch starts after this grid has retired
+      a.sync[4] = static_cast<uint32_t>(w + 1);
+      lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, 1u);
+      lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, 1u);
+      lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, 1u);
+      if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+      st_release_sys(a.flags + w * SF_MB_WORDS + SF_MB_APPLIED, s_ack);
+    }
   }
 }
 
@@ -681,28 +692,27 @@ extern "C" int sf_post_launch(const SfPostArgs* a, uint32_t* local_sync, int gri
 }
 
 template <int OPT>
-static int launch_applier(const SfApplierArgs* a, int grid, cudaStream_t st) {
-  // a persistent kernel: never a programmatic-dependent launch
-  if (a->push.scope_sys) sf::applier_kernel<OPT, true><<<grid, sf::kPushThreads, 0, st>>>(*a);
-  else sf::applier_kernel<OPT, false><<<grid, sf::kPushThreads, 0, st>>>(*a);
+static int launch_applier(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st) {
+  if (a->push.scope_sys) sf::applier_kernel<OPT, true><<<grid, sf::kPushThreads, 0, st>>>(*a, seq);
+  else sf::applier_kernel<OPT, false><<<grid, sf::kPushThreads, 0, st>>>(*a, seq);
   return static_cast<int>(cudaGetLastError());
 }
 
-extern "C" int sf_applier_launch(const SfApplierArgs* a, int grid, cudaStream_t st) {
-  if (grid <= 0) grid = 32;
-  if (grid > 64) grid = 64;
+extern "C" int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st) {
+  if (grid <= 0) grid = 96;
+  if (grid > 148) grid = 148;       // co-resident with the training kernels: 256 threads, ~5 KB smem per CTA
   if (a->n_workers < 1 || a->n_workers > 8) return -6;
   switch (a->push.optimizer) {
-    case SF_OPT_SGD: return launch_applier<SF_OPT_SGD>(a, grid, st);
-    case SF_OPT_MOMENTUM: return launch_applier<SF_OPT_MOMENTUM>(a, grid, st);
-    case SF_OPT_ADAM: return launch_applier<SF_OPT_ADAM>(a, grid, st);
-    case SF_OPT_RMSPROP: return launch_applier<SF_OPT_RMSPROP>(a, grid, st);
-    case SF_OPT_ADAGRAD: return launch_applier<SF_OPT_ADAGRAD>(a, grid, st);
-    case SF_OPT_ADADELTA: return launch_applier<SF_OPT_ADADELTA>(a, grid, st);
-    case SF_OPT_ADAGRAD_DA: return launch_applier<SF_OPT_ADAGRAD_DA>(a, grid, st);
-    case SF_OPT_FTRL: return launch_applier<SF_OPT_FTRL>(a, grid, st);
-    case SF_OPT_PROXIMAL_ADAGRAD: return launch_applier<SF_OPT_PROXIMAL_ADAGRAD>(a, grid, st);
-    case SF_OPT_PROXIMAL_SGD: return launch_applier<SF_OPT_PROXIMAL_SGD>(a, grid, st);
+    case SF_OPT_SGD: return launch_applier<SF_OPT_SGD>(a, seq, grid, st);
+    case SF_OPT_MOMENTUM: return launch_applier<SF_OPT_MOMENTUM>(a, seq, grid, st);
+    case SF_OPT_ADAM: return launch_applier<SF_OPT_ADAM>(a, seq, grid, st);
+    case SF_OPT_RMSPROP: return launch_applier<SF_OPT_RMSPROP>(a, seq, grid, st);
+    case SF_OPT_ADAGRAD: return launch_applier<SF_OPT_ADAGRAD>(a, seq, grid, st);
+    case SF_OPT_ADADELTA: return launch_applier<SF_OPT_ADADELTA>(a, seq, grid, st);
+    case SF_OPT_ADAGRAD_DA: return launch_applier<SF_OPT_ADAGRAD_DA>(a, seq, grid, st);
+    case SF_OPT_FTRL: return launch_applier<SF_OPT_FTRL>(a, seq, grid, st);
+    case SF_OPT_PROXIMAL_ADAGRAD: return launch_applier<SF_OPT_PROXIMAL_ADAGRAD>(a, seq, grid, st);
+    case SF_OPT_PROXIMAL_SGD: return launch_applier<SF_OPT_PROXIMAL_SGD>(a, seq, grid, st);
   }
   return -4;
 }

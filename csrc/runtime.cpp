@@ -7,7 +7,9 @@
 #include <pybind11/numpy.h>
 #include <pybind11/stl.h>
 
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <functional>
 #include <memory>
 #include <stdexcept>
@@ -404,12 +406,13 @@ class StepDriver {
 };
 
 // ---------------------------------------------------------------------------
-// Applier: owns the persistent master-side kernel of the served push mode.
+// Applier: master side of the served push mode.  A host thread keeps `depth` finite poll-and-apply kernels
+// queued on a dedicated high-priority stream (see applier_kernel in optim_push.cu).
 // ---------------------------------------------------------------------------
 class Applier {
  public:
   Applier(const py::dict& push, uintptr_t mailboxes, size_t mailbox_stride, uintptr_t flags, int n_workers, uintptr_t sync,
-          double idle_timeout_s, int grid) {
+          double poll_window_s, int grid, int depth) : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
     py::dict d(push);
     std::memset(&args_, 0, sizeof(args_));
     args_.push = parse_push(d);
@@ -418,49 +421,62 @@ class Applier {
     args_.flags = P<uint32_t>(flags);
     args_.n_workers = n_workers;
     args_.sync = P<uint32_t>(sync);
-    args_.idle_timeout_ns = static_cast<unsigned long long>(idle_timeout_s * 1e9);
-    void* raw = nullptr;
-    ck(cudaHostAlloc(&raw, sizeof(int), cudaHostAllocMapped), "cudaHostAlloc(stop flag)");
-    stop_host_ = static_cast<volatile int*>(raw);
-    *stop_host_ = 0;
-    int* dev_ptr = nullptr;
-    ck(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_ptr), const_cast<int*>(stop_host_), 0), "cudaHostGetDevicePointer");
-    args_.host_stop = dev_ptr;
+    args_.idle_timeout_ns = static_cast<unsigned long long>(poll_window_s * 1e9);
+    ck(cudaGetDevice(&device_), "cudaGetDevice");
     int lo = 0, hi = 0;
     ck(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
     ck(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi), "cudaStreamCreate(applier)");
     ck(cudaMemsetAsync(args_.sync, 0, 8 * sizeof(uint32_t), stream_), "cudaMemsetAsync(applier sync)");
-    ck_rc(sf_applier_launch(&args_, grid, stream_), "applier launch");
-    running_ = true;
+    ck(cudaStreamSynchronize(stream_), "applier init");
+    ck_rc(sf_preload_kernels(), "preload kernels");
+    events_.resize(depth_);
+    for (auto& e : events_) ck(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+    stop_.store(false);
+    thread_ = std::thread([this]() { this->loop(); });
   }
   ~Applier() {
     try { stop(); } catch (...) {}
+    for (auto& e : events_) if (e) cudaEventDestroy(e);
     if (stream_) cudaStreamDestroy(stream_);
-    if (stop_host_) cudaFreeHost(const_cast<int*>(stop_host_));
   }
-  bool alive() {
-    if (!running_) return false;
-    const cudaError_t e = cudaStreamQuery(stream_);
-    if (e == cudaErrorNotReady) return true;
-    running_ = false;
-    if (e != cudaSuccess) ck(e, "applier kernel");
-    return false;
-  }
+  bool alive() const { return thread_.joinable() && !failed_.load(); }
+  long long launches() const { return static_cast<long long>(seq_.load()); }
   void stop() {
-    if (!running_) return;
-    *stop_host_ = 1;
+    if (!thread_.joinable()) return;
+    stop_.store(true);
     {
       py::gil_scoped_release nogil;
-      ck(cudaStreamSynchronize(stream_), "applier stop");
+      thread_.join();
     }
-    running_ = false;
+    if (failed_.load()) throw std::runtime_error("sparkflow_b200 applier thread failed: " + error_);
   }
 
  private:
+  void loop() {
+    if (cudaSetDevice(device_) != cudaSuccess) { failed_.store(true); error_ = "cudaSetDevice"; return; }
+    unsigned int seq = 0;
+    while (!stop_.load(std::memory_order_relaxed)) {
+      const int slot = seq % depth_;
+      if (seq >= static_cast<unsigned int>(depth_)) {
+        const cudaError_t e = cudaEventSynchronize(events_[slot]);      // the launch `depth` ago has retired
+        if (e != cudaSuccess) { failed_.store(true); error_ = cudaGetErrorString(e); return; }
+      }
+      ++seq;
+      const int rc = sf_applier_launch(&args_, seq, grid_, stream_);
+      if (rc != 0) { failed_.store(true); error_ = "applier launch failed"; return; }
+      cudaEventRecord(events_[slot], stream_);
+      seq_.store(seq);
+    }
+    cudaStreamSynchronize(stream_);
+  }
   SfApplierArgs args_;
-  volatile int* stop_host_ = nullptr;
+  int grid_, depth_, device_ = 0;
   cudaStream_t stream_ = nullptr;
-  bool running_ = false;
+  std::vector<cudaEvent_t> events_;
+  std::thread thread_;
+  std::atomic<bool> stop_{false}, failed_{false};
+  std::atomic<unsigned int> seq_{0};
+  std::string error_;
 };
 
 // ---------------------------------------------------------------------------
@@ -631,10 +647,11 @@ PYBIND11_MODULE(_C, m) {
       });
 
   py::class_<Applier>(m, "Applier")
-      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int>(), py::arg("push"), py::arg("mailboxes"),
-           py::arg("mailbox_stride"), py::arg("flags"), py::arg("n_workers"), py::arg("sync"), py::arg("idle_timeout_s") = 30.0,
-           py::arg("grid") = 32)
+      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int>(), py::arg("push"), py::arg("mailboxes"),
+           py::arg("mailbox_stride"), py::arg("flags"), py::arg("n_workers"), py::arg("sync"), py::arg("poll_window_s") = 30e-6,
+           py::arg("grid") = 96, py::arg("depth") = 3)
       .def("alive", &Applier::alive)
+      .def("launches", &Applier::launches)
       .def("stop", &Applier::stop);
   m.attr("MB_WORDS") = static_cast<int>(SF_MB_WORDS);
   m.attr("MB_APPLIED") = static_cast<int>(SF_MB_APPLIED);
@@ -708,6 +725,11 @@ PYBIND11_MODULE(_C, m) {
   m.def("trace_count", &sf_trace_count);
   m.attr("TRACE_REC_BYTES") = 32;
   m.def("read_error_code", &sf_read_error_code);
+  m.def("init_error_channel", []() {
+    ck_rc(sf_init_error_channel(), "init_error_channel");
+    ck_rc(sf_preload_kernels(), "preload kernels");        // no lazy module load in the middle of a run
+  });
+  m.def("read_host_error_code", &sf_read_host_error_code);
   m.def("pack_segs", &pack_segs);
 
   m.def("ipc_alloc", &ipc_alloc);

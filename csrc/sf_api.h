@@ -69,6 +69,8 @@ int sf_gemm_prepare(SfGemm* g);
 int sf_gemm_launch(const SfGemm* g, cudaStream_t st);
 int sf_gemm_pick_bn(int M, int N);
 unsigned int sf_read_error_code();
+int sf_init_error_channel();
+unsigned int sf_read_host_error_code();
 void sf_set_pdl(int enabled);
 int sf_trace_enable(void* buf, unsigned int cap);
 unsigned int sf_trace_count();
@@ -211,11 +213,11 @@ struct SfApplierArgs {
   size_t mailbox_stride;          // floats
   uint32_t* flags;                // [n_workers][SF_MB_WORDS]
   int n_workers;
-  volatile int* host_stop;        // mapped pinned host word: != 0 -> exit
   uint32_t* sync;                 // 8 words of master-local memory for the in-grid protocol
-  unsigned long long idle_timeout_ns;
+  unsigned long long idle_timeout_ns;   // listening window of one launch
 };
-int sf_applier_launch(const SfApplierArgs* a, int grid, cudaStream_t st);
+int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st);
+int sf_preload_kernels();
 
 // host-visible lock helpers for tests (single-thread kernels)
 int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st);

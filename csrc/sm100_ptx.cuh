@@ -19,9 +19,14 @@ namespace sf {
 // a launch failure instead of a dead GPU.
 // ---------------------------------------------------------------------------
 __device__ unsigned int g_sf_error_code = 0;
+__device__ unsigned int* g_sf_error_host = nullptr;     // mapped pinned host word: survives the dead context
 
 __device__ __forceinline__ void sf_fail(unsigned int code) {
   atomicExch(&g_sf_error_code, code);
+  if (g_sf_error_host != nullptr) {
+    // code | blockIdx.x << 12 so the host can see WHICH bounded wait fired even though the trap kills the context
+    *reinterpret_cast<volatile unsigned int*>(g_sf_error_host) = code | (blockIdx.x << 12);
+  }
   __threadfence_system();
   asm volatile("trap;");
 }

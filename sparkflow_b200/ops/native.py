@@ -52,9 +52,40 @@ def _load(name: str) -> ModuleType:
     return mod
 
 
+_err_channel_devices = set()
+
+WAIT_CODES = {0x100: "gemm: TMA producer waiting for a free smem stage", 0x200: "gemm: MMA issuer waiting for operands",
+              0x300: "gemm: epilogue waiting for the accumulator", 0x401: "rw lock: write acquire", 0x402: "rw lock: read acquire",
+              0x403: "push: CTA waiting for the lock grant", 0x404: "pull: CTA waiting for the lock grant",
+              0x405: "pull: waiting for the applier to consume my last post", 0x406: "post: waiting for my mailbox to be consumed",
+              0x407: "applier: leader waiting for the other CTAs"}
+
+
 def cuda_ext() -> ModuleType:
-    """The sm_100a kernel/runtime module (``sparkflow_b200._C``)."""
-    return _load("_C")
+    """The sm_100a kernel/runtime module (``sparkflow_b200._C``).  On a CUDA machine the first call per device
+    also installs the host-visible error word that bounded device waits write before trapping."""
+    mod = _load("_C")
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            dev = torch.cuda.current_device()
+            if dev not in _err_channel_devices:
+                mod.init_error_channel()
+                _err_channel_devices.add(dev)
+    except Exception:  # pragma: no cover
+        pass
+    return mod
+
+
+def describe_device_error() -> str:
+    """Human-readable form of the last bounded-wait failure (readable even after the CUDA context died)."""
+    code = _load("_C").read_host_error_code()
+    if not code:
+        return "no device-side wait failure recorded"
+    base = code & 0xFFF
+    key = base if base in WAIT_CODES else (base & 0xF00)
+    return f"device wait failure 0x{base:x} (block {code >> 12}): {WAIT_CODES.get(key, 'unknown')}"
 
 
 def host_ext() -> ModuleType:

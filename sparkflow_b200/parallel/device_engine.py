@@ -78,6 +78,12 @@ class MasterLayout:
         return cls(ctrl, state, shadow, off, boxes, stride, flags, sync, n_mailboxes)
 
 
+def _sync_current(device: torch.device) -> None:
+    """Stream-level synchronisation.  NEVER a device-wide cudaDeviceSynchronize: in served push mode a persistent
+    applier kernel lives on the master GPU and a device-wide sync would wait for it."""
+    torch.cuda.current_stream(device).synchronize()
+
+
 class MasterState:
     """The parameter server's state on the driver GPU (or a mapping of it in a worker process)."""
 
@@ -123,21 +129,22 @@ class MasterState:
     def flags_ptr(self, worker: int) -> int:
         return self.base + self.ml.flags + worker * self.C.MB_WORDS * 4
 
-    def start_applier(self, acquire_lock: bool, scope_sys: bool, grid: int = 0, idle_timeout_s: float = 300.0) -> None:
-        """Launch the persistent applier kernel on the master GPU (owner process only)."""
+    def start_applier(self, acquire_lock: bool, scope_sys: bool, grid: int = 0, poll_window_s: float = 30e-6, depth: int = 3) -> None:
+        """Start the applier (owner process only): a host thread that keeps `depth` finite poll-and-apply
+        kernels queued on a dedicated high-priority stream of the master GPU."""
         assert self.owner and self.served
         lay = self.layout
         with torch.cuda.device(self.device):
             self._segs_dev = torch.frombuffer(bytearray(self.C.pack_segs(lay.seg_rows())), dtype=torch.uint8).to(self.device)
             self._tile_map = torch.from_numpy(lay.tile_map()).to(self.device)
-            torch.cuda.synchronize(self.device)
+            _sync_current(self.device)
             push = dict(state=native.ptr(self.state), ctrl=native.ptr(self.ctrl), shadow_dst=[native.ptr(self.shadow)], grad=0, applier=1,
                         segs=native.ptr(self._segs_dev), tile_map=native.ptr(self._tile_map), num_tiles=int(self._tile_map.shape[0]),
                         seg_rows=lay.seg_rows(), optimizer=self.spec.opt_id, lock_mode=1 if acquire_lock else 0, drop=0,
                         scope_sys=1 if scope_sys else 0, grad_scale=1.0, hyper=self.spec.native_hyper())
-            grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "48"))
+            grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "112"))
             self.applier = self.C.Applier(push, self.base + self.ml.mailboxes, self.ml.mailbox_stride, self.base + self.ml.flags,
-                                          self.ml.n_mailboxes, self.base + self.ml.applier_sync, idle_timeout_s, grid)
+                                          self.ml.n_mailboxes, self.base + self.ml.applier_sync, poll_window_s, grid, depth)
 
     def stop_applier(self) -> None:
         if self.applier is not None:
@@ -155,10 +162,10 @@ class MasterState:
         self.ctrl.zero_()
         pub = torch.from_numpy(self.layout.publish_reference(flat)).to(torch.bfloat16)
         self.shadow.copy_(pub)
-        torch.cuda.synchronize(self.device)
+        _sync_current(self.device)
 
     def weights(self) -> List[np.ndarray]:
-        torch.cuda.synchronize(self.device)
+        _sync_current(self.device)
         return self.layout.unflatten(self.p.detach().contiguous().cpu().numpy())
 
     def slot_arrays(self) -> List[List[np.ndarray]]:
@@ -170,7 +177,7 @@ class MasterState:
             self.state[:, 1 + i].copy_(torch.from_numpy(self.layout.flatten(per_var)))
         self.ctrl[2] = int(step)
         self.ctrl[3] = int(step)
-        torch.cuda.synchronize(self.device)
+        _sync_current(self.device)
 
     def counters(self) -> Dict[str, int]:
         c = self.ctrl.cpu().numpy()
@@ -404,4 +411,4 @@ def external_push(master: MasterState, layout: ParamLayout, spec: OptimizerSpec,
                     tile_map=native.ptr(tmap), num_tiles=int(tmap.shape[0]), optimizer=spec.opt_id,
                     lock_mode=1 if acquire_lock else 0, grad_scale=1.0, hyper=spec.native_hyper())
         C.push(args, native.ptr(sync), 0, native.current_stream())
-        torch.cuda.synchronize(dev)
+        _sync_current(dev)

@@ -152,6 +152,26 @@ class TrainingSession:
         self._opened = True
         return self
 
+    def quiesce(self) -> None:
+        """Collective: drain every worker, stop the applier, do a genuine device-wide ``torch.cuda.synchronize()``
+        and bring the applier back.  Benchmarks bracket their timed regions with this (a device-wide synchronise
+        can never return while the persistent applier kernel is resident)."""
+        ctx = self.ctx
+        for w in self._workers:
+            if hasattr(w, "drain"):
+                w.drain()
+        D.barrier(ctx)
+        served = self.engine_kind == "b200" and self.push_mode == "served"
+        if served and self.master.owner:
+            self.master.stop_applier()
+        if self.use_cuda:
+            for d in self.local_devices():
+                torch.cuda.synchronize(d)
+        if served and self.master.owner:
+            n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
+            self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1)
+        D.barrier(ctx)
+
     # -- snapshot / resume ------------------------------------------------------------------------------
     def snapshot(self, prefix: str) -> Optional[str]:
         """Write the master's parameters + optimizer slots as a TF-V2 checkpoint (rank 0 only)."""

@@ -24,12 +24,12 @@ class DeviceTrace:
         self.buf = torch.zeros(capacity * 32, dtype=torch.uint8, device=device or "cuda")
 
     def __enter__(self):
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()      # stream-level: a persistent applier kernel may be resident
         self.C.trace_enable(native.ptr(self.buf), self.capacity)
         return self
 
     def __exit__(self, *exc):
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         self.n = min(self.C.trace_count(), self.capacity)
         self.C.trace_enable(0, 0)
         return False

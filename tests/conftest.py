@@ -25,3 +25,16 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_makereport(item, call):
+    outcome = yield
+    rep = outcome.get_result()
+    if rep.failed and "gpu" in item.keywords:
+        try:
+            from sparkflow_b200.ops import native
+
+            rep.sections.append(("sparkflow_b200 device error channel", native.describe_device_error()))
+        except Exception:
+            pass

@@ -48,7 +48,7 @@ def _setup(name, spec, lock=False, pull_mode="copy", served=False):
     w0 = GraphProgram(ir).init_weights(seed=1)
     master.load_weights(w0)
     if served:
-        master.start_applier(lock, scope_sys=False, grid=16, idle_timeout_s=20.0)
+        master.start_applier(lock, scope_sys=False, grid=32)
     worker = DeviceWorker(ir, tf_in, tf_lab, spec, master, acquire_lock=lock, pull_mode=pull_mode, shared=False)
     return ir, master, worker, w0, (tf_in, tf_lab, d, c, kind)
 
