@@ -87,7 +87,7 @@ def run_ours(args, ctx) -> dict:
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001, beta1=0.9, beta2=0.999))
     sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock=lock, iters=1, mini_batch=BATCH,
                            mini_stochastic_iters=1, shuffle=True, engine="b200", seed=1234, pull_mode=args.pull_mode,
-                           push_mode=args.push_mode).open()
+                           push_mode=args.push_mode, devices=[dev.index]).open()
     eng = sess.make_engine(dev)
     rows = max(args.partition_rows, BATCH * 2)
     x, y = _synthetic_partition(rows, seed=100 + ctx.rank)

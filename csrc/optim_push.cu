@@ -559,76 +559,82 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
   const int tid = threadIdx.x;
   const bool leader = blockIdx.x == 0;
   const bool locked = a.push.lock_mode == SF_LOCK_RW;
-  if (leader) {
-    if (tid < 32) {
-      int found = -1;
-      uint32_t posted = 0;
-      const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
-      const unsigned long long t0 = gtime_ns();
-      while (true) {
-        uint32_t ap = 0;
-        bool ready = false;
-        if (tid < a.n_workers) {
-          posted = ld_acquire_sys(a.flags + tid * SF_MB_WORDS + SF_MB_POSTED);
-          ap = ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED);
-          ready = posted != ap;
-        }
-        const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
-        if (m_ready) {
-          // round-robin fairness: first ready worker at or after the cursor
-          const unsigned rot = (m_ready >> rr) | (m_ready << ((32 - rr) & 31));
-          found = (rr + __ffs(rot) - 1) & 31;
-          break;
-        }
-        // listening window over: let the next launch take over (lane 0 decides for the whole warp)
-        if (__ballot_sync(0xffffffffu, gtime_ns() - t0 > a.idle_timeout_ns) & 1u) break;
-        __nanosleep(40);
-      }
-      const uint32_t posted_w = __shfl_sync(0xffffffffu, posted, found < 0 ? 0 : found);
-      if (tid == 0) {
-        uint32_t t = 0;
-        if (found >= 0) {
-          if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
-          t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
-        }
-        a.sync[1] = static_cast<uint32_t>(found);
-        a.sync[2] = t;
-        st_release_gpu(a.sync + 0, seq);
-        s_w = found;
-        s_t = t;
-        s_ack = posted_w;
-      }
-    }
-  } else if (tid == 0) {
-    const unsigned long long t0 = gtime_ns();
-    while (ld_acquire_gpu(a.sync + 0) != seq) {
-      __nanosleep(20);
-      if (gtime_ns() - t0 > a.idle_timeout_ns + kLockTimeoutNs) sf_fail(0x408);
-    }
-    s_w = static_cast<int>(a.sync[1]);
-    s_t = a.sync[2];
-  }
-  __syncthreads();
-  const int w = s_w;
-  if (w < 0) return;                                    // nothing was posted during this listening window
-  float* grad = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
-  for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x) push_tile<OPT>(a.push, grad, tile, &s_t, false, s_tr);
-  __syncthreads();
-  if (tid == 0) {
-    lk_red_release<false>(a.sync + 3, 1u);
+  constexpr int kMaxApplies = 8;            // one launch drains up to this many mailboxes back to back
+  for (int k = 0; k < kMaxApplies; ++k) {
+    const uint32_t epoch = seq * 16u + static_cast<uint32_t>(k);
     if (leader) {
-      const unsigned long long t0 = gtime_ns();
-      while (ld_acquire_gpu(a.sync + 3) != gridDim.x) {
-        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
+      if (tid < 32) {
+        int found = -1;
+        uint32_t posted = 0;
+        const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
+        const unsigned long long t0 = gtime_ns();
+        while (true) {
+          uint32_t ap = 0;
+          bool ready = false;
+          if (tid < a.n_workers) {
+            posted = ld_acquire_sys(a.flags + tid * SF_MB_WORDS + SF_MB_POSTED);
+            ap = ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED);
+            ready = posted != ap;
+          }
+          const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
+          if (m_ready) {
+            // round-robin fairness: first ready worker at or after the cursor
+            const unsigned rot = (m_ready >> rr) | (m_ready << ((32 - rr) & 31));
+            found = (rr + __ffs(rot) - 1) & 31;
+            break;
+          }
+          // the first decision listens for a whole window; follow-ups only take what is already there
+          const bool over = (k > 0) || (gtime_ns() - t0 > a.idle_timeout_ns);
+          if (__ballot_sync(0xffffffffu, over) & 1u) break;      // lane 0 decides for the whole warp
+          __nanosleep(40);
+        }
+        const uint32_t posted_w = __shfl_sync(0xffffffffu, posted, found < 0 ? 0 : found);
+        if (tid == 0) {
+          uint32_t t = 0;
+          if (found >= 0) {
+            if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+            t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
+          }
+          a.sync[1] = static_cast<uint32_t>(found);
+          a.sync[2] = t;
+          st_release_gpu(a.sync + 0, epoch);
+          s_w = found;
+          s_t = t;
+          s_ack = posted_w;
+        }
       }
-      a.sync[3] = 0;                                    // the next launch starts after this grid has retired
-      a.sync[4] = static_cast<uint32_t>(w + 1);
-      lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, 1u);
-      lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, 1u);
-      lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, 1u);
-      if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
-      st_release_sys(a.flags + w * SF_MB_WORDS + SF_MB_APPLIED, s_ack);
+    } else if (tid == 0) {
+      const unsigned long long t0 = gtime_ns();
+      while (ld_acquire_gpu(a.sync + 0) != epoch) {
+        __nanosleep(20);
+        if (gtime_ns() - t0 > a.idle_timeout_ns + kLockTimeoutNs) sf_fail(0x408);
+      }
+      s_w = static_cast<int>(a.sync[1]);
+      s_t = a.sync[2];
     }
+    __syncthreads();
+    const int w = s_w;
+    if (w < 0) return;                                  // nothing (more) is posted: this launch is done
+    float* grad = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
+    for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x) push_tile<OPT>(a.push, grad, tile, &s_t, false, s_tr);
+    __syncthreads();
+    if (tid == 0) {
+      lk_red_release<false>(a.sync + 3, 1u);
+      if (leader) {
+        const unsigned long long t0 = gtime_ns();
+        while (ld_acquire_gpu(a.sync + 3) != gridDim.x) {
+          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
+        }
+        a.sync[3] = 0;                                  // everybody has arrived; the next decision is published after this
+        a.sync[4] = static_cast<uint32_t>(w + 1);
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, 1u);
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, 1u);
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, 1u);
+        if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+        st_release_sys(a.flags + w * SF_MB_WORDS + SF_MB_APPLIED, s_ack);
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -43,7 +43,7 @@ class TrainingSession:
                  shuffle: bool = True, verbose: int = 0, loss_callback: Optional[Callable] = None, engine: str = "auto",
                  seed: Optional[int] = None, initial_weights: Optional[Sequence[np.ndarray]] = None,
                  pull_mode: Optional[str] = None, resume_from: Optional[str] = None, checkpoint_dir: Optional[str] = None,
-                 checkpoint_every: int = 0, push_mode: Optional[str] = None):
+                 checkpoint_every: int = 0, push_mode: Optional[str] = None, devices: Optional[Sequence[int]] = None):
         self.ir = GraphIR.from_metagraph(graph_json)
         self.tf_input, self.tf_label, self.spec = tf_input, tf_label, optimizer
         self.acquire_lock, self.iters = bool(acquire_lock), int(iters)
@@ -58,6 +58,7 @@ class TrainingSession:
         #            'served' = the worker posts its gradient to a mailbox and a persistent applier kernel on the
         #                       master GPU applies it (4 B/param over NVLink instead of 36 B, no remote round trips)
         self.push_mode = push_mode or os.environ.get("SPARKFLOW_PUSH_MODE") or "auto"
+        self.devices = None if devices is None else [int(d) for d in devices]     # single-process mode: GPUs to use
         self.ctx = D.get_context()
         self.use_cuda = torch.cuda.is_available() and engine != "torch" and os.environ.get("SPARKFLOW_ENGINE", "") != "torch"
         self.engine_kind = "torch"
@@ -96,6 +97,8 @@ class TrainingSession:
             return [torch.device("cpu")]
         if self.ctx.world > 1:
             return [torch.device("cuda", self.ctx.local_rank % torch.cuda.device_count())]
+        if self.devices is not None:
+            return [torch.device("cuda", i) for i in self.devices]
         return [torch.device("cuda", i) for i in range(torch.cuda.device_count())]
 
     def open(self) -> "TrainingSession":

@@ -10,7 +10,7 @@ from sparkflow_b200.parallel.session import TrainingSession
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 6
 spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
-sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock="--lock" in sys.argv, engine="b200", seed=0).open()
+sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock="--lock" in sys.argv, engine="b200", seed=0, devices=[0]).open()
 eng = sess.make_engine(torch.device("cuda", 0))
 w = eng.w
 w.use_graphs = False

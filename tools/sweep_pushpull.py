@@ -58,14 +58,14 @@ def main():
         for opt in ("gradient_descent", "adam"):
             spec = OptimizerSpec.from_tf_kwargs(opt, dict(learning_rate=1e-3))
             if ctx.is_master:
-                master = MasterState(lay, spec, dev)
+                master = MasterState(lay, spec, dev, n_mailboxes=ctx.world)
                 master.load_weights([np.zeros((rows, cols), np.float32)])
                 handle = master.ipc_handle()
             else:
                 handle = None
             handle = D.broadcast_object(ctx, handle, 0)
             if not ctx.is_master:
-                master = MasterState.from_ipc(lay, spec, dev, handle)
+                master = MasterState.from_ipc(lay, spec, dev, handle, n_mailboxes=ctx.world)
             D.barrier(ctx)
             if ctx.rank == worker_rank:
                 grads = torch.full((lay.total,), 1e-3, device=dev)
@@ -91,6 +91,26 @@ def main():
                     rec["pull_s"] = t_pull
                     rec["pull_nvlink_GBs"] = lay.shadow_total * 2 / t_pull / 1e9
             D.barrier(ctx)
+            if opt == "adam":
+                # served push: the worker only streams its gradient into its mailbox (4 B / parameter over NVLink);
+                # the applier on the master GPU applies it.  Back-to-back posts wait for the previous apply, so this
+                # is the sustained post + apply rate of one worker.
+                if ctx.is_master:
+                    master.start_applier(False, scope_sys=True)
+                D.barrier(ctx)
+                if ctx.rank == worker_rank:
+                    psync = torch.zeros(16, dtype=torch.int32, device=dev)
+                    post_args = dict(grad=native.ptr(grads), mailbox=master.mailbox_ptr(ctx.rank), flags=master.flags_ptr(ctx.rank),
+                                     loss_acc=native.ptr(loss), loss_out=native.ptr(loss) + 4, n=lay.total)
+                    t_post = timeit(lambda: C.post(post_args, native.ptr(psync), 0, st), iters)
+                    rec["served_push_s"] = t_post
+                    rec["served_push_nvlink_GBs"] = rows * cols * 4 / t_post / 1e9
+                    import time
+                    time.sleep(0.05)
+                D.barrier(ctx)
+                if ctx.is_master:
+                    master.stop_applier()
+                D.barrier(ctx)
             torch.cuda.synchronize()
             if ctx.is_master:
                 master.close()

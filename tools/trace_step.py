@@ -13,7 +13,7 @@ from sparkflow_b200.utils.trace import DeviceTrace
 
 lock = "--lock" in sys.argv
 spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
-sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock=lock, engine="b200", seed=0).open()
+sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock=lock, engine="b200", seed=0, devices=[0]).open()
 eng = sess.make_engine(torch.device("cuda", 0))
 w = eng.w
 plan, bufs = w.build_plan(300, 0)
