@@ -226,12 +226,15 @@ __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc
   if (mc) multimem_st_u4(reinterpret_cast<uint4*>(dst), q);
   else asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
 }
-// One 32x64 parameter tile: load the gradient + the master tuples, apply the optimizer rule in registers, store
-// the tuples back, publish bf16 W / W^T, zero the consumed gradient.  Shared by the worker-side push kernel
-// (master tuples over NVLink) and the master-resident applier (gradient from a worker's mailbox).
-template <int OPT>
-__device__ __forceinline__ void push_tile(const SfPushArgs& a, float* grad, int tile, const uint32_t* s_t_ptr, bool sync_for_t,
-                                          __nv_bfloat16 (*s_tr)[kTileR + 8]) {
+// One 32x64 parameter tile: load the master tuples ONCE, then apply `n_grads` pushes to them back to back in
+// registers (push k uses step number t+k and its own bias-corrected rate: bit-for-bit the result of n_grads
+// separate optimizer steps, one per push, in that order), store the tuples back, publish bf16 W / W^T.
+// Shared by the worker-side push kernel (n_grads = 1, master tuples over NVLink, ZERO: the consumed gradient is
+// cleared for the next step's accumulating epilogues) and the master-resident applier (gradients from up to 8
+// worker mailboxes: state traffic and publish are paid once per batch instead of once per push).
+template <int OPT, bool ZERO>
+__device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* grads, int n_grads, int tile,
+                                          const uint32_t* s_t_ptr, bool sync_for_t, __nv_bfloat16 (*s_tr)[kTileR + 8]) {
   constexpr int NS = Slots<OPT>::n;
   const int tid = threadIdx.x;
   const bool mc = a.shadow_is_mc != 0;
@@ -255,9 +258,19 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* grad, int 
     const bool vec = ((sg.cols & 3) == 0) && ((sg.offset & 3) == 0);
     const int tx = tid & 15, ty = tid >> 4;
     const int c = c0 + tx * 4;
+    auto load_grad = [&](const float* grad, int64_t e, int nv, float (&g)[4]) {
+      g[0] = g[1] = g[2] = g[3] = 0.f;
+      if (nv == 0) return;
+      if (vec) {
+        const float4 gv = *reinterpret_cast<const float4*>(grad + e);
+        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+      } else {
+        for (int j = 0; j < nv; ++j) g[j] = grad[e + j];
+      }
+    };
     // ---- phase 1: issue every load of both half-rows before anything depends on them ----
     float g[2][4];
-    float4 st4[2][4];
+    Upd u[2][4];
     int nv[2];
     int64_t e[2];
 #pragma unroll
@@ -265,55 +278,69 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* grad, int 
       const int r = r0 + ty + 16 * half;
       nv[half] = (r < sg.rows && c < sg.cols) ? ((sg.cols - c) >= 4 ? 4 : (sg.cols - c)) : 0;
       e[half] = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
+      load_grad(grads[0], e[half], nv[half], g[half]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { g[half][j] = 0.f; st4[half][j] = make_float4(0.f, 0.f, 0.f, 0.f); }
-      if (nv[half] == 0) continue;
-      if (vec) {
-        const float4 gv = *reinterpret_cast<const float4*>(grad + e[half]);
-        g[half][0] = gv.x; g[half][1] = gv.y; g[half][2] = gv.z; g[half][3] = gv.w;
-      } else {
-        for (int j = 0; j < nv[half]; ++j) g[half][j] = grad[e[half] + j];
+      for (int j = 0; j < 4; ++j) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!a.drop && j < nv[half]) v = ld_weak_f4(reinterpret_cast<const float*>(a.state + e[half] + j));
+        u[half][j] = Upd{v.x, v.y, v.z, v.w};
       }
-      if (!a.drop) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j < nv[half]) st4[half][j] = ld_weak_f4(reinterpret_cast<const float*>(a.state + e[half] + j));
+      if (ZERO && nv[half] > 0) {
+        // the gradient is consumed: zero it for the next step's accumulating epilogues
+        if (vec) *reinterpret_cast<float4*>(grads[0] + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else for (int j = 0; j < nv[half]; ++j) grads[0][e[half] + j] = 0.f;
       }
     }
     // ---- step number: under the lock it was granted above; Hogwild read it at kernel entry ----
     if (sync_for_t) __syncthreads();     // the step count was written to shared memory by thread 0
-    const float t = static_cast<float>(*s_t_ptr);
-    float lr_t = a.h.lr;
-    if constexpr (OPT == SF_OPT_ADAM) {
-      lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
+    const float t0 = static_cast<float>(*s_t_ptr);
+    // ---- phase 2: n_grads optimizer steps in registers (the next push's gradient is in flight meanwhile) ----
+    if (!a.drop) {
+      for (int k = 0; k < n_grads; ++k) {
+        float gn[2][4];
+        if (k + 1 < n_grads) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) load_grad(grads[k + 1], e[half], nv[half], gn[half]);
+        }
+        const float t = t0 + static_cast<float>(k);
+        float lr_t = a.h.lr;
+        if constexpr (OPT == SF_OPT_ADAM) {
+          lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < nv[half]) apply_rule<OPT>(u[half][j], g[half][j] * a.grad_scale, a.h, t, lr_t);
+        if (k + 1 < n_grads) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g[half][j] = gn[half][j];
+        }
+      }
     }
-    // ---- phase 2: update + stores ----
+    // ---- phase 3: stores ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const int rl = ty + 16 * half;
       const int r = r0 + rl;
       float w[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nv[half] > 0) {
-        // the gradient is consumed: zero it for the next step's accumulating epilogues
-        if (vec) *reinterpret_cast<float4*>(grad + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
-        else for (int j = 0; j < nv[half]; ++j) grad[e[half] + j] = 0.f;
-        if (!a.drop) {
+      if (nv[half] > 0 && !a.drop) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (j < nv[half]) {
-              Upd u{st4[half][j].x, st4[half][j].y, st4[half][j].z, st4[half][j].w};
-              apply_rule<OPT>(u, g[half][j] * a.grad_scale, a.h, t, lr_t);
-              w[j] = u.p;
-              float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
-              st_weak_f4(dst, u.p, NS >= 1 ? u.s0 : 0.f, NS >= 2 ? u.s1 : 0.f, NS >= 3 ? u.s2 : 0.f);
-            }
+        for (int j = 0; j < 4; ++j) {
+          if (j < nv[half]) {
+            const Upd& q = u[half][j];
+            w[j] = q.p;
+            float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
+            st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
           }
-          // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
-          if (sg.w_off >= 0) {
-            const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
-            const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
-            for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8(a.shadow_dst[d] + wo, q, mc && d == 0);
-          }
+        }
+        // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
+        if (sg.w_off >= 0) {
+          const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
+          const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+          for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8(a.shadow_dst[d] + wo, q, mc && d == 0);
         }
       }
       if (sg.wt_off >= 0 && !a.drop) {
@@ -376,8 +403,9 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   if (locked) __syncthreads();      // Hogwild: nothing to wait for, loads below start immediately
 
   // ---------------- tiles ----------------
+  float* const grads[1] = {a.grad};
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
-    push_tile<OPT>(a, a.grad, tile, &s_t, !locked && tile == static_cast<int>(blockIdx.x), s_tr);
+    push_tile<OPT, true>(a, grads, 1, tile, &s_t, !locked && tile == static_cast<int>(blockIdx.x), s_tr);
 
   // ---------------- completion ----------------
   __syncthreads();
@@ -538,69 +566,73 @@ post_kernel(const SfPostArgs a, uint32_t* local_sync) {
 
 // ---------------------------------------------------------------------------
 // applier: master-GPU side of a served push.  A host thread keeps a few of these *finite* kernels queued on a
-// dedicated stream; each one listens for posted mailboxes for at most `poll_ns`, applies AT MOST ONE push and
+// dedicated stream; each one listens for posted mailboxes for at most `poll_ns`, applies what is posted and
 // exits.  (A truly persistent kernel is not an option inside a PyTorch process: CUDA's lazy module loading
 // needs a context-wide synchronisation the first time any kernel is used, which would stall behind it.)
 // CTA 0 is the leader: its first warp scans every worker's POSTED / APPLIED words in one round trip
-// (lane = worker), (lock mode) takes the write lock, and publishes (launch seq, worker, step) to the other CTAs
-// through master-local memory; everybody updates its share of the tiles from that worker's mailbox; the leader
-// bumps the counters, releases the lock and acknowledges through the APPLIED word.  Updates are applied strictly
-// one push at a time: one optimizer step per push, exactly the reference's parameter server.
-// sync words: 0 = launch seq of the published decision, 1 = worker (or -1), 2 = step, 3 = done counter,
-//             4 = round-robin cursor.
+// (lane = worker), (lock mode) takes the write lock ONCE for the whole batch, and publishes (epoch, ready mask,
+// step) to the other CTAs through master-local memory; every CTA then runs its share of the tiles, applying the
+// posted gradients one after the other IN REGISTERS (push_tile): each push is still its own optimizer step with
+// its own step number - exactly the reference's parameter server, one update per push in arrival (round-robin)
+// order - but the tuples and the bf16 publish move once per batch.  The leader bumps the counters by the batch
+// size, releases the lock and acknowledges every consumed mailbox through its APPLIED word.
+// sync words: 0 = epoch of the published decision, 1 = ready mask (0 = nothing), 2 = first step number,
+//             3 = done counter, 4 = round-robin cursor.
 // ---------------------------------------------------------------------------
 template <int OPT, bool SYS>
 __global__ void __launch_bounds__(kPushThreads, 1)
 applier_kernel(const SfApplierArgs a, const uint32_t seq) {
   __shared__ uint32_t s_t;
-  __shared__ int s_w;
-  __shared__ uint32_t s_ack;
+  __shared__ uint32_t s_mask;
+  __shared__ int s_n;
+  __shared__ float* s_grads[8];
   __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
   const int tid = threadIdx.x;
   const bool leader = blockIdx.x == 0;
   const bool locked = a.push.lock_mode == SF_LOCK_RW;
-  constexpr int kMaxApplies = 8;            // one launch drains up to this many mailboxes back to back
-  for (int k = 0; k < kMaxApplies; ++k) {
+  constexpr int kMaxBatches = 8;            // one launch keeps draining while mailboxes are posted
+  for (int k = 0; k < kMaxBatches; ++k) {
     const uint32_t epoch = seq * 16u + static_cast<uint32_t>(k);
+    uint32_t posted = 0;                    // leader warp: lane w holds worker w's POSTED word
     if (leader) {
       if (tid < 32) {
-        int found = -1;
-        uint32_t posted = 0;
-        const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
+        unsigned m_ready = 0;
         const unsigned long long t0 = gtime_ns();
         while (true) {
-          uint32_t ap = 0;
           bool ready = false;
           if (tid < a.n_workers) {
             posted = ld_acquire_sys(a.flags + tid * SF_MB_WORDS + SF_MB_POSTED);
-            ap = ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED);
+            const uint32_t ap = ld_relaxed_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED);
             ready = posted != ap;
           }
-          const unsigned m_ready = __ballot_sync(0xffffffffu, ready);
-          if (m_ready) {
-            // round-robin fairness: first ready worker at or after the cursor
-            const unsigned rot = (m_ready >> rr) | (m_ready << ((32 - rr) & 31));
-            found = (rr + __ffs(rot) - 1) & 31;
-            break;
-          }
+          m_ready = __ballot_sync(0xffffffffu, ready);
+          if (m_ready) break;
           // the first decision listens for a whole window; follow-ups only take what is already there
           const bool over = (k > 0) || (gtime_ns() - t0 > a.idle_timeout_ns);
           if (__ballot_sync(0xffffffffu, over) & 1u) break;      // lane 0 decides for the whole warp
           __nanosleep(40);
         }
-        const uint32_t posted_w = __shfl_sync(0xffffffffu, posted, found < 0 ? 0 : found);
+        if (a.max_batch > 0 && a.max_batch < 8) {                // keep only the first max_batch workers after the cursor
+          const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
+          unsigned keep = 0;
+          int cnt = 0;
+          for (int i = 0; i < a.n_workers && cnt < a.max_batch; ++i) {
+            const int w = (rr + i) % a.n_workers;
+            if (m_ready >> w & 1u) { keep |= 1u << w; ++cnt; }
+          }
+          m_ready = keep;
+        }
         if (tid == 0) {
           uint32_t t = 0;
-          if (found >= 0) {
+          if (m_ready) {
             if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
             t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
           }
-          a.sync[1] = static_cast<uint32_t>(found);
+          a.sync[1] = m_ready;
           a.sync[2] = t;
           st_release_gpu(a.sync + 0, epoch);
-          s_w = found;
+          s_mask = m_ready;
           s_t = t;
-          s_ack = posted_w;
         }
       }
     } else if (tid == 0) {
@@ -609,29 +641,46 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         __nanosleep(20);
         if (gtime_ns() - t0 > a.idle_timeout_ns + kLockTimeoutNs) sf_fail(0x408);
       }
-      s_w = static_cast<int>(a.sync[1]);
+      s_mask = a.sync[1];
       s_t = a.sync[2];
     }
     __syncthreads();
-    const int w = s_w;
-    if (w < 0) return;                                  // nothing (more) is posted: this launch is done
-    float* grad = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
-    for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x) push_tile<OPT>(a.push, grad, tile, &s_t, false, s_tr);
-    __syncthreads();
+    const uint32_t mask = s_mask;
+    if (mask == 0) return;                              // nothing (more) is posted: this launch is done
     if (tid == 0) {
-      lk_red_release<false>(a.sync + 3, 1u);
-      if (leader) {
+      // application order: round-robin from the cursor, so no worker's push is always last in a batch
+      const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
+      int n = 0;
+      for (int i = 0; i < a.n_workers; ++i) {
+        const int w = (rr + i) % a.n_workers;
+        if (mask >> w & 1u) s_grads[n++] = a.mailboxes + static_cast<size_t>(w) * a.mailbox_stride;
+      }
+      s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x)
+      push_tile<OPT, false>(a.push, s_grads, n, tile, &s_t, false, s_tr);
+    __syncthreads();
+    if (tid == 0) lk_red_release<false>(a.sync + 3, 1u);
+    if (leader && tid < 32) {
+      if (tid == 0) {
         const unsigned long long t0 = gtime_ns();
         while (ld_acquire_gpu(a.sync + 3) != gridDim.x) {
           if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
         }
         a.sync[3] = 0;                                  // everybody has arrived; the next decision is published after this
-        a.sync[4] = static_cast<uint32_t>(w + 1);
-        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, 1u);
-        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, 1u);
-        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, 1u);
+        a.sync[4] = static_cast<uint32_t>(32 - __clz(mask));     // cursor: one past the highest worker served
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, static_cast<uint32_t>(n));
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, static_cast<uint32_t>(n));
+        lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, static_cast<uint32_t>(n));
         if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
-        st_release_sys(a.flags + w * SF_MB_WORDS + SF_MB_APPLIED, s_ack);
+      }
+      __syncwarp();
+      // lane w acknowledges worker w (release: ordered after lane 0's acquire of the done counter by the warp barrier)
+      if (mask >> tid & 1u) {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        st_release_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED, posted);
       }
     }
     __syncthreads();

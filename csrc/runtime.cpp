@@ -366,7 +366,10 @@ class StepDriver {
     for (int k = 0; k < n; ++k) {
       if (ip[k] < 0 || ip[k] >= static_cast<int>(entries_.size())) throw std::runtime_error("StepDriver.run: bad plan id");
       Entry& e = entries_[ip[k]];
-      if (e.primed) ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(slot free)");
+      if (e.primed) {
+        ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(slot free)");
+        harvest(e);
+      }
       ck(cudaMemcpyAsync(e.x_stage, x_host_ + static_cast<size_t>(sp[k]) * x_row_, static_cast<size_t>(e.batch) * x_row_,
                          cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(x)");
       if (e.y_stage && y_host_)
@@ -375,16 +378,33 @@ class StepDriver {
       ck(cudaEventRecord(e.ready, copy_), "cudaEventRecord(ready)");
       ck(cudaStreamWaitEvent(compute_, e.ready, 0), "cudaStreamWaitEvent");
       e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
-      ck(cudaMemcpyAsync(ring_ + (step_ % ring_len_), e.loss_out, sizeof(float), cudaMemcpyDeviceToHost, compute_), "cudaMemcpyAsync(loss)");
+      // the step's last kernel stores the loss straight into this entry's pinned host word (zero-copy D2H: no
+      // copy-engine operation on the compute stream); it is moved into the ring once the step has retired
       ck(cudaEventRecord(e.free_, compute_), "cudaEventRecord(free)");
+      e.pending = step_;
       e.primed = true;
       ++step_;
     }
   }
   long long steps() const { return step_; }
+  // wait for every in-flight step and move their losses into the ring
+  void flush() {
+    py::gil_scoped_release nogil;
+    for (auto& e : entries_)
+      if (e.primed && e.pending >= 0) {
+        ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(flush)");
+        harvest(e);
+      }
+  }
 
  private:
+  struct Entry;
+  void harvest(Entry& e) {
+    if (e.pending >= 0) ring_[e.pending % ring_len_] = *const_cast<volatile float*>(e.loss_out);
+    e.pending = -1;
+  }
   struct Entry {
+    long long pending = -1;
     py::object keep;
     Plan* plan = nullptr;
     char* x_stage = nullptr;
@@ -412,7 +432,7 @@ class StepDriver {
 class Applier {
  public:
   Applier(const py::dict& push, uintptr_t mailboxes, size_t mailbox_stride, uintptr_t flags, int n_workers, uintptr_t sync,
-          double poll_window_s, int grid, int depth) : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
+          double poll_window_s, int grid, int depth, int max_batch) : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
     py::dict d(push);
     std::memset(&args_, 0, sizeof(args_));
     args_.push = parse_push(d);
@@ -422,6 +442,7 @@ class Applier {
     args_.n_workers = n_workers;
     args_.sync = P<uint32_t>(sync);
     args_.idle_timeout_ns = static_cast<unsigned long long>(poll_window_s * 1e9);
+    args_.max_batch = max_batch;
     ck(cudaGetDevice(&device_), "cudaGetDevice");
     int lo = 0, hi = 0;
     ck(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
@@ -647,9 +668,9 @@ PYBIND11_MODULE(_C, m) {
       });
 
   py::class_<Applier>(m, "Applier")
-      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int>(), py::arg("push"), py::arg("mailboxes"),
+      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int, int>(), py::arg("push"), py::arg("mailboxes"),
            py::arg("mailbox_stride"), py::arg("flags"), py::arg("n_workers"), py::arg("sync"), py::arg("poll_window_s") = 30e-6,
-           py::arg("grid") = 96, py::arg("depth") = 3)
+           py::arg("grid") = 96, py::arg("depth") = 3, py::arg("max_batch") = 8)
       .def("alive", &Applier::alive)
       .def("launches", &Applier::launches)
       .def("stop", &Applier::stop);
@@ -664,7 +685,8 @@ PYBIND11_MODULE(_C, m) {
       .def(py::init<uintptr_t, uintptr_t, uintptr_t, size_t, uintptr_t, size_t, uintptr_t, int>())
       .def("add_plan", &StepDriver::add_plan)
       .def("run", &StepDriver::run)
-      .def("steps", &StepDriver::steps);
+      .def("steps", &StepDriver::steps)
+      .def("flush", &StepDriver::flush);
 
   // direct (un-planned) entry points, used by tests and the eager paths
   m.def("cast_transpose", [](uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,

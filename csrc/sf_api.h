@@ -215,6 +215,7 @@ struct SfApplierArgs {
   int n_workers;
   uint32_t* sync;                 // 8 words of master-local memory for the in-grid protocol
   unsigned long long idle_timeout_ns;   // listening window of one launch
+  int max_batch;                  // pushes fused into one pass over the state (1..8; 0 = 8)
 };
 int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st);
 int sf_preload_kernels();

@@ -129,9 +129,11 @@ class MasterState:
     def flags_ptr(self, worker: int) -> int:
         return self.base + self.ml.flags + worker * self.C.MB_WORDS * 4
 
-    def start_applier(self, acquire_lock: bool, scope_sys: bool, grid: int = 0, poll_window_s: float = 30e-6, depth: int = 3) -> None:
+    def start_applier(self, acquire_lock: bool, scope_sys: bool, grid: int = 0, poll_window_s: float = 30e-6, depth: int = 3,
+                      max_batch: int = 0) -> None:
         """Start the applier (owner process only): a host thread that keeps `depth` finite poll-and-apply
-        kernels queued on a dedicated high-priority stream of the master GPU."""
+        kernels queued on a dedicated high-priority stream of the master GPU.  `max_batch` pushes (default 8,
+        env SPARKFLOW_APPLIER_BATCH) are applied per pass over the state - each still its own optimizer step."""
         assert self.owner and self.served
         lay = self.layout
         with torch.cuda.device(self.device):
@@ -144,7 +146,8 @@ class MasterState:
                         scope_sys=1 if scope_sys else 0, grad_scale=1.0, hyper=self.spec.native_hyper())
             grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "112"))
             self.applier = self.C.Applier(push, self.base + self.ml.mailboxes, self.ml.mailbox_stride, self.base + self.ml.flags,
-                                          self.ml.n_mailboxes, self.base + self.ml.applier_sync, poll_window_s, grid, depth)
+                                          self.ml.n_mailboxes, self.base + self.ml.applier_sync, poll_window_s, grid, depth,
+                                          max_batch or int(os.environ.get("SPARKFLOW_APPLIER_BATCH", "8")))
 
     def stop_applier(self) -> None:
         if self.applier is not None:

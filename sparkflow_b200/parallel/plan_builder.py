@@ -92,7 +92,12 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     x_stage = zeros(B, D, dtype=f32)
     need_labels = (train or with_loss) and not lp.target_is_input
     y_stage = zeros(B, lp.label_dim, dtype=f32) if need_labels else None
-    loss_out = zeros(1, dtype=f32)
+    if train:
+        # training steps hand their loss to the host with a zero-copy store from the last kernel (pinned, device-mapped)
+        loss_out = torch.zeros(1, dtype=f32).pin_memory()
+        keep.append(loss_out)
+    else:
+        loss_out = zeros(1, dtype=f32)
     wsrc = worker._weight_src()
     plan = C.Plan()
     branches = worker.use_branches and train

@@ -170,6 +170,7 @@ class B200Engine(Engine):
         self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
         self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
         self._primed = [False, False]
+        self._pending = [None, None]            # slot -> (ring index, pinned loss word) not yet harvested
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._gather = [None, None]
@@ -207,6 +208,7 @@ class B200Engine(Engine):
         plan, bufs = w.build_plan(B, slot, with_pull=pull)
         if self._primed[slot]:
             self._slot_free[slot].synchronize()            # host gather buffer + staging are reusable
+            self._harvest(slot)
         hx, hy = self._host_batch(rows, slot)
         with torch.cuda.stream(w.copy_stream):
             bufs.x_stage.copy_(hx, non_blocking=True)
@@ -217,13 +219,20 @@ class B200Engine(Engine):
             self._slot_ready[slot].record(w.copy_stream)
         w.stream.wait_event(self._slot_ready[slot])
         w.run_plan(plan)
-        with torch.cuda.stream(w.stream):
-            self.loss_ring[self.step_idx % self.LOSS_RING].copy_(bufs.loss_out[0], non_blocking=True)
-            self.d2h_bytes += 4
-            self._slot_free[slot].record(w.stream)
+        # the step's last kernel (push / post) stores the loss into the plan's pinned host word: a 4-byte zero-copy
+        # D2H per step, harvested into the ring when the slot is reused or the loss is asked for
+        self._slot_free[slot].record(w.stream)
+        self._pending[slot] = (self.step_idx % self.LOSS_RING, bufs.loss_out)
+        self.d2h_bytes += 4
         self._primed[slot] = True
         self._driver_last = None
         self.step_idx += 1
+
+    def _harvest(self, slot: int) -> None:
+        pend = self._pending[slot]
+        if pend is not None:
+            self.loss_ring[pend[0]] = float(pend[1][0])
+            self._pending[slot] = None
 
     def permute(self, order: np.ndarray) -> None:
         """Physically shuffle the pinned partition (threaded native row gather into the spare buffers)."""
@@ -278,6 +287,8 @@ class B200Engine(Engine):
         if not starts:
             return
         self.w.stream.synchronize()       # python-path steps (if any) are done before the driver takes over the ring
+        self._harvest(0)
+        self._harvest(1)
         ids = np.asarray([drv_ids[(self._driver.steps() + k) & 1] for k in range(len(starts))], dtype=np.int32)
         self._driver.run(ids, np.asarray(starts, dtype=np.int64))
         n = len(starts)
@@ -288,6 +299,10 @@ class B200Engine(Engine):
 
     def last_loss(self) -> float:
         self.w.stream.synchronize()
+        self._harvest(0)
+        self._harvest(1)
+        if self._driver is not None:
+            self._driver.flush()
         if self._driver_last is not None:
             return float(self.loss_ring[self._driver_last])
         return float(self.loss_ring[(self.step_idx - 1) % self.LOSS_RING])

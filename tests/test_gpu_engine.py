@@ -154,3 +154,49 @@ def test_served_push_mailbox_applier_tracks_oracle(lock):
     assert master.applier.alive()
     master.close()
     assert master.applier is None
+
+
+@pytest.mark.parametrize("opt", ["adam", "momentum", "rmsprop"])
+@pytest.mark.parametrize("max_batch", [1, 3, 8])
+def test_applier_batch_is_sequential_pushes(opt, max_batch):
+    """Four gradients posted at once are applied in ONE pass over the state (or max_batch at a time), and the result
+    equals four separate optimizer steps in mailbox order, each with its own step number - no gradient aggregation."""
+    import time
+    kw = dict(learning_rate=0.01)
+    if opt == "momentum":
+        kw["momentum"] = 0.9
+    spec = OptimizerSpec.from_tf_kwargs(opt, kw)
+    ir = GraphIR.from_metagraph(zoo.build("test_mlp"))
+    lp = compile_graph(ir, "x:0", "y:0")
+    need_w, need_wt = plan_publish_needs(lp)
+    lay = ParamLayout.build(ir.param_shapes(), need_w, need_wt)
+    dev = torch.device("cuda:0")
+    n_w = 4
+    master = MasterState(lay, spec, dev, n_mailboxes=n_w)
+    w0 = GraphProgram(ir).init_weights(seed=3)
+    master.load_weights(w0)
+    rng = np.random.default_rng(5)
+    grads = [[rng.standard_normal(s).astype(np.float32) for _, s in ir.param_shapes()] for _ in range(n_w)]
+    ps = ParameterServer(w0, spec, acquire_lock=True)
+    boxes = master._bytes[master.ml.mailboxes:master.ml.mailboxes + n_w * master.ml.mailbox_stride * 4].view(torch.float32)
+    boxes = boxes.view(n_w, master.ml.mailbox_stride)
+    flags = master._bytes[master.ml.flags:master.ml.flags + n_w * master.C.MB_WORDS * 4].view(torch.int32).view(n_w, master.C.MB_WORDS)
+    flags.zero_()
+    for w in range(n_w):
+        boxes[w, :lay.total] = torch.from_numpy(lay.flatten(grads[w])).to(dev)
+        LocalTransport(ps).push(grads[w])
+    flags[:, 0] = 1                                    # POSTED = 1 for every worker before the applier starts
+    torch.cuda.current_stream(dev).synchronize()
+    master.start_applier(True, scope_sys=False, grid=8, max_batch=max_batch)
+    t0 = time.time()
+    while master.counters()["pushes"] < n_w and time.time() - t0 < 10:
+        time.sleep(0.01)
+    cnt = master.counters()
+    assert cnt["pushes"] == n_w and cnt["step"] == n_w and cnt["version"] == n_w and cnt["lock"] == 0, cnt
+    assert flags[:, master.C.MB_APPLIED].cpu().tolist() == [1] * n_w
+    for a, b, v in zip(master.weights(), ps.weights(), ir.trainable):
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-6, err_msg=v.name)
+    # published bf16 operands match the final fp32 parameters
+    pub = lay.publish_reference(lay.flatten(master.weights()))
+    np.testing.assert_allclose(master.shadow.float().cpu().numpy(), torch.from_numpy(pub).to(torch.bfloat16).float().numpy(), rtol=0, atol=1e-2)
+    master.close()
