@@ -111,11 +111,16 @@ def run_ours(args, ctx) -> dict:
     sampler = ClockSampler(dev.index or 0).start() if ctx.rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
+    host0 = list(eng._driver.host_ns()) if getattr(eng, "_driver", None) is not None else None
     e0.record(eng.w.stream)
     e2e_steps(K, W)
     e1.record(eng.w.stream)
     eng.finish()                         # stream sync + wait until the master has applied this rank's last push
     t_wall = time.perf_counter() - t_wall0
+    host_us = None
+    if host0 is not None:
+        names = ("wait_slot", "h2d_enqueue", "event_handoff", "graph_launch", "record")
+        host_us = {n: (b - a) / K / 1e3 for n, a, b in zip(names, host0, eng._driver.host_ns())}
     sess.quiesce()
     e2e_ms = _max_over_ranks(ctx, e0.elapsed_time(e1))
     wall_ms = _max_over_ranks(ctx, t_wall * 1e3)
@@ -166,7 +171,8 @@ def run_ours(args, ctx) -> dict:
                          f"{rows * DIMS[0] * 4 >> 20} MiB > L2, a fresh minibatch H2D every step",
                    "kernels_per_step": plan.names(), "cuda_graph": bool(w.use_graphs)},
         "e2e": {"value": ctx.world * BATCH * K / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms / K,
-                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step), "wall_ms_per_step": wall_ms / K},
+                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step), "wall_ms_per_step": wall_ms / K,
+                "host_us_per_step": host_us},
         "gpu_launches": int(launches * K * ctx.world),
         "warm_cache_ms_per_step": warm_ms / K,
         "clocks": clocks, "final_loss": last_loss, "master_counters": counters,

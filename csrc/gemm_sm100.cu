@@ -20,6 +20,7 @@
 // The B operand may live in *peer* GPU memory: the tensor map simply carries the peer-mapped
 // address, and the TMA engine pulls weight tiles over NVLink while the MMA pipeline runs
 // (the "pull-fused" first dense layer of the parameter-server design).
+#include <cstdlib>
 #include "sm100_ptx.cuh"
 #include "sf_api.h"
 
@@ -46,6 +47,143 @@ __device__ __forceinline__ float act_bwd_from_out(float a, int act) {
     case SF_ACT_TANH: return 1.f - a * a;
     default: return 1.f;
   }
+}
+
+// One 32-column chunk of a thread's output row: everything between the accumulator (v, already in registers) and
+// global memory.  `aux_pref` / `tgt_pref` are the act'(a) operand / label row of this chunk when the caller fetched
+// them before the accumulator wait (nullptr: read here).  kLoss compiles the fused softmax-CE / MSE heads in.
+template <bool kLoss>
+__device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32_t (&v)[32], const float* s_bias32, int row, bool row_ok,
+                                          int col0, int M, int N, int lane, const uint4* aux_pref, const float* tgt_pref) {
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha + s_bias32[j];
+    if (ep.act != SF_ACT_NONE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
+    }
+    if (kLoss && ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
+      // whole row lives in this thread (host guarantees N <= 32): softmax + CE + gradient in registers
+      float ysum = 0.f, zy = 0.f, mx = -INFINITY;
+      const float* yv = tgt_pref;                         // N <= 32: the single chunk was prefetched
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (row_ok && col0 + j < N) mx = fmaxf(mx, f[j]);
+      float se = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (col0 + j < N && row_ok) {
+          se += __expf(f[j] - mx);
+          ysum += yv[j];
+          zy += yv[j] * f[j];
+        }
+      }
+      const float inv_b = 1.f / static_cast<float>(M);
+      float lrow = row_ok ? ((mx + __logf(se)) * ysum - zy) * inv_b : 0.f;
+      const float inv_se = row_ok ? 1.f / se : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        f[j] = (col0 + j < N && row_ok) ? (__expf(f[j] - mx) * inv_se * ysum - yv[j]) * inv_b : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
+      if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow);
+    } else if (kLoss && ep.loss_mode == SF_LOSS_MSE) {
+      const float scale = 2.f / (static_cast<float>(M) * static_cast<float>(N));
+      const float* tp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target + col0;
+      float lrow = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (row_ok && col0 + j < N) {
+          const float d = f[j] - (tgt_pref != nullptr ? tgt_pref[j] : tp[j]);
+          lrow += d * d;
+          f[j] = d * scale * act_bwd_from_out(f[j], ep.act);
+        } else {
+          f[j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
+      if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow * 0.5f * scale);
+    }
+    if (ep.aux != nullptr && row_ok) {
+      const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + col0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (col0 + g * 8 < ep.ld_aux) {
+          const uint4 q = (aux_pref != nullptr) ? aux_pref[g] : *reinterpret_cast<const uint4*>(ap + g * 8);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float2 a2 = __bfloat1622float2(h[t]);
+            f[g * 8 + 2 * t] *= act_bwd_from_out(a2.x, ep.aux_act);
+            f[g * 8 + 2 * t + 1] *= act_bwd_from_out(a2.y, ep.aux_act);
+          }
+        }
+      }
+    }
+    // padded columns / rows contribute exact zeros everywhere below
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j >= N || !row_ok) f[j] = 0.f;
+
+    if (ep.colsum != nullptr) {
+      // transpose-reduce over the 32 rows held by this warp: 31 shuffles, lane j ends up with
+      // the sum of column col0 + j.
+      float r[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = f[j];
+#pragma unroll
+      for (int w = 16; w >= 1; w >>= 1) {
+        const bool upper = (lane & w) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+          const float send = upper ? r[j] : r[j + w];
+          const float keep = upper ? r[j + w] : r[j];
+          r[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+      }
+      // after the butterfly lane l holds column bitrev-free index: position is l itself
+      if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, r[0]);
+    }
+
+    if (ep.out_f32 != nullptr && row_ok) {
+      float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+      if (ep.accumulate) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) atomicAdd(op + j, f[j]);
+      } else if ((ep.ld_f32 & 3) == 0 && col0 + 32 <= N &&
+                 (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(op + 4 * g) =
+              make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < N) op[j] = f[j];
+      }
+    }
+    if (ep.out_bf16 != nullptr && row_ok) {
+      __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (col0 + g * 8 < ep.ld_bf16) {
+          uint4 q;
+          q.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+          q.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+          q.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+          q.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+          *reinterpret_cast<uint4*>(op + g * 8) = q;
+        }
+      }
+    }
+    if (ep.outT_bf16 != nullptr && row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N)
+          ep.outT_bf16[static_cast<size_t>(col0 + j) * ep.ld_t + row] = __float2bfloat16(f[j]);
+    }
 }
 
 template <int BN>
@@ -192,135 +330,7 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld_wait();
       const int col0 = n0 + c * 32;
       if (col0 >= ep.n_store_limit) break;   // whole chunk outside every output pitch
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha + s_bias[c * 32 + j];
-      if (ep.act != SF_ACT_NONE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
-      }
-      if (ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
-        // whole row lives in this thread (host guarantees N <= 32): softmax + CE + gradient in registers
-        float ysum = 0.f, zy = 0.f, mx = -INFINITY;
-        float* yv = tgt0;                                   // N <= 32: the single chunk was prefetched
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (row_ok && col0 + j < N) mx = fmaxf(mx, f[j]);
-        float se = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (col0 + j < N && row_ok) {
-            se += __expf(f[j] - mx);
-            ysum += yv[j];
-            zy += yv[j] * f[j];
-          }
-        }
-        const float inv_b = 1.f / static_cast<float>(M);
-        float lrow = row_ok ? ((mx + __logf(se)) * ysum - zy) * inv_b : 0.f;
-        const float inv_se = row_ok ? 1.f / se : 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          f[j] = (col0 + j < N && row_ok) ? (__expf(f[j] - mx) * inv_se * ysum - yv[j]) * inv_b : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
-        if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow);
-      } else if (ep.loss_mode == SF_LOSS_MSE) {
-        const float scale = 2.f / (static_cast<float>(M) * static_cast<float>(N));
-        const float* tp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target + col0;
-        float lrow = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (row_ok && col0 + j < N) {
-            const float d = f[j] - (c == 0 ? tgt0[j] : tp[j]);
-            lrow += d * d;
-            f[j] = d * scale * act_bwd_from_out(f[j], ep.act);
-          } else {
-            f[j] = 0.f;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
-        if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow * 0.5f * scale);
-      }
-      if (ep.aux != nullptr && row_ok) {
-        const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + col0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (col0 + g * 8 < ep.ld_aux) {
-            const uint4 q = (c == 0) ? aux0[g] : *reinterpret_cast<const uint4*>(ap + g * 8);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 a2 = __bfloat1622float2(h[t]);
-              f[g * 8 + 2 * t] *= act_bwd_from_out(a2.x, ep.aux_act);
-              f[g * 8 + 2 * t + 1] *= act_bwd_from_out(a2.y, ep.aux_act);
-            }
-          }
-        }
-      }
-      // padded columns / rows contribute exact zeros everywhere below
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j >= N || !row_ok) f[j] = 0.f;
-
-      if (ep.colsum != nullptr) {
-        // transpose-reduce over the 32 rows held by this warp: 31 shuffles, lane j ends up with
-        // the sum of column col0 + j.
-        float r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = f[j];
-#pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) {
-          const bool upper = (lane & w) != 0;
-#pragma unroll
-          for (int j = 0; j < w; ++j) {
-            const float send = upper ? r[j] : r[j + w];
-            const float keep = upper ? r[j + w] : r[j];
-            r[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
-          }
-        }
-        // after the butterfly lane l holds column bitrev-free index: position is l itself
-        if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, r[0]);
-      }
-
-      if (ep.out_f32 != nullptr && row_ok) {
-        float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
-        if (ep.accumulate) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) atomicAdd(op + j, f[j]);
-        } else if ((ep.ld_f32 & 3) == 0 && col0 + 32 <= N &&
-                   (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g)
-            *reinterpret_cast<float4*>(op + 4 * g) =
-                make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) op[j] = f[j];
-        }
-      }
-      if (ep.out_bf16 != nullptr && row_ok) {
-        __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (col0 + g * 8 < ep.ld_bf16) {
-            uint4 q;
-            q.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-            q.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-            q.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-            q.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(op + g * 8) = q;
-          }
-        }
-      }
-      if (ep.outT_bf16 != nullptr && row_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < N)
-            ep.outT_bf16[static_cast<size_t>(col0 + j) * ep.ld_t + row] = __float2bfloat16(f[j]);
-      }
+      epi_chunk<true>(ep, v, s_bias + c * 32, row, row_ok, col0, M, N, lane, c == 0 ? aux0 : nullptr, c == 0 ? tgt0 : nullptr);
     }
     if (tr) {                             // phase record: wait start / accumulator ready / epilogue done
       const unsigned int i = atomicAdd(&g_trace_n, 1u);
@@ -392,9 +402,20 @@ extern "C" int sf_gemm_prepare(SfGemm* g) {
   if (g->M <= 0 || g->N <= 0 || g->K <= 0) return -2;
   if (g->bn == 0) g->bn = sf_gemm_pick_bn(g->M, g->N);
   if (g->split_k <= 0) g->split_k = 1;
+  // large, un-split problems go to the persistent 2-CTA kernel (gemm_pair_sm100.cu): 256x256 tiles per CTA pair
+  {
+    const long long pair_tiles = static_cast<long long>((g->M + 255) / 256) * ((g->N + 255) / 256);
+    const bool eligible = g->split_k == 1 && g->ep.loss_mode == SF_LOSS_NONE && g->M >= 256 && g->N >= 256;
+    const char* env = getenv("SPARKFLOW_GEMM_PAIR");
+    int want = g->pair;
+    if (env != nullptr && want < 0) want = atoi(env);
+    if (want < 0) want = (g->bn == 256 && pair_tiles >= 74 && g->K >= 512) ? 1 : 0;
+    g->pair = (want > 0 && eligible) ? 1 : 0;
+    if (g->pair) g->bn = 256;
+  }
   int rc = sf_make_tmap_bf16_kmajor(&g->tmA, g->a, g->M, g->K, g->lda, sf::kBM);
   if (rc) return rc;
-  rc = sf_make_tmap_bf16_kmajor(&g->tmB, g->b, g->N, g->K, g->ldb, g->bn);
+  rc = sf_make_tmap_bf16_kmajor(&g->tmB, g->b, g->N, g->K, g->ldb, g->pair ? 128 : g->bn);
   if (rc) return rc;
   const int total_kb = (g->K + sf::kBK - 1) / sf::kBK;
   if (g->split_k > total_kb) g->split_k = total_kb;
@@ -429,6 +450,7 @@ static cudaError_t launch_bn(const SfGemm* g, cudaStream_t st) {
 }
 
 extern "C" int sf_gemm_launch(const SfGemm* g, cudaStream_t st) {
+  if (g->pair) return sf_gemm_pair_launch(g, st);
   cudaError_t e;
   switch (g->bn) {
     case 32: e = launch_bn<32>(g, st); break;

@@ -1,5 +1,6 @@
 // Unity translation unit for all device code (one copy of the sf::g_sf_error_code symbol).
 #include "gemm_sm100.cu"
+#include "gemm_pair_sm100.cu"
 #include "elementwise.cu"
 #include "optim_push.cu"
 #include "conv.cu"
@@ -19,7 +20,7 @@
   SF_PRELOAD((sf::K<SF_OPT_PROXIMAL_SGD, SYS>))
 
 extern "C" int sf_preload_kernels() {
-  SF_PRELOAD(sf::sf_gemm_kernel<32>); SF_PRELOAD(sf::sf_gemm_kernel<64>); SF_PRELOAD(sf::sf_gemm_kernel<128>); SF_PRELOAD(sf::sf_gemm_kernel<256>);
+  SF_PRELOAD(sf::sf_gemm_kernel<32>); SF_PRELOAD(sf::sf_gemm_kernel<64>); SF_PRELOAD(sf::sf_gemm_kernel<128>); SF_PRELOAD(sf::sf_gemm_kernel<256>); SF_PRELOAD(sf::sf_gemm_pair_kernel);
   SF_PRELOAD(sf::cast_transpose_kernel<false>); SF_PRELOAD(sf::cast_transpose_kernel<true>);
   SF_PRELOAD(sf::softmax_xent_kernel); SF_PRELOAD(sf::mse_kernel); SF_PRELOAD(sf::argmax_rows_kernel);
   SF_PRELOAD(sf::im2col_kernel); SF_PRELOAD(sf::col2im_kernel); SF_PRELOAD(sf::maxpool_fwd_kernel); SF_PRELOAD(sf::maxpool_bwd_kernel);

@@ -9,6 +9,7 @@
 
 #include <atomic>
 #include <cstring>
+#include <chrono>
 #include <thread>
 #include <functional>
 #include <memory>
@@ -62,6 +63,8 @@ struct Gemm {
     g.ldb = getd<int>(d, "ldb", g.K);
     g.bn = getd<int>(d, "bn", 0);
     g.split_k = getd<int>(d, "split_k", 1);
+    g.pair = getd<int>(d, "pair", -1);
+    g.pair_ctas = getd<int>(d, "pair_ctas", 0);
     g.ep.out_f32 = P<float>(getd<uintptr_t>(d, "out_f32", 0));
     g.ep.ld_f32 = getd<int>(d, "ld_f32", g.N);
     g.ep.out_bf16 = P<__nv_bfloat16>(getd<uintptr_t>(d, "out_bf16", 0));
@@ -89,6 +92,7 @@ struct Gemm {
   void launch(uintptr_t stream) const { ck_rc(sf_gemm_launch(&g, S(stream)), "sf_gemm_launch"); }
   int bn() const { return g.bn; }
   int split_k() const { return g.split_k; }
+  int pair() const { return g.pair; }
   py::tuple grid() const {
     return py::make_tuple((g.N + g.bn - 1) / g.bn, (g.M + 127) / 128, g.split_k);
   }
@@ -363,29 +367,40 @@ class StepDriver {
     const int32_t* ip = ids.data();
     const int64_t* sp = starts.data();
     py::gil_scoped_release nogil;
+    using clk = std::chrono::steady_clock;
+    auto ns = [](clk::time_point a, clk::time_point b) { return std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
     for (int k = 0; k < n; ++k) {
       if (ip[k] < 0 || ip[k] >= static_cast<int>(entries_.size())) throw std::runtime_error("StepDriver.run: bad plan id");
       Entry& e = entries_[ip[k]];
+      const auto t0 = clk::now();
       if (e.primed) {
         ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(slot free)");
         harvest(e);
       }
+      const auto t1 = clk::now();
       ck(cudaMemcpyAsync(e.x_stage, x_host_ + static_cast<size_t>(sp[k]) * x_row_, static_cast<size_t>(e.batch) * x_row_,
                          cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(x)");
       if (e.y_stage && y_host_)
         ck(cudaMemcpyAsync(e.y_stage, y_host_ + static_cast<size_t>(sp[k]) * y_row_, static_cast<size_t>(e.batch) * y_row_,
                            cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(y)");
+      const auto t2 = clk::now();
       ck(cudaEventRecord(e.ready, copy_), "cudaEventRecord(ready)");
       ck(cudaStreamWaitEvent(compute_, e.ready, 0), "cudaStreamWaitEvent");
+      const auto t3 = clk::now();
       e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
+      const auto t4 = clk::now();
       // the step's last kernel stores the loss straight into this entry's pinned host word (zero-copy D2H: no
       // copy-engine operation on the compute stream); it is moved into the ring once the step has retired
       ck(cudaEventRecord(e.free_, compute_), "cudaEventRecord(free)");
+      const auto t5 = clk::now();
+      host_ns_[0] += ns(t0, t1); host_ns_[1] += ns(t1, t2); host_ns_[2] += ns(t2, t3); host_ns_[3] += ns(t3, t4); host_ns_[4] += ns(t4, t5);
       e.pending = step_;
       e.primed = true;
       ++step_;
     }
   }
+  // host nanoseconds spent per phase since construction: wait-for-slot, H2D enqueue, event hand-off, graph launch, record
+  std::vector<long long> host_ns() const { return std::vector<long long>(host_ns_, host_ns_ + 5); }
   long long steps() const { return step_; }
   // wait for every in-flight step and move their losses into the ring
   void flush() {
@@ -422,6 +437,7 @@ class StepDriver {
   float* ring_;
   int ring_len_;
   long long step_ = 0;
+  long long host_ns_[5] = {0, 0, 0, 0, 0};
   std::vector<Entry> entries_;
 };
 
@@ -572,6 +588,7 @@ PYBIND11_MODULE(_C, m) {
       .def("launch", &Gemm::launch)
       .def_property_readonly("bn", &Gemm::bn)
       .def_property_readonly("split_k", &Gemm::split_k)
+      .def_property_readonly("pair", &Gemm::pair)
       .def_property_readonly("grid", &Gemm::grid);
 
   py::class_<Plan>(m, "Plan")
@@ -686,7 +703,8 @@ PYBIND11_MODULE(_C, m) {
       .def("add_plan", &StepDriver::add_plan)
       .def("run", &StepDriver::run)
       .def("steps", &StepDriver::steps)
-      .def("flush", &StepDriver::flush);
+      .def("flush", &StepDriver::flush)
+      .def("host_ns", &StepDriver::host_ns);
 
   // direct (un-planned) entry points, used by tests and the eager paths
   m.def("cast_transpose", [](uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,

@@ -58,6 +58,8 @@ struct SfGemm {
   int bn;                         // 0 = auto
   int split_k;                    // 0/1 = none
   int kblocks_per_split;          // filled
+  int pair;                       // in: -1 = auto, 0 = one-CTA kernel, 1 = force the 2-CTA persistent kernel; out: 0 / 1
+  int pair_ctas;                  // CTAs of the persistent 2-CTA kernel (0 = 148)
   SfGemmEpilogue ep;
 };
 
@@ -67,6 +69,7 @@ extern "C" {
 
 int sf_gemm_prepare(SfGemm* g);
 int sf_gemm_launch(const SfGemm* g, cudaStream_t st);
+int sf_gemm_pair_launch(const SfGemm* g, cudaStream_t st);
 int sf_gemm_pick_bn(int M, int N);
 unsigned int sf_read_error_code();
 int sf_init_error_channel();

@@ -38,7 +38,7 @@ def _bf16_pad(x, ld):
 
 
 def _run_gemm(C, M, N, K, bn=0, split_k=1, bias=False, act=None, aux_act=None, colsum=False, want_bf16=True,
-              want_t=True, accumulate=False, seed=0):
+              want_t=True, accumulate=False, seed=0, pair=-1, pair_ctas=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     a = torch.randn(M, K, device="cuda", generator=g) * 0.5
     b = torch.randn(N, K, device="cuda", generator=g) * 0.5
@@ -58,7 +58,8 @@ def _run_gemm(C, M, N, K, bn=0, split_k=1, bias=False, act=None, aux_act=None, c
     d = dict(a=native.ptr(a16), b=native.ptr(b16), M=M, N=N, K=K, lda=lda, ldb=ldb, bn=bn, split_k=split_k,
              out_f32=native.ptr(out_f32), ld_f32=N, out_bf16=native.ptr(out_bf16), ld_bf16=ldn,
              outT_bf16=native.ptr(outT), ld_t=ldt, bias=native.ptr(bias_t), act=ACT[act], aux=native.ptr(aux),
-             ld_aux=ldn, aux_act=ACT[aux_act], colsum=native.ptr(cs), alpha=1.0, accumulate=int(accumulate))
+             ld_aux=ldn, aux_act=ACT[aux_act], colsum=native.ptr(cs), alpha=1.0, accumulate=int(accumulate), pair=pair,
+             pair_ctas=pair_ctas)
     gm = C.Gemm(d)
     gm.launch(native.current_stream())
     torch.cuda.synchronize()
@@ -114,6 +115,21 @@ def test_gemm_split_k_accumulate(C):
 
 def test_gemm_large(C):
     _run_gemm(C, 2048, 2048, 2048, want_t=False)
+
+
+@pytest.mark.parametrize("M,N,K,ctas", [(512, 512, 256, 0), (1000, 520, 1000, 0), (256, 256, 64, 0), (2048, 2048, 512, 8),
+                                          (1536, 1280, 320, 6), (4096, 4096, 1024, 0)])
+def test_gemm_pair_kernel(C, M, N, K, ctas):
+    """persistent 2-CTA (cta_group::2) kernel: tails, more tiles than CTA pairs (double-buffered TMEM phases)"""
+    gm = _run_gemm(C, M, N, K, pair=1, pair_ctas=ctas, want_t=(M * N <= 1 << 22))
+    assert gm.pair == 1
+
+
+def test_gemm_pair_kernel_epilogues(C):
+    gm = _run_gemm(C, 768, 512, 512, pair=1, bias=True, act="relu")
+    assert gm.pair == 1
+    _run_gemm(C, 768, 512, 512, pair=1, aux_act="sigmoid", colsum=True)
+    _run_gemm(C, 512, 768, 256, pair=1, want_bf16=False, want_t=False, accumulate=True)
 
 
 def test_cast_transpose(C):

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_engine.py tests/test_gpu_kernels.py -m gpu -x -q > gpurun_out/t17_tests.log 2>&1; tail -4 gpurun_out/t17_tests.log
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:sf_gemm_kernel -s 4 -c 1 -f -o gpurun_out/prof_gemm8192 python tools/profile_gemm.py 8192 8192 8192 > gpurun_out/t17_ncu_gemm.log 2>&1; tail -2 gpurun_out/t17_ncu_gemm.log
-timeout 400 ncu --set full --clock-control none --import-source on -k 'regex:gemm|push|pull|cast' -s 44 -c 11 -f -o gpurun_out/prof_step python tools/profile_step.py 6 > gpurun_out/t17_ncu_step.log 2>&1; tail -2 gpurun_out/t17_ncu_step.log
-timeout 300 python bench.py --steps 300 --warmup 30 > gpurun_out/t17_bench_lock.json 2> gpurun_out/t17_bench_lock.err; cut -c1-400 gpurun_out/t17_bench_lock.json
-timeout 300 python bench.py --steps 300 --warmup 30 --mode hogwild > gpurun_out/t17_bench_hog.json 2> gpurun_out/t17_bench_hog.err; cut -c1-400 gpurun_out/t17_bench_hog.json
-ls -la gpurun_out/*.ncu-rep
+timeout 300 python tools/trace_e2e.py 2>&1 | tail -3
+timeout 300 python bench.py --steps 300 --warmup 30 --mode hogwild > gpurun_out/t19_bench.json 2> gpurun_out/t19_bench.err; python -c "
+import json;d=json.load(open('gpurun_out/t19_bench.json'));print('1gpu hog dev',d['value']/1e6,d['ms_per_step']*1e3,'warm',d['warm_cache_ms_per_step']*1e3,'e2e',d['e2e'])"
+timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "gemm" > gpurun_out/t19_gemm_tests.log 2>&1; tail -15 gpurun_out/t19_gemm_tests.log
+timeout 300 python tools/bench_gemm.py 2>&1 | tail -8
