@@ -363,6 +363,15 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
   }
 }
 
+// step-completion word for a spinning host: ((uint32*)loss_out)[1] = ++*done_dev, ordered after the loss store
+__device__ __forceinline__ void signal_done(float* loss_out, unsigned int* done_dev) {
+  if (done_dev == nullptr) return;
+  const unsigned int v = *done_dev + 1;
+  *done_dev = v;
+  asm volatile("fence.acq_rel.sys;" ::: "memory");
+  st_release_sys(reinterpret_cast<uint32_t*>(loss_out) + 1, v);
+}
+
 template <int OPT, bool SYS>
 __global__ void __launch_bounds__(kPushThreads, 1)
 push_kernel(const SfPushArgs a, uint32_t* local_sync) {
@@ -420,6 +429,7 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
         *a.loss_out = *a.loss_acc;
         *a.loss_acc = 0.f;
       }
+      signal_done(a.loss_out, a.done_dev);
       if (a.drop) {
         lk_red_relaxed<SYS>(a.ctrl + SF_CTRL_DROPPED, 1u);
       } else {
@@ -555,6 +565,7 @@ post_kernel(const SfPostArgs a, uint32_t* local_sync) {
         *a.loss_out = *a.loss_acc;
         *a.loss_acc = 0.f;
       }
+      signal_done(a.loss_out, a.done_dev);
       if (!a.drop) {
         st_release_gpu(local_sync + 4, s_seq + 1);
         st_release_sys(a.flags + SF_MB_POSTED, s_seq + 1);

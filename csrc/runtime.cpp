@@ -8,6 +8,7 @@
 #include <pybind11/stl.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <thread>
@@ -134,6 +135,7 @@ SfPushArgs parse_push(const py::dict& d) {
   a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
   a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
   a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
+  a.done_dev = P<unsigned int>(getd<uintptr_t>(d, "done_dev", 0));
   a.segs = P<const SfTensorSeg>(getd<uintptr_t>(d, "segs", 0));
   a.tile_map = P<const int32_t>(getd<uintptr_t>(d, "tile_map", 0));
   a.num_tiles = getd<int>(d, "num_tiles", 0);
@@ -175,9 +177,28 @@ SfPostArgs parse_post(const py::dict& d) {
   a.flags = P<uint32_t>(getd<uintptr_t>(d, "flags", 0));
   a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
   a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
+  a.done_dev = P<unsigned int>(getd<uintptr_t>(d, "done_dev", 0));
   a.n = getd<size_t>(d, "n", 0);
   a.drop = getd<int>(d, "drop", 0);
   if (!a.grad || !a.mailbox || !a.flags || a.n == 0 || (a.n % 4)) throw std::runtime_error("post: grad/mailbox/flags/n (multiple of 4) are required");
+  return a;
+}
+
+SfFetchArgs parse_fetch(const py::dict& d) {
+  SfFetchArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.desc = P<const SfFetchDesc>(getd<uintptr_t>(d, "desc", 0));
+  a.sched = P<const long long>(getd<uintptr_t>(d, "sched", 0));
+  a.ring_mask = getd<unsigned int>(d, "ring_mask", 0);
+  a.counter = P<unsigned int>(getd<uintptr_t>(d, "counter", 0));
+  a.sync = P<unsigned int>(getd<uintptr_t>(d, "sync", 0));
+  a.x_out = P<float>(getd<uintptr_t>(d, "x_out", 0));
+  a.y_out = P<float>(getd<uintptr_t>(d, "y_out", 0));
+  a.rows = getd<int>(d, "rows", 0);
+  a.cols = getd<int>(d, "cols", 0);
+  a.y_cols = getd<int>(d, "y_cols", 0);
+  if (!a.desc || !a.sched || !a.counter || !a.sync || !a.x_out || a.rows <= 0 || a.cols <= 0)
+    throw std::runtime_error("fetch: desc/sched/counter/sync/x_out/rows/cols are required");
   return a;
 }
 
@@ -338,7 +359,13 @@ class StepDriver {
   StepDriver(uintptr_t compute_stream, uintptr_t copy_stream, uintptr_t x_host, size_t x_row_bytes, uintptr_t y_host,
              size_t y_row_bytes, uintptr_t loss_ring, int ring_len)
       : compute_(S(compute_stream)), copy_(S(copy_stream)), x_host_(P<const char>(x_host)), x_row_(x_row_bytes),
-        y_host_(P<const char>(y_host)), y_row_(y_row_bytes), ring_(P<float>(loss_ring)), ring_len_(ring_len) {}
+        y_host_(P<const char>(y_host)), y_row_(y_row_bytes), ring_(P<float>(loss_ring)), ring_len_(ring_len) {
+    auto flag = [](const char* n) { const char* v = getenv(n); return v != nullptr && v[0] == '1'; };
+    probe_ = flag("SPARKFLOW_DRV_PROBE");
+    no_h2d_ = flag("SPARKFLOW_DRV_NO_H2D");
+    if (const char* f = getenv("SPARKFLOW_DRV_H2D_FRAC")) h2d_frac_ = atof(f);      // diagnostics only
+    if (probe_) ck(cudaEventCreate(&base_), "cudaEventCreate(base)");
+  }
   ~StepDriver() {
     for (auto& e : entries_) {
       if (e.ready) cudaEventDestroy(e.ready);
@@ -354,8 +381,10 @@ class StepDriver {
     e.y_stage = P<char>(y_stage);
     e.loss_out = P<float>(loss_out);
     e.batch = batch;
-    ck(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming), "cudaEventCreate");
-    ck(cudaEventCreateWithFlags(&e.free_, cudaEventDisableTiming), "cudaEventCreate");
+    const unsigned int evf = probe_ ? cudaEventDefault : cudaEventDisableTiming;
+    ck(cudaEventCreateWithFlags(&e.ready, evf), "cudaEventCreate");
+    ck(cudaEventCreateWithFlags(&e.free_, evf), "cudaEventCreate");
+    if (probe_) ck(cudaEventCreateWithFlags(&e.start, evf), "cudaEventCreate");
     entries_.push_back(e);
     return static_cast<int>(entries_.size()) - 1;
   }
@@ -374,18 +403,24 @@ class StepDriver {
       Entry& e = entries_[ip[k]];
       const auto t0 = clk::now();
       if (e.primed) {
-        ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(slot free)");
+        wait_free(e);
         harvest(e);
       }
       const auto t1 = clk::now();
-      ck(cudaMemcpyAsync(e.x_stage, x_host_ + static_cast<size_t>(sp[k]) * x_row_, static_cast<size_t>(e.batch) * x_row_,
-                         cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(x)");
-      if (e.y_stage && y_host_)
+      if (probe_ && !base_recorded_) {
+        ck(cudaEventRecord(base_, compute_), "cudaEventRecord(base)");
+        base_recorded_ = true;
+      }
+      if (!no_h2d_)
+      ck(cudaMemcpyAsync(e.x_stage, x_host_ + static_cast<size_t>(sp[k]) * x_row_,
+                         static_cast<size_t>(static_cast<double>(e.batch) * h2d_frac_) * x_row_, cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(x)");
+      if (e.y_stage && y_host_ && !no_h2d_)
         ck(cudaMemcpyAsync(e.y_stage, y_host_ + static_cast<size_t>(sp[k]) * y_row_, static_cast<size_t>(e.batch) * y_row_,
                            cudaMemcpyHostToDevice, copy_), "cudaMemcpyAsync(y)");
       const auto t2 = clk::now();
       ck(cudaEventRecord(e.ready, copy_), "cudaEventRecord(ready)");
       ck(cudaStreamWaitEvent(compute_, e.ready, 0), "cudaStreamWaitEvent");
+      if (probe_) ck(cudaEventRecord(e.start, compute_), "cudaEventRecord(start)");
       const auto t3 = clk::now();
       e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
       const auto t4 = clk::now();
@@ -399,34 +434,138 @@ class StepDriver {
       ++step_;
     }
   }
+  // ---- zero-copy mode: the step graphs fetch their successor's minibatch themselves (fetch_kernel on a side
+  // branch), so one step costs the host ONE cudaGraphLaunch: no copy-engine DMA, no events.  Completion is a pinned
+  // word the step's last kernel writes (spun on by this thread); the minibatch schedule is a pinned ring the
+  // fetch kernel reads.  Plans must be registered in slot order: the graph of slot s fetches into slot s+1.
+  // `self_fetch_plans[s]`: an (un-captured) plan that fetches + prepares input set s, used for the first minibatch of a call
+  void enable_fetch(uintptr_t sched_host, int ring_len, py::list self_fetch_plans) {
+    if (ring_len <= 0 || (ring_len & (ring_len - 1))) throw std::runtime_error("StepDriver: schedule ring must be a power of two");
+    if (static_cast<size_t>(py::len(self_fetch_plans)) != entries_.size()) throw std::runtime_error("StepDriver: one fetch plan per step plan");
+    sched_ = P<long long>(sched_host);
+    sched_mask_ = static_cast<unsigned int>(ring_len - 1);
+    self_fetch_.clear();
+    self_fetch_keep_.clear();
+    for (auto item : self_fetch_plans) {
+      self_fetch_keep_.push_back(py::reinterpret_borrow<py::object>(item));
+      self_fetch_.push_back(item.cast<Plan*>());
+    }
+    fetch_mode_ = true;
+  }
+  void run_fetch(py::array_t<int32_t, py::array::c_style | py::array::forcecast> ids,
+                 py::array_t<int64_t, py::array::c_style | py::array::forcecast> starts) {
+    if (!fetch_mode_) throw std::runtime_error("StepDriver.run_fetch: enable_fetch first");
+    const int n = static_cast<int>(ids.size());
+    if (starts.size() != n) throw std::runtime_error("StepDriver.run_fetch: ids/starts length mismatch");
+    if (n == 0) return;
+    const int32_t* ip = ids.data();
+    const int64_t* sp = starts.data();
+    const int S_ = static_cast<int>(entries_.size());
+    py::gil_scoped_release nogil;
+    using clk = std::chrono::steady_clock;
+    auto ns = [](clk::time_point a, clk::time_point b) { return std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+    // the first minibatch of this call is fetched by a stand-alone launch into the first plan's input set
+    if (ip[0] < 0 || ip[0] >= S_) throw std::runtime_error("StepDriver.run_fetch: bad plan id");
+    sched_[fetch_seq_ & sched_mask_] = sp[0];
+    ++fetch_seq_;
+    self_fetch_[ip[0]]->run(reinterpret_cast<uintptr_t>(compute_));
+    for (int k = 0; k < n; ++k) {
+      if (ip[k] < 0 || ip[k] >= S_) throw std::runtime_error("StepDriver.run_fetch: bad plan id");
+      if (k > 0 && ip[k] != (ip[k - 1] + 1) % S_) throw std::runtime_error("StepDriver.run_fetch: plan ids must walk the slots in order");
+      Entry& e = entries_[ip[k]];
+      const auto t0 = clk::now();
+      wait_done(e);
+      const auto t1 = clk::now();
+      // what this graph's fetch node brings in: the next step's minibatch (the last one re-reads its own rows)
+      sched_[fetch_seq_ & sched_mask_] = sp[k + 1 < n ? k + 1 : k];
+      ++fetch_seq_;
+      std::atomic_thread_fence(std::memory_order_seq_cst);
+      const auto t2 = clk::now();
+      e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
+      const auto t3 = clk::now();
+      host_ns_[0] += ns(t0, t1); host_ns_[2] += ns(t1, t2); host_ns_[3] += ns(t2, t3);
+      ++e.launched;
+      e.pending = step_;
+      e.primed = true;
+      ++step_;
+    }
+  }
   // host nanoseconds spent per phase since construction: wait-for-slot, H2D enqueue, event hand-off, graph launch, record
   std::vector<long long> host_ns() const { return std::vector<long long>(host_ns_, host_ns_ + 5); }
+  std::vector<float> probe() const { return probe_rows_; }
   long long steps() const { return step_; }
   // wait for every in-flight step and move their losses into the ring
   void flush() {
     py::gil_scoped_release nogil;
     for (auto& e : entries_)
       if (e.primed && e.pending >= 0) {
-        ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(flush)");
+        if (fetch_mode_) wait_done(e);
+        else ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(flush)");
         harvest(e);
       }
   }
 
  private:
   struct Entry;
+  // The loop thread never sleeps: a blocked thread's wake-up (tens of microseconds, more inside a VM) would land on
+  // the critical path of the next step.  SPARKFLOW_DRIVER_BLOCK=1 restores cudaEventSynchronize.
+  void wait_free(Entry& e) {
+    static const bool block = [] { const char* v = getenv("SPARKFLOW_DRIVER_BLOCK"); return v != nullptr && v[0] == '1'; }();
+    if (block) {
+      ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(slot free)");
+      return;
+    }
+    cudaError_t q;
+    while ((q = cudaEventQuery(e.free_)) == cudaErrorNotReady) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+    }
+    ck(q, "cudaEventQuery(slot free)");
+  }
+  // zero-copy mode: spin on the pinned completion word written by the step's last kernel (no CUDA call at all)
+  void wait_done(Entry& e) {
+    if (e.launched == 0) return;
+    volatile unsigned int* done = reinterpret_cast<volatile unsigned int*>(e.loss_out) + 1;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long long spins = 0;
+    while (static_cast<int>(*done - static_cast<unsigned int>(e.launched)) < 0) {
+#if defined(__x86_64__)
+      __builtin_ia32_pause();
+#endif
+      if ((++spins & 0xFFFFF) == 0) {
+        if (cudaStreamQuery(compute_) != cudaErrorNotReady && static_cast<int>(*done - static_cast<unsigned int>(e.launched)) < 0 &&
+            std::chrono::steady_clock::now() - t0 > std::chrono::seconds(5))
+          throw std::runtime_error("StepDriver: the step's completion word never arrived (device error?)");
+      }
+    }
+    if (e.pending >= 0) ring_[e.pending % ring_len_] = *const_cast<volatile float*>(e.loss_out);
+    e.pending = -1;
+  }
   void harvest(Entry& e) {
+    if (probe_ && !fetch_mode_ && e.pending >= 0 && probe_rows_.size() < 4096 * 4) {
+      float a = 0.f, b = 0.f, c = 0.f;
+      cudaEventElapsedTime(&a, base_, e.ready);
+      cudaEventElapsedTime(&b, base_, e.start);
+      cudaEventElapsedTime(&c, base_, e.free_);
+      probe_rows_.push_back(static_cast<float>(e.pending));
+      probe_rows_.push_back(a * 1e3f);
+      probe_rows_.push_back(b * 1e3f);
+      probe_rows_.push_back(c * 1e3f);
+    }
     if (e.pending >= 0) ring_[e.pending % ring_len_] = *const_cast<volatile float*>(e.loss_out);
     e.pending = -1;
   }
   struct Entry {
     long long pending = -1;
+    unsigned long long launched = 0;      // zero-copy mode: graph launches so far (the completion word counts them)
     py::object keep;
     Plan* plan = nullptr;
     char* x_stage = nullptr;
     char* y_stage = nullptr;
     float* loss_out = nullptr;
     int batch = 0;
-    cudaEvent_t ready = nullptr, free_ = nullptr;
+    cudaEvent_t ready = nullptr, free_ = nullptr, start = nullptr;
     bool primed = false;
   };
   cudaStream_t compute_, copy_;
@@ -438,6 +577,16 @@ class StepDriver {
   int ring_len_;
   long long step_ = 0;
   long long host_ns_[5] = {0, 0, 0, 0, 0};
+  bool probe_ = false, no_h2d_ = false, base_recorded_ = false;
+  double h2d_frac_ = 1.0;
+  bool fetch_mode_ = false;
+  long long* sched_ = nullptr;
+  unsigned int sched_mask_ = 0;
+  unsigned long long fetch_seq_ = 0;
+  std::vector<Plan*> self_fetch_;
+  std::vector<py::object> self_fetch_keep_;
+  cudaEvent_t base_ = nullptr;
+  std::vector<float> probe_rows_;      // (step, H2D done, graph may start, graph done) in us since the first step
   std::vector<Entry> entries_;
 };
 
@@ -679,6 +828,10 @@ PYBIND11_MODULE(_C, m) {
              const SfPostArgs a = parse_post(d);
              p.add("post", [=](cudaStream_t st) { return sf_post_launch(&a, P<uint32_t>(local_sync), grid, st); });
            })
+      .def("add_fetch", [](Plan& p, const py::dict& d, int grid) {
+        const SfFetchArgs a = parse_fetch(d);
+        p.add("fetch", [=](cudaStream_t st) { return sf_fetch_launch(&a, grid, st); });
+      })
       .def("add_pull", [](Plan& p, const py::dict& d, uintptr_t local_sync, int grid) {
         const SfPullArgs a = parse_pull(d);
         p.add("pull", [=](cudaStream_t st) { return sf_pull_launch(&a, P<uint32_t>(local_sync), grid, st); });
@@ -704,9 +857,19 @@ PYBIND11_MODULE(_C, m) {
       .def("run", &StepDriver::run)
       .def("steps", &StepDriver::steps)
       .def("flush", &StepDriver::flush)
-      .def("host_ns", &StepDriver::host_ns);
+      .def("enable_fetch", &StepDriver::enable_fetch)
+      .def("run_fetch", &StepDriver::run_fetch)
+      .def("host_ns", &StepDriver::host_ns)
+      .def("probe", &StepDriver::probe);
 
   // direct (un-planned) entry points, used by tests and the eager paths
+  m.def("fetch", [](const py::dict& d, int grid, uintptr_t stream) {
+    const SfFetchArgs a = parse_fetch(d);
+    ck_rc(sf_fetch_launch(&a, grid, S(stream)), "fetch");
+  });
+  m.def("hostcopy", [](uintptr_t src_host, uintptr_t dst, size_t bytes, int grid, uintptr_t stream) {
+    ck_rc(sf_hostcopy(P<const void>(src_host), P<void>(dst), bytes, grid, S(stream)), "hostcopy");
+  });
   m.def("cast_transpose", [](uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, uintptr_t outT,
                              int ld_t, int rows, int cols, uintptr_t stream) {
     ck_rc(idx ? sf_gather_cast_transpose(P<const float>(in), ld_in, P<const int32_t>(idx), P<__nv_bfloat16>(out),

@@ -82,6 +82,25 @@ unsigned int sf_trace_count();
 // Elementwise / reduction kernels (elementwise.cu)
 // ---------------------------------------------------------------------------
 // fp32 [rows, cols] (ld_in) -> bf16 [rows, ld_out] and optional transpose bf16 [cols, ld_t]
+int sf_hostcopy(const void* src_host, void* dst, size_t bytes, int grid, cudaStream_t st);
+
+// In-graph minibatch fetch (zero-copy): SM loads stream one minibatch (features + label rows, fp32) from the pinned
+// host partition into device staging, for the step AFTER the one whose graph contains this node.
+struct SfFetchDesc {              // lives in DEVICE memory (rewritten when the host partition moves)
+  const float* x_host; const float* y_host;
+  long long x_ld, y_ld;           // floats per row
+};
+struct SfFetchArgs {
+  const SfFetchDesc* desc;
+  const long long* sched;         // pinned host ring of minibatch row starts, indexed by the fetch sequence number
+  unsigned int ring_mask;
+  unsigned int* counter;          // device: fetches completed so far (= sequence number of this fetch)
+  unsigned int* sync;             // device: CTA arrival counter
+  float* x_out;                   // [rows, cols] fp32
+  float* y_out;                   // [rows, y_cols] or nullptr
+  int rows, cols, y_cols;
+};
+int sf_fetch_launch(const SfFetchArgs* a, int grid, cudaStream_t st);
 int sf_cast_transpose(const float* in, int ld_in, __nv_bfloat16* out, int ld_out,
                       __nv_bfloat16* outT, int ld_t, int rows, int cols, cudaStream_t st);
 // gather rows by index then cast/transposes (minibatch assembly on the device)
@@ -144,7 +163,9 @@ struct SfPushArgs {
   int shadow_is_mc;
   float* grad;                    // local flat gradient (consumed, then zeroed for the next step)
   float* loss_acc;                // local: loss accumulated by the loss kernel (consumed + zeroed)
-  float* loss_out;                // local: last step's loss for the host to read
+  float* loss_out;                // last step's loss for the host to read (device or pinned host memory)
+  unsigned int* done_dev;         // optional device counter: incremented per push, its value is also stored to
+                                  // ((uint32*)loss_out)[1] (after the loss) so a host can spin on step completion
   const SfTensorSeg* segs;        // device array
   const int32_t* tile_map;        // device array [num_tiles * 3] = (seg, tile_row, tile_col)
   int num_tiles;
@@ -205,6 +226,7 @@ struct SfPostArgs {
   float* mailbox;                 // this worker's mailbox in master memory (peer mapped)
   uint32_t* flags;                // this worker's flag words in master memory
   float* loss_acc; float* loss_out;
+  unsigned int* done_dev;         // see SfPushArgs
   size_t n;                       // floats (multiple of 4)
   int drop;                       // fault injection: consume the gradient, post nothing
 };

@@ -20,6 +20,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional
 
+import os
+
 import torch
 
 from ..models.compiler import ACT_IDS, Layer, LayerPlan, UnsupportedGraph
@@ -72,10 +74,24 @@ def _split_k(tiles: int, kblocks: int) -> int:
     return max(1, min(148 // max(tiles, 1), kblocks // 4))
 
 
+def add_fetch_ops(plan, fetch: Dict[str, Any], B: int, D: int) -> None:
+    """fetch node (linear zero-copy stream of the minibatch into fp32 staging) + the cast / transpose that turns it into
+    the first layer's operands, both for the input set ``fetch['target']``."""
+    P = native.ptr
+    t = fetch["target"]
+    plan.add_fetch(fetch["args"], int(os.environ.get("SPARKFLOW_FETCH_CTAS", "8")))
+    plan.add_cast_transpose(P(t["x32"]), D, 0, P(t["a0"]), t["a0"].shape[1], P(t["a0T"]), 0 if t["a0T"] is None else t["a0T"].shape[1], B, D)
+
+
 def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = True, upto: Optional[int] = None,
-          post: Optional[str] = None, with_loss: bool = False) -> BuiltPlan:
+          post: Optional[str] = None, with_loss: bool = False, inputs: Optional[Dict[str, Any]] = None,
+          fetch: Optional[Dict[str, Any]] = None) -> BuiltPlan:
     """``train``: full step (fwd + loss + bwd + push).  Otherwise forward up to dense index ``upto``
-    (None = last) producing an fp32 result (+ArgMax), or forward + loss only when ``with_loss``."""
+    (None = last) producing an fp32 result (+ArgMax), or forward + loss only when ``with_loss``.
+
+    ``inputs`` (zero-copy mode): dict(x32, a0, a0T, y) already holding this step's minibatch (fp32 staging, bf16
+    operands, labels) - no H2D staging and no cast kernel on the critical path; ``fetch``: dict(args, target) of the
+    fetch node that fills the NEXT slot's input set from the pinned host partition on a side branch of this graph."""
     C, dev, lay, lp = worker.C, worker.device, worker.layout, worker.plan
     check_grammar(lp)
     P = native.ptr
@@ -89,13 +105,20 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
 
     ldB = round_up(B, 8)
     D = lp.input_dim
-    x_stage = zeros(B, D, dtype=f32)
     need_labels = (train or with_loss) and not lp.target_is_input
-    y_stage = zeros(B, lp.label_dim, dtype=f32) if need_labels else None
-    if train:
-        # training steps hand their loss to the host with a zero-copy store from the last kernel (pinned, device-mapped)
-        loss_out = torch.zeros(1, dtype=f32).pin_memory()
+    if inputs is not None:
+        x_stage, y_stage = inputs["x32"], inputs["y"]
+    else:
+        x_stage = zeros(B, D, dtype=f32)
+        y_stage = zeros(B, lp.label_dim, dtype=f32) if need_labels else None
+    done_dev = None
+    if train and os.environ.get("SPARKFLOW_DEVICE_LOSS") != "1":
+        # training steps hand their loss to the host with a zero-copy store from the last kernel (pinned, device-mapped):
+        # word 0 = loss, word 1 = completion sequence number (only written when a done counter is attached)
+        loss_out = torch.zeros(2, dtype=f32).pin_memory()
         keep.append(loss_out)
+        if inputs is not None:
+            done_dev = zeros(1, dtype=torch.int32)
     else:
         loss_out = zeros(1, dtype=f32)
     wsrc = worker._weight_src()
@@ -110,6 +133,12 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     trainable = [i for i, l in enumerate(layers) if l.kind in ("dense", "conv")]
     first_trainable = trainable[0]
 
+    # ---------------- next step's minibatch: zero-copy fetch on its own branch for the whole step ----------------
+    if fetch is not None:
+        plan.fork(3)
+        plan.branch(3)
+        add_fetch_ops(plan, fetch, B, D)
+        plan.branch(0)
     # ---------------- pull || input cast ----------------
     if do_pull and branches:
         plan.fork(1)
@@ -119,9 +148,12 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     elif do_pull:
         plan.add_pull(worker._pull_args(), P(worker.sync_pull), 0)
     first_is_dense = layers[first_trainable].kind == "dense"
-    a0 = zeros(B, round_up(D, 8))
-    a0T = zeros(D, ldB) if (train and first_is_dense) else None
-    plan.add_cast_transpose(P(x_stage), D, 0, P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
+    if inputs is not None:
+        a0, a0T = inputs["a0"], inputs["a0T"]
+    else:
+        a0 = zeros(B, round_up(D, 8))
+        a0T = zeros(D, ldB) if (train and first_is_dense) else None
+        plan.add_cast_transpose(P(x_stage), D, 0, P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
     if do_pull and branches:
         plan.join(1)
 
@@ -315,10 +347,13 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             continue
     if branches:
         plan.join(2)
+    if fetch is not None:
+        plan.join(3)
     if with_push:
+        extra = dict(done_dev=P(done_dev)) if done_dev is not None else {}
         if worker.served:
-            plan.add_post(worker._post_args(loss_out), P(worker.sync_push), 0)
+            plan.add_post(dict(worker._post_args(loss_out), **extra), P(worker.sync_push), 0)
         else:
-            plan.add_push(worker._push_args(loss_out), P(worker.sync_push), 0)
+            plan.add_push(dict(worker._push_args(loss_out), **extra), P(worker.sync_push), 0)
     keep.append(gemms)
     return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep)

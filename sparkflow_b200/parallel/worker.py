@@ -21,6 +21,8 @@ from __future__ import annotations
 import uuid
 from typing import Callable, List, Optional, Sequence, Union
 
+import os
+
 import numpy as np
 import torch
 
@@ -167,16 +169,22 @@ class B200Engine(Engine):
         self.w = worker
         self.step_idx = 0
         self.loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32).pin_memory()
-        self._slot_free = [torch.cuda.Event(), torch.cuda.Event()]
-        self._slot_ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self._primed = [False, False]
-        self._pending = [None, None]            # slot -> (ring index, pinned loss word) not yet harvested
+        # staging slots: the host may run SLOTS-1 steps ahead of the GPU (H2D of step k+1.. overlaps step k)
+        self.SLOTS = max(2, int(os.environ.get("SPARKFLOW_SLOTS", "4")))
+        S = self.SLOTS
+        self._slot_free = [torch.cuda.Event() for _ in range(S)]
+        self._slot_ready = [torch.cuda.Event() for _ in range(S)]
+        self._primed = [False] * S
+        self._pending = [None] * S              # slot -> (ring index, pinned loss word) not yet harvested
         self.h2d_bytes = 0
         self.d2h_bytes = 0
-        self._gather = [None, None]
+        self._gather = [None] * S
         self._driver = None
         self._driver_plans = {}
         self._driver_last = None
+        self._fetch_drivers = {}
+        self._fetch_partition_set = False
+        self.h2d_mode = os.environ.get("SPARKFLOW_H2D", "dma")
         self._X2 = self._Y2 = None
 
     def load_partition(self, features, labels):
@@ -185,6 +193,8 @@ class B200Engine(Engine):
         if labels is not None and not self.w.plan.target_is_input:
             self.Y = torch.as_tensor(np.ascontiguousarray(labels, dtype=np.float32)).pin_memory()
         self.partition_rows = self.X.shape[0]
+        if self._fetch_partition_set:
+            self.w.set_fetch_partition(self.X, self.Y)
 
     def _host_batch(self, rows: Rows, slot: int):
         if isinstance(rows, slice):
@@ -203,7 +213,7 @@ class B200Engine(Engine):
 
     def train(self, rows, pull, slot=None):
         w = self.w
-        slot = (self.step_idx & 1) if slot is None else slot
+        slot = (self.step_idx % self.SLOTS) if slot is None else slot
         B = (rows.stop - rows.start) if isinstance(rows, slice) else len(rows)
         plan, bufs = w.build_plan(B, slot, with_pull=pull)
         if self._primed[slot]:
@@ -238,6 +248,8 @@ class B200Engine(Engine):
         """Physically shuffle the pinned partition (threaded native row gather into the spare buffers)."""
         self.w.stream.synchronize()
         self.w.copy_stream.synchronize()
+        for drv in self._fetch_drivers.values():
+            drv.flush()
         from ..ops.native import host_ext
 
         H = host_ext()
@@ -250,19 +262,30 @@ class B200Engine(Engine):
         if self.Y is not None:
             H.gather_rows(self.Y.data_ptr(), self._Y2.data_ptr(), idx, self.Y.shape[1] * 4, 4)
             self.Y, self._Y2 = self._Y2, self.Y
-        self._driver = None                     # host base pointers changed
-        self._driver_plans = {}
+        if not self._fetch_drivers:
+            self._driver = None                 # DMA driver: host base pointers are baked into it
+            self._driver_plans = {}
+        if self._fetch_partition_set:
+            self.w.set_fetch_partition(self.X, self.Y)      # fetch-mode graphs read the partition through a device descriptor
 
     # ---- native inner loop -------------------------------------------------------------------------
     def train_contiguous(self, starts: Sequence[int], batch: int, pull: bool = True) -> None:
-        """Run ``len(starts)`` steps on contiguous row blocks ``[s, s + batch)`` through the C++ StepDriver
-        (H2D of every minibatch, graph replay, loss D2H – no Python in the loop)."""
+        """Run ``len(starts)`` steps on contiguous row blocks ``[s, s + batch)`` through the C++ StepDriver - no Python
+        in the loop.  ``SPARKFLOW_H2D=dma`` (default): copy-engine H2D of every minibatch on a side stream, SLOTS-deep,
+        event hand-off to the step graph.  ``SPARKFLOW_H2D=fetch``: every step's CUDA graph fetches the NEXT minibatch
+        from the pinned partition itself (zero-copy SM loads + cast on a side branch), so a step costs the host one
+        ``cudaGraphLaunch`` and nothing sits between two graphs.  Measured on this pod (profiles/r1_e2e_h2d_modes.md):
+        fetch removes the cast from the critical path (step 55 vs 57 us) but SM reads of cold host pages run at
+        ~20 GB/s vs 40 GB/s for the DMA engine, so dma is the faster end-to-end choice here."""
         w = self.w
         if not w.use_graphs or len(starts) == 0:
             for s0 in starts:
                 self.train(slice(int(s0), int(s0) + batch), pull)
             return
         starts = [int(v) for v in starts]
+        if self.h2d_mode == "fetch":
+            self._train_fetch(starts, batch, pull)
+            return
         key = (batch, pull)
         drv_ids = self._driver_plans.get(key)
         if drv_ids is None:
@@ -271,7 +294,7 @@ class B200Engine(Engine):
                                               self.X.shape[1] * 4, 0 if self.Y is None else self.Y.data_ptr(),
                                               0 if self.Y is None else self.Y.shape[1] * 4, self.loss_ring.data_ptr(), self.LOSS_RING)
             drv_ids = []
-            for slot in (0, 1):
+            for slot in range(self.SLOTS):
                 plan, bufs = w.build_plan(batch, slot, with_pull=pull)
                 if not plan.captured():
                     # the first use of a plan runs it eagerly (a REAL step on the next scheduled minibatch) and
@@ -287,9 +310,9 @@ class B200Engine(Engine):
         if not starts:
             return
         self.w.stream.synchronize()       # python-path steps (if any) are done before the driver takes over the ring
-        self._harvest(0)
-        self._harvest(1)
-        ids = np.asarray([drv_ids[(self._driver.steps() + k) & 1] for k in range(len(starts))], dtype=np.int32)
+        for slot in range(self.SLOTS):
+            self._harvest(slot)
+        ids = np.asarray([drv_ids[(self._driver.steps() + k) % self.SLOTS] for k in range(len(starts))], dtype=np.int32)
         self._driver.run(ids, np.asarray(starts, dtype=np.int64))
         n = len(starts)
         self.h2d_bytes += n * batch * (self.X.shape[1] + (0 if self.Y is None else self.Y.shape[1])) * 4
@@ -297,10 +320,42 @@ class B200Engine(Engine):
         self._driver_last = (self._driver.steps() - 1) % self.LOSS_RING
         self.step_idx += n
 
+    def _train_fetch(self, starts: List[int], batch: int, pull: bool) -> None:
+        w = self.w
+        key = (batch, pull)
+        drv = self._fetch_drivers.get(key)
+        if drv is None:
+            S = self.SLOTS
+            if not self._fetch_partition_set:
+                w.set_fetch_partition(self.X, self.Y)
+                self._fetch_partition_set = True
+            d = w.C.StepDriver(w.stream.cuda_stream, w.copy_stream.cuda_stream, self.X.data_ptr(), self.X.shape[1] * 4,
+                               0 if self.Y is None else self.Y.data_ptr(), 0 if self.Y is None else self.Y.shape[1] * 4,
+                               self.loss_ring.data_ptr(), self.LOSS_RING)
+            for slot in range(S):
+                plan, bufs = w.build_plan(batch, slot, with_pull=pull, fetch_slots=S)
+                if not plan.captured():
+                    plan.capture(w.stream.cuda_stream)
+                d.add_plan(plan, 0, 0, bufs.loss_out.data_ptr(), batch)
+            d.enable_fetch(w.fetch_ctx()["sched"].data_ptr(), w.FETCH_RING, [w.fetch_plan(batch, slot) for slot in range(S)])
+            drv = self._fetch_drivers[key] = d
+        self.w.stream.synchronize()       # python-path steps (if any) are done before the driver takes over the ring
+        for slot in range(self.SLOTS):
+            self._harvest(slot)
+        n = len(starts)
+        ids = np.asarray([(drv.steps() + k) % self.SLOTS for k in range(n)], dtype=np.int32)
+        drv.run_fetch(ids, np.asarray(starts, dtype=np.int64))
+        # every step's graph pulls one minibatch over PCIe (the first one of the call by a stand-alone fetch launch)
+        self.h2d_bytes += (n + 1) * batch * (self.X.shape[1] + (0 if self.Y is None else self.Y.shape[1])) * 4
+        self.d2h_bytes += n * 8
+        self._driver = drv
+        self._driver_last = (drv.steps() - 1) % self.LOSS_RING
+        self.step_idx += n
+
     def last_loss(self) -> float:
         self.w.stream.synchronize()
-        self._harvest(0)
-        self._harvest(1)
+        for slot in range(self.SLOTS):
+            self._harvest(slot)
         if self._driver is not None:
             self._driver.flush()
         if self._driver_last is not None:

@@ -200,3 +200,48 @@ def test_applier_batch_is_sequential_pushes(opt, max_batch):
     pub = lay.publish_reference(lay.flatten(master.weights()))
     np.testing.assert_allclose(master.shadow.float().cpu().numpy(), torch.from_numpy(pub).to(torch.bfloat16).float().numpy(), rtol=0, atol=1e-2)
     master.close()
+
+
+@pytest.mark.parametrize("mode", ["fetch", "dma"])
+@pytest.mark.parametrize("served", [False, True])
+def test_train_contiguous_native_loop_tracks_oracle(mode, served, monkeypatch):
+    """the C++ StepDriver loop: zero-copy in-graph minibatch fetch (one cudaGraphLaunch per step) and the copy-engine
+    variant both walk the same minibatches as the oracle, before and after a physical shuffle of the pinned partition"""
+    monkeypatch.setenv("SPARKFLOW_H2D", mode)
+    spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
+    ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, True, served=served)
+    X, Y = _data(640, d, c, kind)
+    eng = B200Engine(worker)
+    assert eng.h2d_mode == mode
+    eng.load_partition(X, Y)
+    ps = ParameterServer(w0, spec, acquire_lock=True)
+    ref = TorchEngine(ir, tf_in, tf_lab, LocalTransport(ps))
+    ref.load_partition(X, Y)
+    starts = [0, 64, 128, 192, 256, 320, 384, 448, 512, 576, 0]
+    eng.train_contiguous(starts, 64, pull=True)
+    for s0 in starts:
+        ref.train(slice(s0, s0 + 64), pull=True)
+    eng.finish()
+    # loss of the LAST minibatch (rows 0..63) evaluated with the weights that step pulled
+    l_dev = eng.last_loss()
+    l_ref = float(ref.prog.loss(ref._feed(slice(0, 64)), ref.weights))
+    assert abs(l_dev - l_ref) < 0.05 * max(1.0, abs(l_ref)), (l_dev, l_ref)
+    order = np.random.default_rng(3).permutation(640)
+    eng.permute(order)
+    ref.load_partition(X[order], Y[order])
+    eng.train_contiguous(starts[:5], 64, pull=True)
+    for s0 in starts[:5]:
+        ref.train(slice(s0, s0 + 64), pull=True)
+    eng.finish()
+    import time
+    n = len(starts) + 5
+    t0 = time.time()
+    while master.counters()["pushes"] < n and time.time() - t0 < 10:
+        time.sleep(0.01)
+    assert master.counters()["pushes"] == n
+    for a, b, v in zip(master.weights(), ps.weights(), ir.trainable):
+        assert np.abs(a - b).max() < 5 * 0.001 * n, v.name
+        assert np.mean(np.abs(a - b)) < 0.35 * 0.001 * n, v.name
+    l_ref = float(ref.prog.loss(ref._feed(slice(256, 320)), ref.weights))
+    assert abs(eng.last_loss() - l_ref) < 0.05 * max(1.0, abs(l_ref)), (eng.last_loss(), l_ref)
+    master.close()
