@@ -1,10 +1,10 @@
 #!/bin/bash
-# usage: tools/run_scaling.sh <tag> [steps] [warmup]   (run on a multi-GPU box; writes gpurun_out/scale_<tag>_*.json)
-TAG=${1:-scale}; STEPS=${2:-300}; WARM=${3:-30}
+# usage: tools/run_scaling.sh <tag> [steps] [warmup] ["1 2 4 8"]   (run on a multi-GPU box; writes gpurun_out/scale_<tag>_*.json)
+TAG=${1:-scale}; STEPS=${2:-300}; WARM=${3:-30}; NLIST=${4:-"1 2 4 8"}
 mkdir -p gpurun_out
 NG=$(python -c "import torch; print(torch.cuda.device_count())")
 for MODE in lock hogwild; do
-  for N in 1 2 4 8; do
+  for N in $NLIST; do
     [ "$N" -gt "$NG" ] && continue
     if [ "$N" = "1" ]; then
       timeout 300 python bench.py --gpus 1 --steps $STEPS --warmup $WARM --mode $MODE > gpurun_out/scale_${TAG}_${MODE}_$N.json 2> gpurun_out/scale_${TAG}_${MODE}_$N.err
