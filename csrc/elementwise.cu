@@ -324,6 +324,33 @@ extern "C" int sf_cast_transpose(const float* in, int ld_in, __nv_bfloat16* out,
                                      static_cast<const int32_t*>(nullptr), out, ld_out, outT, ld_t, rows, cols));
 }
 
+namespace sf {
+// fp32 row gather out[r, :] = in[idx[r], :] (label rows / fp32 targets of a minibatch drawn from an HBM-resident partition)
+__global__ void __launch_bounds__(256)
+gather_rows_f32_kernel(const float* __restrict__ in, int ld_in, const int32_t* __restrict__ idx, float* __restrict__ out, int ld_out,
+                       int rows, int cols) {
+  TraceScope trace;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.mark();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < rows; r += nwarps) {
+    const float* src = in + static_cast<size_t>(idx[r]) * ld_in;
+    float* dst = out + static_cast<size_t>(r) * ld_out;
+    for (int c = lane; c < cols; c += 32) dst[c] = src[c];
+  }
+  trace.end(KID_CAST);
+}
+}  // namespace sf
+
+extern "C" int sf_gather_rows_f32(const float* in, int ld_in, const int32_t* idx, float* out, int ld_out, int rows, int cols,
+                                  cudaStream_t st) {
+  int grid = (rows + 7) / 8;
+  if (grid > 296) grid = 296;
+  if (grid < 1) grid = 1;
+  return static_cast<int>(sf::launch(sf::gather_rows_f32_kernel, dim3(grid), dim3(256), 0, st, in, ld_in, idx, out, ld_out, rows, cols));
+}
+
 extern "C" int sf_gather_cast_transpose(const float* in, int ld_in, const int32_t* idx,
                                         __nv_bfloat16* out, int ld_out, __nv_bfloat16* outT, int ld_t,
                                         int rows, int cols, cudaStream_t st) {

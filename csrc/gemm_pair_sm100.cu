@@ -26,12 +26,12 @@ namespace sf {
 
 constexpr int kPairBN = 256;               // tile columns (B rows): 128 staged by each CTA
 constexpr int kPairHalfN = kPairBN / 2;
-constexpr int kPairStages = 6;
 constexpr int kPairABytes = kBM * kBK * 2;          // 16 KB
 constexpr int kPairBBytes = kPairHalfN * kBK * 2;   // 16 KB
 constexpr int kPairStageBytes = kPairABytes + kPairBBytes;
 constexpr int kPairBarBytes = 256;
-constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + kPairBarBytes + kPairBN * 4 + 1024;
+template <int kPairStages>
+constexpr int pair_smem_bytes() { return kPairStages * kPairStageBytes + kPairBarBytes + kPairBN * 4 + 1024; }
 
 __device__ __forceinline__ void pair_tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
   const int per_group = group_m * tiles_n;
@@ -43,6 +43,7 @@ __device__ __forceinline__ void pair_tile_coords(int t, int tiles_m, int tiles_n
   tn = r / gm;
 }
 
+template <int kPairStages>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 sf_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const SfGemmEpilogue ep,
                     int M, int N, int K, int tiles_m, int tiles_n, int group_m) {
@@ -197,10 +198,12 @@ sf_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
 }  // namespace sf
 
-extern "C" int sf_gemm_pair_launch(const SfGemm* g, cudaStream_t st) {
+template <int kPairStages>
+static int pair_launch(const SfGemm* g, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sf::sf_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sf::kPairSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(sf::sf_gemm_pair_kernel<kPairStages>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         sf::pair_smem_bytes<kPairStages>());
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
@@ -211,17 +214,24 @@ extern "C" int sf_gemm_pair_launch(const SfGemm* g, cudaStream_t st) {
   if (pairs > tiles) pairs = tiles;
   if (pairs < 1) pairs = 1;
   // a wave of `pairs` concurrent tiles should cover a near-square block of the output: group_m tile rows at a time
-  int group_m = 8;
+  static const int env_group = [] { const char* v = getenv("SPARKFLOW_PAIR_GROUP_M"); return v ? atoi(v) : 0; }();
+  int group_m = env_group > 0 ? env_group : 8;
   if (group_m > tiles_m) group_m = tiles_m;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(sf::kGemmThreads);
-  cfg.dynamicSmemBytes = sf::kPairSmemBytes;
+  cfg.dynamicSmemBytes = sf::pair_smem_bytes<kPairStages>();
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = sf::pdl_enabled() ? 1 : 0;
-  return static_cast<int>(cudaLaunchKernelEx(&cfg, sf::sf_gemm_pair_kernel, g->tmA, g->tmB, g->ep, g->M, g->N, g->K, tiles_m, tiles_n, group_m));
+  return static_cast<int>(cudaLaunchKernelEx(&cfg, sf::sf_gemm_pair_kernel<kPairStages>, g->tmA, g->tmB, g->ep, g->M, g->N, g->K, tiles_m, tiles_n,
+                                             group_m));
+}
+
+extern "C" int sf_gemm_pair_launch(const SfGemm* g, cudaStream_t st) {
+  static const int stages = [] { const char* v = getenv("SPARKFLOW_PAIR_STAGES"); return v ? atoi(v) : 6; }();
+  return stages == 7 ? pair_launch<7>(g, st) : pair_launch<6>(g, st);
 }

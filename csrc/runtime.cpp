@@ -490,6 +490,45 @@ class StepDriver {
       ++step_;
     }
   }
+  // ---- resident mode: the partition lives in HBM; a step's minibatch is `perm[start : start + batch]` (device int32
+  // row ids), copied device-to-device into the plan's index buffer right before its graph, which gathers the rows
+  // itself.  No PCIe traffic per step; completion is the pinned word written by the step's last kernel.
+  void run_resident(py::array_t<int32_t, py::array::c_style | py::array::forcecast> ids,
+                    py::array_t<int64_t, py::array::c_style | py::array::forcecast> starts, uintptr_t perm_dev) {
+    const int n = static_cast<int>(ids.size());
+    if (starts.size() != n) throw std::runtime_error("StepDriver.run_resident: ids/starts length mismatch");
+    if (n == 0) return;
+    const int32_t* ip = ids.data();
+    const int64_t* sp = starts.data();
+    const int32_t* perm = P<const int32_t>(perm_dev);
+    py::gil_scoped_release nogil;
+    // plans may also have been replayed by other paths: re-baseline the completion counters once per call
+    ck(cudaStreamSynchronize(compute_), "cudaStreamSynchronize(resident)");
+    for (auto& e : entries_) {
+      harvest(e);
+      e.launched = *(reinterpret_cast<volatile unsigned int*>(e.loss_out) + 1);
+    }
+    using clk = std::chrono::steady_clock;
+    auto ns = [](clk::time_point a, clk::time_point b) { return std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+    for (int k = 0; k < n; ++k) {
+      if (ip[k] < 0 || ip[k] >= static_cast<int>(entries_.size())) throw std::runtime_error("StepDriver.run_resident: bad plan id");
+      Entry& e = entries_[ip[k]];
+      const auto t0 = clk::now();
+      if (e.primed && e.pending >= 0) wait_done(e);
+      const auto t1 = clk::now();
+      ck(cudaMemcpyAsync(e.x_stage, perm + sp[k], static_cast<size_t>(e.batch) * sizeof(int32_t), cudaMemcpyDeviceToDevice, compute_),
+         "cudaMemcpyAsync(minibatch row ids)");
+      const auto t2 = clk::now();
+      e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
+      const auto t3 = clk::now();
+      host_ns_[0] += ns(t0, t1); host_ns_[1] += ns(t1, t2); host_ns_[3] += ns(t2, t3);
+      ++e.launched;
+      e.pending = step_;
+      e.primed = true;
+      done_mode_ = true;
+      ++step_;
+    }
+  }
   // host nanoseconds spent per phase since construction: wait-for-slot, H2D enqueue, event hand-off, graph launch, record
   std::vector<long long> host_ns() const { return std::vector<long long>(host_ns_, host_ns_ + 5); }
   std::vector<float> probe() const { return probe_rows_; }
@@ -499,7 +538,7 @@ class StepDriver {
     py::gil_scoped_release nogil;
     for (auto& e : entries_)
       if (e.primed && e.pending >= 0) {
-        if (fetch_mode_) wait_done(e);
+        if (fetch_mode_ || done_mode_) wait_done(e);
         else ck(cudaEventSynchronize(e.free_), "cudaEventSynchronize(flush)");
         harvest(e);
       }
@@ -579,7 +618,7 @@ class StepDriver {
   long long host_ns_[5] = {0, 0, 0, 0, 0};
   bool probe_ = false, no_h2d_ = false, base_recorded_ = false;
   double h2d_frac_ = 1.0;
-  bool fetch_mode_ = false;
+  bool fetch_mode_ = false, done_mode_ = false;
   long long* sched_ = nullptr;
   unsigned int sched_mask_ = 0;
   unsigned long long fetch_seq_ = 0;
@@ -765,6 +804,12 @@ PYBIND11_MODULE(_C, m) {
                                               P<__nv_bfloat16>(outT), ld_t, rows, cols, st);
              });
            })
+      .def("add_gather_rows",
+           [](Plan& p, uintptr_t in, int ld_in, uintptr_t idx, uintptr_t out, int ld_out, int rows, int cols) {
+             p.add("gather_rows", [=](cudaStream_t st) {
+               return sf_gather_rows_f32(P<const float>(in), ld_in, P<const int32_t>(idx), P<float>(out), ld_out, rows, cols, st);
+             });
+           })
       .def("add_softmax_xent",
            [](Plan& p, uintptr_t logits, int ld_logits, uintptr_t labels, int ld_labels, uintptr_t loss,
               uintptr_t dz, int ld_dz, uintptr_t dzT, int ld_t, uintptr_t dbias, int rows, int cols) {
@@ -859,6 +904,7 @@ PYBIND11_MODULE(_C, m) {
       .def("flush", &StepDriver::flush)
       .def("enable_fetch", &StepDriver::enable_fetch)
       .def("run_fetch", &StepDriver::run_fetch)
+      .def("run_resident", &StepDriver::run_resident)
       .def("host_ns", &StepDriver::host_ns)
       .def("probe", &StepDriver::probe);
 

@@ -82,6 +82,7 @@ unsigned int sf_trace_count();
 // Elementwise / reduction kernels (elementwise.cu)
 // ---------------------------------------------------------------------------
 // fp32 [rows, cols] (ld_in) -> bf16 [rows, ld_out] and optional transpose bf16 [cols, ld_t]
+int sf_gather_rows_f32(const float* in, int ld_in, const int32_t* idx, float* out, int ld_out, int rows, int cols, cudaStream_t st);
 int sf_hostcopy(const void* src_host, void* dst, size_t bytes, int grid, cudaStream_t st);
 
 // In-graph minibatch fetch (zero-copy): SM loads stream one minibatch (features + label rows, fp32) from the pinned

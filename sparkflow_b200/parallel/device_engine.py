@@ -201,6 +201,7 @@ class StepBuffers:
     y_stage: Optional[torch.Tensor]
     loss_out: torch.Tensor
     result: Optional[torch.Tensor] = None
+    idx: Optional[torch.Tensor] = None     # resident mode: device int32 [B] row ids gathered by the step itself
 
 
 class DeviceWorker:
@@ -343,13 +344,20 @@ class DeviceWorker:
             self._plans[key] = plan
         return self._plans[key]
 
-    def build_plan(self, B: int, slot: int = 0, with_pull: bool = True, with_push: bool = True, fetch_slots: int = 0):
+    def build_plan(self, B: int, slot: int = 0, with_pull: bool = True, with_push: bool = True, fetch_slots: int = 0,
+                   resident: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None):
         """Compile the training step for batch size ``B`` reading from staging-buffer set ``slot``.  With
         ``fetch_slots`` = S > 0 the plan is a zero-copy one: it consumes input set ``slot`` and its graph fetches
         the next minibatch into input set ``(slot + 1) % S``."""
         from . import plan_builder
 
-        key = (B, slot, with_pull, with_push, fetch_slots)
+        key = (B, slot, with_pull, with_push, fetch_slots, None if resident is None else resident[0].data_ptr())
+        if key not in self._plans and resident is not None:
+            built = plan_builder.build(self, B, train=True, with_pull=with_pull, with_push=with_push, resident=dict(x=resident[0], y=resident[1]))
+            self._plans[key] = built.plan
+            self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result, built.idx)
+            self._keep.append(built.keep)
+            self.launches_per_step = len(built.plan)
         if key not in self._plans and fetch_slots > 0:
             built = plan_builder.build(self, B, train=True, with_pull=with_pull, with_push=with_push, inputs=self.input_set(B, slot),
                                        fetch=dict(args=self.fetch_args(B, (slot + 1) % fetch_slots),

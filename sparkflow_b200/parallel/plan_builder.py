@@ -37,6 +37,7 @@ class BuiltPlan:
     loss_out: torch.Tensor
     result: Optional[torch.Tensor] = None
     keep: List[Any] = field(default_factory=list)
+    idx: Optional[torch.Tensor] = None       # resident mode: int32 [B] row ids of the minibatch this plan trains on
 
 
 def check_grammar(lp: LayerPlan) -> None:
@@ -85,13 +86,15 @@ def add_fetch_ops(plan, fetch: Dict[str, Any], B: int, D: int) -> None:
 
 def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = True, upto: Optional[int] = None,
           post: Optional[str] = None, with_loss: bool = False, inputs: Optional[Dict[str, Any]] = None,
-          fetch: Optional[Dict[str, Any]] = None) -> BuiltPlan:
+          fetch: Optional[Dict[str, Any]] = None, resident: Optional[Dict[str, Any]] = None) -> BuiltPlan:
     """``train``: full step (fwd + loss + bwd + push).  Otherwise forward up to dense index ``upto``
     (None = last) producing an fp32 result (+ArgMax), or forward + loss only when ``with_loss``.
 
     ``inputs`` (zero-copy mode): dict(x32, a0, a0T, y) already holding this step's minibatch (fp32 staging, bf16
     operands, labels) - no H2D staging and no cast kernel on the critical path; ``fetch``: dict(args, target) of the
-    fetch node that fills the NEXT slot's input set from the pinned host partition on a side branch of this graph."""
+    fetch node that fills the NEXT slot's input set from the pinned host partition on a side branch of this graph.
+    ``resident``: dict(x, y) device tensors holding the whole partition in HBM - the step gathers its minibatch rows
+    (ids in the returned ``idx`` buffer) itself: gather fused into the cast kernel, label rows by a row-gather kernel."""
     C, dev, lay, lp = worker.C, worker.device, worker.layout, worker.plan
     check_grammar(lp)
     P = native.ptr
@@ -106,8 +109,13 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     ldB = round_up(B, 8)
     D = lp.input_dim
     need_labels = (train or with_loss) and not lp.target_is_input
+    idx_stage = None
     if inputs is not None:
         x_stage, y_stage = inputs["x32"], inputs["y"]
+    elif resident is not None:
+        idx_stage = zeros(B, dtype=torch.int32)
+        x_stage = zeros(B, D, dtype=f32) if lp.target_is_input else None      # fp32 target rows (autoencoders)
+        y_stage = zeros(B, lp.label_dim, dtype=f32) if need_labels else None
     else:
         x_stage = zeros(B, D, dtype=f32)
         y_stage = zeros(B, lp.label_dim, dtype=f32) if need_labels else None
@@ -117,8 +125,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         # word 0 = loss, word 1 = completion sequence number (only written when a done counter is attached)
         loss_out = torch.zeros(2, dtype=f32).pin_memory()
         keep.append(loss_out)
-        if inputs is not None:
-            done_dev = zeros(1, dtype=torch.int32)
+        done_dev = zeros(1, dtype=torch.int32)
     else:
         loss_out = zeros(1, dtype=f32)
     wsrc = worker._weight_src()
@@ -153,7 +160,15 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     else:
         a0 = zeros(B, round_up(D, 8))
         a0T = zeros(D, ldB) if (train and first_is_dense) else None
-        plan.add_cast_transpose(P(x_stage), D, 0, P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
+        if resident is not None:
+            xr, yr = resident["x"], resident["y"]
+            plan.add_cast_transpose(P(xr), xr.shape[1], P(idx_stage), P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
+            if x_stage is not None:
+                plan.add_gather_rows(P(xr), xr.shape[1], P(idx_stage), P(x_stage), D, B, D)
+            if y_stage is not None:
+                plan.add_gather_rows(P(yr), yr.shape[1], P(idx_stage), P(y_stage), y_stage.shape[1], B, y_stage.shape[1])
+        else:
+            plan.add_cast_transpose(P(x_stage), D, 0, P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
     if do_pull and branches:
         plan.join(1)
 
@@ -356,4 +371,4 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         else:
             plan.add_push(dict(worker._push_args(loss_out), **extra), P(worker.sync_push), 0)
     keep.append(gemms)
-    return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep)
+    return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep, idx_stage)

@@ -185,14 +185,37 @@ class B200Engine(Engine):
         self._fetch_drivers = {}
         self._fetch_partition_set = False
         self.h2d_mode = os.environ.get("SPARKFLOW_H2D", "dma")
+        self.partition_mode = os.environ.get("SPARKFLOW_PARTITION", "pinned")
+        self.resident = False
+        self.Xd = self.Yd = self.perm_d = None
+        self._resident_driver = {}
+        self._idx_pinned = [None] * S
         self._X2 = self._Y2 = None
 
     def load_partition(self, features, labels):
+        """``SPARKFLOW_PARTITION=pinned`` (default): the partition stays in pinned host memory and every step copies its
+        minibatch host->device.  ``resident``: the partition is uploaded to HBM once (180 GB per B200 hold any Spark
+        partition the reference could train on); shuffles are a device index permutation and every step gathers its rows
+        on the device - no PCIe traffic in the training loop.  ``auto``: resident when it fits in a quarter of free HBM."""
         self.X = torch.as_tensor(np.ascontiguousarray(features, dtype=np.float32)).pin_memory()
         self.Y = None
         if labels is not None and not self.w.plan.target_is_input:
             self.Y = torch.as_tensor(np.ascontiguousarray(labels, dtype=np.float32)).pin_memory()
         self.partition_rows = self.X.shape[0]
+        mode = self.partition_mode
+        if mode == "auto":
+            need = self.X.numel() * 4 + (0 if self.Y is None else self.Y.numel() * 4)
+            free, _ = torch.cuda.mem_get_info(self.w.device)
+            mode = "resident" if need * 4 <= free else "pinned"
+        self.resident = mode == "resident"
+        self.Xd = self.Yd = self.perm_d = None
+        if self.resident:
+            with torch.cuda.stream(self.w.stream):
+                self.Xd = self.X.to(self.w.device, non_blocking=True)
+                self.Yd = None if self.Y is None else self.Y.to(self.w.device, non_blocking=True)
+                self.perm_d = torch.arange(self.partition_rows, dtype=torch.int32, device=self.w.device)
+            self.w.stream.synchronize()
+            self._resident_driver = {}
         if self._fetch_partition_set:
             self.w.set_fetch_partition(self.X, self.Y)
 
@@ -211,9 +234,42 @@ class B200Engine(Engine):
             torch.index_select(self.Y, 0, idx, out=g[1])
         return g
 
+    def _train_resident(self, rows, pull, slot):
+        w = self.w
+        B = (rows.stop - rows.start) if isinstance(rows, slice) else len(rows)
+        plan, bufs = w.build_plan(B, slot, with_pull=pull, resident=(self.Xd, self.Yd))
+        if self._primed[slot]:
+            self._slot_free[slot].synchronize()
+            self._harvest(slot)
+        with torch.cuda.stream(w.stream):
+            if isinstance(rows, slice):
+                bufs.idx.copy_(self.perm_d[rows], non_blocking=True)
+            else:
+                # explicit row ids index the partition in its CURRENT (possibly permuted) order
+                host = self._idx_pinned[slot]
+                if host is None or host.numel() != B:
+                    host = self._idx_pinned[slot] = torch.empty(B, dtype=torch.int64).pin_memory()
+                host.copy_(torch.as_tensor(np.asarray(rows, dtype=np.int64)))
+                self.h2d_bytes += B * 8
+                bufs.idx.copy_(self.perm_d[host.to(w.device, non_blocking=True)], non_blocking=True)
+        w.run_plan(plan)
+        self._slot_free[slot].record(w.stream)
+        self._pending[slot] = (self.step_idx % self.LOSS_RING, bufs.loss_out)
+        self.d2h_bytes += 4
+        self._primed[slot] = True
+        self._driver_last = None
+        self.step_idx += 1
+
     def train(self, rows, pull, slot=None):
         w = self.w
         slot = (self.step_idx % self.SLOTS) if slot is None else slot
+        if self._driver_last is not None:
+            # the native loop ran since the last Python-driven step: its steps share these staging buffers
+            w.stream.synchronize()
+            if self._driver is not None:
+                self._driver.flush()
+        if self.resident:
+            return self._train_resident(rows, pull, slot)
         B = (rows.stop - rows.start) if isinstance(rows, slice) else len(rows)
         plan, bufs = w.build_plan(B, slot, with_pull=pull)
         if self._primed[slot]:
@@ -245,7 +301,13 @@ class B200Engine(Engine):
             self._pending[slot] = None
 
     def permute(self, order: np.ndarray) -> None:
-        """Physically shuffle the pinned partition (threaded native row gather into the spare buffers)."""
+        """Shuffle the partition: a device index permutation when it is HBM-resident, otherwise a physical shuffle of the
+        pinned host copy (threaded native row gather into the spare buffers)."""
+        if self.resident:
+            with torch.cuda.stream(self.w.stream):
+                order_d = torch.as_tensor(np.asarray(order, dtype=np.int64)).to(self.w.device)
+                self.perm_d = self.perm_d[order_d].contiguous()
+            return
         self.w.stream.synchronize()
         self.w.copy_stream.synchronize()
         for drv in self._fetch_drivers.values():
@@ -283,6 +345,9 @@ class B200Engine(Engine):
                 self.train(slice(int(s0), int(s0) + batch), pull)
             return
         starts = [int(v) for v in starts]
+        if self.resident:
+            self._train_contiguous_resident(starts, batch, pull)
+            return
         if self.h2d_mode == "fetch":
             self._train_fetch(starts, batch, pull)
             return
@@ -318,6 +383,29 @@ class B200Engine(Engine):
         self.h2d_bytes += n * batch * (self.X.shape[1] + (0 if self.Y is None else self.Y.shape[1])) * 4
         self.d2h_bytes += n * 4
         self._driver_last = (self._driver.steps() - 1) % self.LOSS_RING
+        self.step_idx += n
+
+    def _train_contiguous_resident(self, starts: List[int], batch: int, pull: bool) -> None:
+        w = self.w
+        key = (batch, pull, self.Xd.data_ptr())
+        drv = self._resident_driver.get(key)
+        if drv is None:
+            d = w.C.StepDriver(w.stream.cuda_stream, w.copy_stream.cuda_stream, 0, 0, 0, 0, self.loss_ring.data_ptr(), self.LOSS_RING)
+            for slot in range(self.SLOTS):
+                plan, bufs = w.build_plan(batch, slot, with_pull=pull, resident=(self.Xd, self.Yd))
+                if not plan.captured():
+                    plan.capture(w.stream.cuda_stream)
+                d.add_plan(plan, bufs.idx.data_ptr(), 0, bufs.loss_out.data_ptr(), batch)
+            drv = self._resident_driver[key] = d
+        w.stream.synchronize()
+        for slot in range(self.SLOTS):
+            self._harvest(slot)
+        n = len(starts)
+        ids = np.asarray([(drv.steps() + k) % self.SLOTS for k in range(n)], dtype=np.int32)
+        drv.run_resident(ids, np.asarray(starts, dtype=np.int64), self.perm_d.data_ptr())
+        self.d2h_bytes += n * 8
+        self._driver = drv
+        self._driver_last = (drv.steps() - 1) % self.LOSS_RING
         self.step_idx += n
 
     def _train_fetch(self, starts: List[int], batch: int, pull: bool) -> None:

@@ -202,17 +202,20 @@ def test_applier_batch_is_sequential_pushes(opt, max_batch):
     master.close()
 
 
-@pytest.mark.parametrize("mode", ["fetch", "dma"])
+@pytest.mark.parametrize("mode", ["fetch", "dma", "resident"])
 @pytest.mark.parametrize("served", [False, True])
 def test_train_contiguous_native_loop_tracks_oracle(mode, served, monkeypatch):
     """the C++ StepDriver loop: zero-copy in-graph minibatch fetch (one cudaGraphLaunch per step) and the copy-engine
     variant both walk the same minibatches as the oracle, before and after a physical shuffle of the pinned partition"""
-    monkeypatch.setenv("SPARKFLOW_H2D", mode)
+    if mode == "resident":
+        monkeypatch.setenv("SPARKFLOW_PARTITION", "resident")       # HBM-resident partition, device-side gather / shuffle
+    else:
+        monkeypatch.setenv("SPARKFLOW_H2D", mode)
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
     ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, True, served=served)
     X, Y = _data(640, d, c, kind)
     eng = B200Engine(worker)
-    assert eng.h2d_mode == mode
+    assert eng.partition_mode == "resident" if mode == "resident" else eng.h2d_mode == mode
     eng.load_partition(X, Y)
     ps = ParameterServer(w0, spec, acquire_lock=True)
     ref = TorchEngine(ir, tf_in, tf_lab, LocalTransport(ps))
@@ -232,9 +235,16 @@ def test_train_contiguous_native_loop_tracks_oracle(mode, served, monkeypatch):
     eng.train_contiguous(starts[:5], 64, pull=True)
     for s0 in starts[:5]:
         ref.train(slice(s0, s0 + 64), pull=True)
+    # explicit row ids (the reference's mini_stochastic_iters mode) index the shuffled partition
+    picks = [np.random.default_rng(10 + i).choice(640, 64, replace=False) for i in range(2)]
+    for rows in picks:
+        eng.train(rows, pull=True)
+        ref.train(rows, pull=True)
+    eng.train_contiguous([256], 64, pull=True)
+    ref.train(slice(256, 320), pull=True)
     eng.finish()
     import time
-    n = len(starts) + 5
+    n = len(starts) + 5 + 3
     t0 = time.time()
     while master.counters()["pushes"] < n and time.time() - t0 < 10:
         time.sleep(0.01)

@@ -12,6 +12,7 @@ from sparkflow_b200.ops import native
 from sparkflow_b200.ops.layout import round_up
 
 M, N, K = (int(v) for v in sys.argv[1:4]) if len(sys.argv) >= 4 else (4096, 4096, 4096)
+pair = 1 if "--pair" in sys.argv else 0
 C = native.cuda_ext()
 C.set_pdl(0)
 a = torch.randn(M, round_up(K, 8), device="cuda").to(torch.bfloat16)
@@ -19,7 +20,7 @@ b = torch.randn(N, round_up(K, 8), device="cuda").to(torch.bfloat16)
 out = torch.zeros(M, round_up(N, 8), dtype=torch.bfloat16, device="cuda")
 bias = torch.randn(N, device="cuda")
 g = C.Gemm(dict(a=native.ptr(a), b=native.ptr(b), M=M, N=N, K=K, lda=a.shape[1], ldb=b.shape[1], out_bf16=native.ptr(out),
-                ld_bf16=out.shape[1], bias=native.ptr(bias), act=1))
+                ld_bf16=out.shape[1], bias=native.ptr(bias), act=1, pair=pair))
 st = native.current_stream()
 for _ in range(8):
     g.launch(st)
