@@ -35,6 +35,14 @@ if ROOT not in sys.path:
 METRIC = "MNIST-DNN samples/sec (device-timed, max over ranks)"
 BATCH = 300
 DIMS = [784, 256, 256, 10]
+# --model: the other workloads the reference ships (BASELINE.json configs 3-5); (input dim, label dim or 0, description)
+MODELS = {
+    "simple_dnn": (784, 10, "simple_dnn 784-256-256-10"),
+    "cnn": (784, 10, "cnn_example conv5x5x32-pool-conv3x3x64-pool-dense256-10"),
+    "autoencoder": (784, 0, "autoencoder_example 784-256-128-256-784"),
+    "autoencoder_small": (784, 0, "autoencoder 784-32-784"),
+    "wide_dnn": (4096, 1000, "wide_dnn 4096-4096x4-1000"),
+}
 
 
 def reference_arm(args) -> int:
@@ -63,12 +71,12 @@ def _max_over_ranks(ctx, value: float) -> float:
     return max(D.all_gather_object(ctx, float(value)))
 
 
-def _synthetic_partition(rows: int, seed: int):
+def _synthetic_partition(rows: int, seed: int, in_dim: int = DIMS[0], n_classes: int = DIMS[-1]):
     import numpy as np
 
     rng = np.random.default_rng(seed)
-    x = rng.random((rows, DIMS[0]), dtype=np.float32)
-    y = np.eye(DIMS[-1], dtype=np.float32)[rng.integers(0, DIMS[-1], rows)]
+    x = rng.random((rows, in_dim), dtype=np.float32)
+    y = np.eye(n_classes, dtype=np.float32)[rng.integers(0, n_classes, rows)] if n_classes else None
     return x, y
 
 
@@ -85,12 +93,15 @@ def run_ours(args, ctx) -> dict:
     torch.cuda.set_device(dev)
     lock = args.mode == "lock"
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001, beta1=0.9, beta2=0.999))
-    sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock=lock, iters=1, mini_batch=BATCH,
+    in_dim, n_classes, model_desc = MODELS[args.model]
+    sess = TrainingSession(zoo.build(args.model), "x:0", "y:0" if n_classes else None, spec, acquire_lock=lock, iters=1, mini_batch=BATCH,
                            mini_stochastic_iters=1, shuffle=True, engine="b200", seed=1234, pull_mode=args.pull_mode,
                            push_mode=args.push_mode, devices=[dev.index]).open()
     eng = sess.make_engine(dev)
     rows = max(args.partition_rows, BATCH * 2)
-    x, y = _synthetic_partition(rows, seed=100 + ctx.rank)
+    if in_dim * rows * 4 > (1 << 30):
+        rows = max(BATCH * 2, (1 << 30) // (in_dim * 4))
+    x, y = _synthetic_partition(rows, seed=100 + ctx.rank, in_dim=in_dim, n_classes=n_classes)
     eng.load_partition(x, y)
     K, W = args.steps, args.warmup
     n_batches = rows // BATCH
@@ -161,14 +172,15 @@ def run_ours(args, ctx) -> dict:
     counters = sess.counters()
     launches = len(plan)
     res = {
-        "metric": METRIC, "value": ctx.world * BATCH * K / (dev_ms / 1e3), "unit": "samples/s", "n_gpus": ctx.world, "steps": K,
+        "metric": METRIC if args.model == "simple_dnn" else f"{args.model} samples/sec (device-timed, max over ranks)",
+        "value": ctx.world * BATCH * K / (dev_ms / 1e3), "unit": "samples/s", "n_gpus": ctx.world, "steps": K,
         "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "impl": "sparkflow_b200",
-        "config": {"model": "simple_dnn 784-256-256-10", "global_batch": ctx.world * BATCH, "seq_len": 1,
+        "config": {"model": model_desc, "global_batch": ctx.world * BATCH, "seq_len": 1,
                    "parallelism": f"async-ps dp{ctx.world} ({'rw-lock' if lock else 'hogwild'}, master on gpu0)",
                    "optimizer": "adam(1e-3), one step per push on the master", "pull_mode": w.pull_mode, "push_mode": sess.push_mode,
                    "l2": "device-timed value: 256 MiB flush between steps (outside the event pairs); e2e: pinned partition "
-                         f"{rows * DIMS[0] * 4 >> 20} MiB > L2, a fresh minibatch H2D every step",
+                         f"{rows * in_dim * 4 >> 20} MiB > L2, a fresh minibatch H2D every step",
                    "kernels_per_step": plan.names(), "cuda_graph": bool(w.use_graphs)},
         "e2e": {"value": ctx.world * BATCH * K / (e2e_ms / 1e3), "unit": "samples/s", "ms_per_step": e2e_ms / K,
                 "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step), "wall_ms_per_step": wall_ms / K,
@@ -240,6 +252,7 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl"])
+    ap.add_argument("--model", default="simple_dnn", choices=sorted(MODELS), help="workload (the headline metric is simple_dnn)")
     ap.add_argument("--mode", default="lock", choices=["lock", "hogwild"], help="acquire_lock=True (BASELINE config 2) or Hogwild")
     ap.add_argument("--pull-mode", default=None, choices=[None, "copy", "direct"])
     ap.add_argument("--push-mode", default=None, choices=[None, "direct", "served"],

@@ -373,7 +373,7 @@ __device__ __forceinline__ void signal_done(float* loss_out, unsigned int* done_
 }
 
 template <int OPT, bool SYS>
-__global__ void __launch_bounds__(kPushThreads, 1)
+__global__ void __launch_bounds__(kPushThreads, 2)
 push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   __shared__ uint32_t s_t;
   __shared__ uint32_t s_epoch;
@@ -719,8 +719,10 @@ static int launch_push(const SfPushArgs* a, uint32_t* ls, int grid, cudaStream_t
 }
 
 extern "C" int sf_push_launch(const SfPushArgs* a, uint32_t* local_sync, int grid, cudaStream_t st) {
-  if (grid <= 0) grid = a->num_tiles < 148 ? a->num_tiles : 148;
-  if (grid > 148) grid = 148;          // lock mode needs every CTA resident
+  // lock mode needs every CTA resident: at most two 256-thread CTAs per SM (launch bounds); big models use both for
+  // twice the loads in flight per SM
+  if (grid <= 0) grid = a->num_tiles < 296 ? a->num_tiles : 296;
+  if (grid > 296) grid = 296;
   if (grid < 1) grid = 1;
   switch (a->optimizer) {
     case SF_OPT_SGD: return launch_push<SF_OPT_SGD>(a, local_sync, grid, st);
