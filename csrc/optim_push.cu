@@ -232,9 +232,11 @@ __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc
 // Shared by the worker-side push kernel (n_grads = 1, master tuples over NVLink, ZERO: the consumed gradient is
 // cleared for the next step's accumulating epilogues) and the master-resident applier (gradients from up to 8
 // worker mailboxes: state traffic and publish are paid once per batch instead of once per push).
+// `pub0` / `vec0`: publish targets standing in for a.shadow_dst[0] / a.vec_pub[0] (the applier alternates buffers).
 template <int OPT, bool ZERO>
 __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* grads, int n_grads, int tile,
-                                          const uint32_t* s_t_ptr, bool sync_for_t, __nv_bfloat16 (*s_tr)[kTileR + 8]) {
+                                          const uint32_t* s_t_ptr, bool sync_for_t, __nv_bfloat16 (*s_tr)[kTileR + 8],
+                                          __nv_bfloat16* pub0, float* vec0) {
   constexpr int NS = Slots<OPT>::n;
   const int tid = threadIdx.x;
   const bool mc = a.shadow_is_mc != 0;
@@ -334,13 +336,18 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
             w[j] = q.p;
             float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
             st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
+            if (a.n_vec_pub > 0 && e[half] + j >= a.vec_offset) {       // 1-D variables: fp32 publish copy / copies
+              const long long vi = e[half] + j - a.vec_offset;
+              vec0[vi] = q.p;
+              if (a.n_vec_pub > 1) a.vec_pub[1][vi] = q.p;
+            }
           }
         }
         // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
         if (sg.w_off >= 0) {
           const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
           const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
-          for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8(a.shadow_dst[d] + wo, q, mc && d == 0);
+          for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8((d == 0 ? pub0 : a.shadow_dst[d]) + wo, q, mc && d == 0);
         }
       }
       if (sg.wt_off >= 0 && !a.drop) {
@@ -356,7 +363,7 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
       if (cc < sg.cols && rr < sg.rows) {
         const int64_t to = sg.wt_off + static_cast<int64_t>(cc) * sg.wt_ld + rr;
         const uint4 q = *reinterpret_cast<const uint4*>(&s_tr[cl][part * 8]);
-        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16(a.shadow_dst[d] + to, q, mc && d == 0);
+        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16((d == 0 ? pub0 : a.shadow_dst[d]) + to, q, mc && d == 0);
       }
       __syncthreads();
     }
@@ -414,7 +421,7 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
   // ---------------- tiles ----------------
   float* const grads[1] = {a.grad};
   for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x)
-    push_tile<OPT, true>(a, grads, 1, tile, &s_t, !locked && tile == static_cast<int>(blockIdx.x), s_tr);
+    push_tile<OPT, true>(a, grads, 1, tile, &s_t, !locked && tile == static_cast<int>(blockIdx.x), s_tr, a.shadow_dst[0], a.vec_pub[0]);
 
   // ---------------- completion ----------------
   __syncthreads();
@@ -470,11 +477,16 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
     }
     __syncthreads();
   }
+  const bool dbuf = locked && a.dbuf != 0;
+  __shared__ uint32_t s_cur;
   if (locked) {
     if (tid == 0) {
       const uint32_t epoch = ld_acquire_gpu(local_sync + 3);
       if (blockIdx.x == 0) {
-        rw_acquire_read<SYS>(a.ctrl + SF_CTRL_LOCK);
+        uint32_t cur = 0;
+        if (dbuf) cur = atom_add_acqrel_sys(a.ctrl + SF_CTRL_PUB, 1u) >> 31;      // register + learn the complete buffer
+        else rw_acquire_read<SYS>(a.ctrl + SF_CTRL_LOCK);
+        local_sync[1] = cur;
         st_release_gpu(local_sync + 0, epoch + 1);
       } else {
         const unsigned long long t0 = gtime_ns();
@@ -483,13 +495,15 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
         }
       }
       s_epoch = epoch;
+      s_cur = local_sync[1];
     }
     __syncthreads();
   }
+  const uint32_t cur = dbuf ? s_cur : 0u;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t gid = static_cast<size_t>(blockIdx.x) * blockDim.x + tid;
   {
-    const uint4* s = reinterpret_cast<const uint4*>(a.src);
+    const uint4* s = reinterpret_cast<const uint4*>(cur ? a.src_alt : a.src);
     uint4* d = reinterpret_cast<uint4*>(a.dst);
     const size_t n16 = a.n_bf16 / 8;
     // 4 independent 16-byte loads in flight per thread to cover the ~2 us NVLink latency
@@ -501,7 +515,10 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
     }
     for (; i < n16; i += stride) d[i] = ld_stream_u4(s + i);
   }
-  if (a.src_state != nullptr) {      // 1-D variables: gather .x of the interleaved master state
+  if (dbuf) {                        // 1-D variables: the fp32 copy that belongs to the same published version
+    const float* vp = a.vec_pub[cur];
+    for (size_t i = gid; i < a.n_f32; i += stride) a.dst_f32[i] = ld_relaxed_sys_f32(vp + i);
+  } else if (a.src_state != nullptr) {      // 1-D variables: gather .x of the interleaved master state
     for (size_t i = gid; i < a.n_f32; i += stride) a.dst_f32[i] = ld_stream_f4(a.src_state + i).x;
   }
   if (gid == 0 && a.seen_version != nullptr) *a.seen_version = ld_relaxed_sys(a.ctrl + SF_CTRL_VERSION);
@@ -512,7 +529,8 @@ pull_kernel(const SfPullArgs a, uint32_t* local_sync) {
       if (prev == gridDim.x - 1) {
         (void)ld_acquire_gpu(local_sync + 2);
         local_sync[2] = 0;
-        rw_release_read<SYS>(a.ctrl + SF_CTRL_LOCK);
+        if (dbuf) lk_red_release<SYS>(a.ctrl + SF_CTRL_PUB, 0u - 1u);
+        else rw_release_read<SYS>(a.ctrl + SF_CTRL_LOCK);
         st_release_gpu(local_sync + 3, s_epoch + 1);
       }
     }
@@ -595,6 +613,7 @@ __global__ void __launch_bounds__(kPushThreads, 1)
 applier_kernel(const SfApplierArgs a, const uint32_t seq) {
   __shared__ uint32_t s_t;
   __shared__ uint32_t s_mask;
+  __shared__ uint32_t s_buf;
   __shared__ int s_n;
   __shared__ float* s_grads[8];
   __shared__ __align__(16) __nv_bfloat16 s_tr[kTileC][kTileR + 8];
@@ -634,16 +653,28 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
           m_ready = keep;
         }
         if (tid == 0) {
-          uint32_t t = 0;
+          uint32_t t = 0, buf = 0;
           if (m_ready) {
-            if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+            if (locked) rw_acquire_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);       // vs. worker-applied / external pushes
+            if (a.dbuf) {
+              // write the buffer that is NOT current.  Pulls still copying it registered before the last flip: one
+              // instant with no pull in flight (any time after that flip) means they are all gone.
+              const unsigned long long t0 = gtime_ns();
+              uint32_t pub;
+              while (((pub = ld_acquire_sys(a.push.ctrl + SF_CTRL_PUB)) & 0xFFFFu) != 0u) {
+                if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x409);
+              }
+              buf = (pub >> 31) ^ 1u;
+            }
             t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
           }
           a.sync[1] = m_ready;
           a.sync[2] = t;
+          a.sync[5] = buf;
           st_release_gpu(a.sync + 0, epoch);
           s_mask = m_ready;
           s_t = t;
+          s_buf = buf;
         }
       }
     } else if (tid == 0) {
@@ -654,6 +685,7 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
       }
       s_mask = a.sync[1];
       s_t = a.sync[2];
+      s_buf = a.sync[5];
     }
     __syncthreads();
     const uint32_t mask = s_mask;
@@ -670,8 +702,10 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
     }
     __syncthreads();
     const int n = s_n;
+    __nv_bfloat16* const pub0 = (a.dbuf && s_buf) ? a.shadow_alt : a.push.shadow_dst[0];
+    float* const vec0 = (a.dbuf && s_buf) ? a.vec_pub_alt : a.push.vec_pub[0];
     for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x)
-      push_tile<OPT, false>(a.push, s_grads, n, tile, &s_t, false, s_tr);
+      push_tile<OPT, false>(a.push, s_grads, n, tile, &s_t, false, s_tr, pub0, vec0);
     __syncthreads();
     if (tid == 0) lk_red_release<false>(a.sync + 3, 1u);
     if (leader && tid < 32) {
@@ -682,6 +716,9 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         }
         a.sync[3] = 0;                                  // everybody has arrived; the next decision is published after this
         a.sync[4] = static_cast<uint32_t>(32 - __clz(mask));     // cursor: one past the highest worker served
+        // the freshly written buffer becomes the current one (release: after every CTA's publish stores, which the
+        // acquire of the done counter above made visible to this thread)
+        if (a.dbuf) (void)atom_xor_release_sys(a.push.ctrl + SF_CTRL_PUB, 0x80000000u);
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, static_cast<uint32_t>(n));
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, static_cast<uint32_t>(n));
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, static_cast<uint32_t>(n));

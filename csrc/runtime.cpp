@@ -131,6 +131,11 @@ SfPushArgs parse_push(const py::dict& d) {
   if (dsts.size() > 8) throw std::runtime_error("push: at most 8 publish destinations");
   a.n_shadow_dst = static_cast<int>(dsts.size());
   for (size_t i = 0; i < dsts.size(); ++i) a.shadow_dst[i] = P<__nv_bfloat16>(dsts[i]);
+  auto vps = getd<std::vector<uintptr_t>>(d, "vec_pub", {});
+  if (vps.size() > 2) throw std::runtime_error("push: at most 2 vec_pub targets");
+  a.n_vec_pub = static_cast<int>(vps.size());
+  for (size_t i = 0; i < vps.size(); ++i) a.vec_pub[i] = P<float>(vps[i]);
+  a.vec_offset = getd<long long>(d, "vec_offset", 0);
   a.shadow_is_mc = getd<int>(d, "shadow_is_mc", 0);
   a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
   a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
@@ -217,6 +222,11 @@ SfPullArgs parse_pull(const py::dict& d) {
   a.scope_sys = getd<int>(d, "scope_sys", 1);
   a.wait_applied = P<const uint32_t>(getd<uintptr_t>(d, "wait_applied", 0));
   a.my_posted = P<const uint32_t>(getd<uintptr_t>(d, "my_posted", 0));
+  a.dbuf = getd<int>(d, "dbuf", 0);
+  a.src_alt = P<const __nv_bfloat16>(getd<uintptr_t>(d, "src_alt", 0));
+  a.vec_pub[0] = P<const float>(getd<uintptr_t>(d, "vec_pub0", 0));
+  a.vec_pub[1] = P<const float>(getd<uintptr_t>(d, "vec_pub1", 0));
+  if (a.dbuf && (!a.src_alt || (a.n_f32 && (!a.vec_pub[0] || !a.vec_pub[1])))) throw std::runtime_error("pull: dbuf needs src_alt and vec_pub0/1");
   if (a.wait_applied && !a.my_posted) throw std::runtime_error("pull: wait_applied needs my_posted");
   if (a.n_bf16 % 8) throw std::runtime_error("pull: bf16 size must be a 16-byte multiple");
   if (!a.ctrl) throw std::runtime_error("pull: ctrl is required");
@@ -636,7 +646,7 @@ class StepDriver {
 class Applier {
  public:
   Applier(const py::dict& push, uintptr_t mailboxes, size_t mailbox_stride, uintptr_t flags, int n_workers, uintptr_t sync,
-          double poll_window_s, int grid, int depth, int max_batch) : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
+          double poll_window_s, int grid, int depth, int max_batch, uintptr_t shadow_alt, uintptr_t vec_pub_alt) : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
     py::dict d(push);
     std::memset(&args_, 0, sizeof(args_));
     args_.push = parse_push(d);
@@ -647,6 +657,10 @@ class Applier {
     args_.sync = P<uint32_t>(sync);
     args_.idle_timeout_ns = static_cast<unsigned long long>(poll_window_s * 1e9);
     args_.max_batch = max_batch;
+    args_.shadow_alt = P<__nv_bfloat16>(shadow_alt);
+    args_.vec_pub_alt = P<float>(vec_pub_alt);
+    args_.dbuf = shadow_alt != 0 ? 1 : 0;
+    if (args_.dbuf && args_.push.n_vec_pub > 0 && !args_.vec_pub_alt) throw std::runtime_error("applier: dbuf needs vec_pub_alt");
     ck(cudaGetDevice(&device_), "cudaGetDevice");
     int lo = 0, hi = 0;
     ck(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
@@ -767,6 +781,7 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "sparkflow_b200 native runtime (sm_100a kernels + step-plan runner)";
   m.attr("ARCH") = "sm_100a";
   m.attr("CTRL_WORDS") = static_cast<int>(SF_CTRL_WORDS);
+  m.attr("CTRL_PUB") = static_cast<int>(SF_CTRL_PUB);
   m.attr("SEG_BYTES") = static_cast<int>(sizeof(SfTensorSeg));
   m.attr("PUSH_TILE_R") = 32;
   m.attr("PUSH_TILE_C") = 64;
@@ -883,9 +898,9 @@ PYBIND11_MODULE(_C, m) {
       });
 
   py::class_<Applier>(m, "Applier")
-      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int, int>(), py::arg("push"), py::arg("mailboxes"),
+      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int, int, uintptr_t, uintptr_t>(), py::arg("push"), py::arg("mailboxes"),
            py::arg("mailbox_stride"), py::arg("flags"), py::arg("n_workers"), py::arg("sync"), py::arg("poll_window_s") = 30e-6,
-           py::arg("grid") = 96, py::arg("depth") = 3, py::arg("max_batch") = 8)
+           py::arg("grid") = 96, py::arg("depth") = 3, py::arg("max_batch") = 8, py::arg("shadow_alt") = 0, py::arg("vec_pub_alt") = 0)
       .def("alive", &Applier::alive)
       .def("launches", &Applier::launches)
       .def("stop", &Applier::stop);

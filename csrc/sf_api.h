@@ -161,6 +161,9 @@ struct SfPushArgs {
   // With NVLS a single multicast alias covers every replica (shadow_is_mc = 1).
   __nv_bfloat16* shadow_dst[8];
   int n_shadow_dst;
+  float* vec_pub[2];              // optional fp32 publish of the 1-D variables (double-buffered publish), indexed from
+  int n_vec_pub;                  // vec_offset; the worker-applied push writes both copies, the applier one per pass
+  long long vec_offset;
   int shadow_is_mc;
   float* grad;                    // local flat gradient (consumed, then zeroed for the next step)
   float* loss_acc;                // local: loss accumulated by the loss kernel (consumed + zeroed)
@@ -191,6 +194,7 @@ enum SfCtrl {
   SF_CTRL_PUSHES = 3,       // total pushes applied
   SF_CTRL_ERRORS = 4,
   SF_CTRL_DROPPED = 5,
+  SF_CTRL_PUB = 6,          // double-buffered publish: bit 31 = current buffer, [0,16) = pulls in flight (either buffer)
   SF_CTRL_WORDS = 64
 };
 
@@ -212,6 +216,12 @@ struct SfPullArgs {
   // push always observes the worker's own update (the reference's POST /update is synchronous)
   const uint32_t* wait_applied;   // master flag word (peer mapped) or nullptr
   const uint32_t* my_posted;      // local word holding the sequence number of my last post
+  // double-buffered publish (served push, lock mode): instead of the RW lock the pull registers in SF_CTRL_PUB with
+  // ONE remote atomic, learns which of the two complete publish buffers is current and copies that one; the applier
+  // writes the other buffer and flips.  Pulls never wait for an update in progress and still never see a torn one.
+  int dbuf;
+  const __nv_bfloat16* src_alt;   // publish buffer 1 (src is buffer 0)
+  const float* vec_pub[2];        // fp32 copies of the 1-D variables, one per buffer
 };
 int sf_pull_launch(const SfPullArgs* a, uint32_t* local_sync, int grid, cudaStream_t st);
 
@@ -241,6 +251,9 @@ struct SfApplierArgs {
   int n_workers;
   uint32_t* sync;                 // 8 words of master-local memory for the in-grid protocol
   unsigned long long idle_timeout_ns;   // listening window of one launch
+  int dbuf;                       // double-buffered publish: passes alternate between (push.shadow_dst[0], push.vec_pub[0])
+  __nv_bfloat16* shadow_alt;      // and (shadow_alt, vec_pub_alt); SF_CTRL_PUB bit 31 names the complete one
+  float* vec_pub_alt;
   int max_batch;                  // pushes fused into one pass over the state (1..8; 0 = 8)
 };
 int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st);

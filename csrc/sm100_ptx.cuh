@@ -393,6 +393,16 @@ __device__ __forceinline__ uint32_t atom_add_acqrel_sys(uint32_t* p, uint32_t va
                : "memory");
   return old;
 }
+__device__ __forceinline__ uint32_t atom_xor_release_sys(uint32_t* p, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.release.sys.global.xor.b32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.relaxed.sys.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ uint32_t atom_add_relaxed_sys(uint32_t* p, uint32_t val) {
   uint32_t old;
   asm volatile("atom.relaxed.sys.global.add.u32 %0, [%1], %2;"

@@ -55,6 +55,9 @@ class MasterLayout:
     flags: int = 0
     applier_sync: int = 0
     n_mailboxes: int = 0
+    shadow_alt: int = 0            # second publish buffer + fp32 copies of the 1-D tail (double-buffered publish)
+    vec_pub0: int = 0
+    vec_pub1: int = 0
 
     @classmethod
     def build(cls, layout: ParamLayout, ctrl_words: int, n_mailboxes: int = 0, mb_words: int = 32) -> "MasterLayout":
@@ -75,7 +78,10 @@ class MasterLayout:
         flags = take(n_mailboxes * mb_words * 4)
         sync = take(64)
         boxes = take(n_mailboxes * stride * 4)
-        return cls(ctrl, state, shadow, off, boxes, stride, flags, sync, n_mailboxes)
+        shadow_alt = take(layout.shadow_total * 2)
+        vp0 = take(max(layout.vec_count, 4) * 4)
+        vp1 = take(max(layout.vec_count, 4) * 4)
+        return cls(ctrl, state, shadow, off, boxes, stride, flags, sync, n_mailboxes, shadow_alt, vp0, vp1)
 
 
 def _sync_current(device: torch.device) -> None:
@@ -105,6 +111,13 @@ class MasterState:
         self.p = self.state[:, 0]
         self.slots = [self.state[:, 1 + i] for i in range(3)]
         self.shadow = self._bytes[self.ml.shadow:self.ml.shadow + layout.shadow_total * 2].view(torch.bfloat16)
+        # double-buffered publish (served push + lock mode + replica pulls): see SfPullArgs.dbuf in csrc/sf_api.h
+        self.dbuf_capable = n_mailboxes > 0 and os.environ.get("SPARKFLOW_PUBLISH", "double") != "single"
+        self.dbuf_active = False
+        if n_mailboxes > 0:
+            self.shadow_alt = self._bytes[self.ml.shadow_alt:self.ml.shadow_alt + layout.shadow_total * 2].view(torch.bfloat16)
+            nv = max(layout.vec_count, 4)
+            self.vec_pub = [self._bytes[o:o + nv * 4].view(torch.float32) for o in (self.ml.vec_pub0, self.ml.vec_pub1)]
 
     # -- owner-side API ---------------------------------------------------------------------------
     def ipc_handle(self) -> bytes:
@@ -130,7 +143,7 @@ class MasterState:
         return self.base + self.ml.flags + worker * self.C.MB_WORDS * 4
 
     def start_applier(self, acquire_lock: bool, scope_sys: bool, grid: int = 0, poll_window_s: float = 30e-6, depth: int = 3,
-                      max_batch: int = 0) -> None:
+                      max_batch: int = 0, dbuf: bool = False) -> None:
         """Start the applier (owner process only): a host thread that keeps `depth` finite poll-and-apply
         kernels queued on a dedicated high-priority stream of the master GPU.  `max_batch` pushes (default 8,
         env SPARKFLOW_APPLIER_BATCH) are applied per pass over the state - each still its own optimizer step."""
@@ -140,19 +153,52 @@ class MasterState:
             self._segs_dev = torch.frombuffer(bytearray(self.C.pack_segs(lay.seg_rows())), dtype=torch.uint8).to(self.device)
             self._tile_map = torch.from_numpy(lay.tile_map()).to(self.device)
             _sync_current(self.device)
-            push = dict(state=native.ptr(self.state), ctrl=native.ptr(self.ctrl), shadow_dst=[native.ptr(self.shadow)], grad=0, applier=1,
+            self.dbuf_active = bool(dbuf and acquire_lock and self.dbuf_capable)
+            self.ctrl[self.C.CTRL_PUB + 1] = 1 if self.dbuf_active else 0        # workers read the publish protocol from here
+            extra = {}
+            if self.dbuf_active:
+                self._sync_publish_buffers()
+                extra = dict(vec_pub=[native.ptr(self.vec_pub[0])], vec_offset=lay.vec_offset)
+            push = dict(state=native.ptr(self.state), ctrl=native.ptr(self.ctrl), shadow_dst=[native.ptr(self.shadow)], grad=0, applier=1, **extra,
                         segs=native.ptr(self._segs_dev), tile_map=native.ptr(self._tile_map), num_tiles=int(self._tile_map.shape[0]),
                         seg_rows=lay.seg_rows(), optimizer=self.spec.opt_id, lock_mode=1 if acquire_lock else 0, drop=0,
                         scope_sys=1 if scope_sys else 0, grad_scale=1.0, hyper=self.spec.native_hyper())
             grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "112"))
             self.applier = self.C.Applier(push, self.base + self.ml.mailboxes, self.ml.mailbox_stride, self.base + self.ml.flags,
                                           self.ml.n_mailboxes, self.base + self.ml.applier_sync, poll_window_s, grid, depth,
-                                          max_batch or int(os.environ.get("SPARKFLOW_APPLIER_BATCH", "8")))
+                                          max_batch or int(os.environ.get("SPARKFLOW_APPLIER_BATCH", "8")),
+                                          native.ptr(self.shadow_alt) if self.dbuf_active else 0,
+                                          native.ptr(self.vec_pub[1]) if self.dbuf_active else 0)
 
     def stop_applier(self) -> None:
         if self.applier is not None:
             self.applier.stop()
             self.applier = None
+            if self.dbuf_active:
+                self._settle_publish()
+
+    def _sync_publish_buffers(self) -> None:
+        """Both publish buffers (and the fp32 copies of the 1-D tail) = the current parameters; buffer 0 current."""
+        lay = self.layout
+        with torch.cuda.device(self.device):
+            self.shadow_alt.copy_(self.shadow)
+            if lay.vec_count:
+                v = self.state[lay.vec_offset:lay.vec_offset + lay.vec_count, 0]
+                self.vec_pub[0][:lay.vec_count].copy_(v)
+                self.vec_pub[1][:lay.vec_count].copy_(v)
+            self.ctrl[self.C.CTRL_PUB] = 0
+            _sync_current(self.device)
+
+    def _settle_publish(self) -> None:
+        """The applier is stopped: make buffer 0 the current, complete one (readers that do not follow the double-buffer
+        protocol - TMA-direct inference plans, worker-applied pushes - only know buffer 0)."""
+        with torch.cuda.device(self.device):
+            pub = int(self.ctrl[self.C.CTRL_PUB].item()) & 0xFFFFFFFF
+            if pub >> 31:
+                self.shadow.copy_(self.shadow_alt)
+                self.vec_pub[0].copy_(self.vec_pub[1])
+            self.ctrl[self.C.CTRL_PUB] = 0
+            _sync_current(self.device)
 
     def load_weights(self, weights: Sequence[np.ndarray]) -> None:
         """Initialise params, slots, control block and the bf16 publish buffer (owner only)."""
@@ -165,6 +211,8 @@ class MasterState:
         self.ctrl.zero_()
         pub = torch.from_numpy(self.layout.publish_reference(flat)).to(torch.bfloat16)
         self.shadow.copy_(pub)
+        if self.ml.n_mailboxes > 0:
+            self._sync_publish_buffers()
         _sync_current(self.device)
 
     def weights(self) -> List[np.ndarray]:
@@ -225,6 +273,14 @@ class DeviceWorker:
         self.worker_index = worker_index
         self.served = bool(master.served)          # push = post to my mailbox, the master-resident applier applies it
         self.pull_mode = pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")
+        # lock mode without a lock on the read side: pulls pick the complete one of two publish buffers (see start_applier)
+        self.use_dbuf = False
+        if self.served:
+            applier_dbuf = int(master.ctrl[self.C.CTRL_PUB + 1].item()) == 1      # written by start_applier (before any worker exists)
+            if applier_dbuf and (self.pull_mode != "copy" or not acquire_lock):
+                raise RuntimeError("the applier publishes double-buffered (lock mode, replica pulls) but this worker was created with "
+                                   f"pull_mode={self.pull_mode!r}, acquire_lock={acquire_lock}")
+            self.use_dbuf = applier_dbuf
         if self.pull_mode == "direct" and self.lock_mode:
             self.pull_mode = "copy"            # a locked pull must be a private snapshot
         self.use_graphs = use_graphs and os.environ.get("SPARKFLOW_NO_GRAPHS") != "1"
@@ -289,7 +345,9 @@ class DeviceWorker:
                     ctrl=native.ptr(m.ctrl), seen_version=native.ptr(self.seen_version), lock_mode=self.lock_mode,
                     scope_sys=self.scope_sys,
                     wait_applied=(m.flags_ptr(self.worker_index) + self.C.MB_APPLIED * 4) if self.served else 0,
-                    my_posted=(native.ptr(self.sync_push) + 16) if self.served else 0)
+                    my_posted=(native.ptr(self.sync_push) + 16) if self.served else 0,
+                    **(dict(dbuf=1, src_alt=native.ptr(m.shadow_alt), vec_pub0=native.ptr(m.vec_pub[0]), vec_pub1=native.ptr(m.vec_pub[1]))
+                       if self.use_dbuf else {}))
 
     # ------------------------------------------------------------------------------------------
     # ---- zero-copy minibatch fetch (in-graph SM loads from the pinned host partition) ------------------------

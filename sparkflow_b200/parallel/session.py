@@ -150,10 +150,16 @@ class TrainingSession:
             self.master.load_slots(slots, step)
         if self.engine_kind == "b200" and self.push_mode == "served" and self.master.owner:
             n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
-            self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1)
+            self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1, dbuf=self._dbuf())
         D.barrier(ctx)
         self._opened = True
         return self
+
+    def _dbuf(self) -> bool:
+        """Double-buffered publish is usable when every worker pulls into a replica (not TMA-direct from buffer 0)."""
+        import os
+
+        return (self.pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")) == "copy"
 
     def quiesce(self) -> None:
         """Collective: drain every worker, stop the applier, do a genuine device-wide ``torch.cuda.synchronize()``
@@ -172,7 +178,7 @@ class TrainingSession:
                 torch.cuda.synchronize(d)
         if served and self.master.owner:
             n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
-            self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1)
+            self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1, dbuf=self._dbuf())
         D.barrier(ctx)
 
     # -- snapshot / resume ------------------------------------------------------------------------------
@@ -229,7 +235,7 @@ class TrainingSession:
         if self.engine_kind == "b200" and self.push_mode == "served" and self.master.owner:
             if self.master.applier is None or not self.master.applier.alive():      # idle timeout between rounds
                 n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
-                self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1)
+                self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1, dbuf=self._dbuf())
         D.barrier(ctx)
         mine = [(i, p) for i, p in enumerate(partitions) if i % ctx.world == ctx.rank]
         devices = self.local_devices()

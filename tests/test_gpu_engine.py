@@ -37,7 +37,7 @@ def _data(n, d, c, kind, seed=0):
     return X, Y
 
 
-def _setup(name, spec, lock=False, pull_mode="copy", served=False):
+def _setup(name, spec, lock=False, pull_mode="copy", served=False, dbuf=False):
     tf_in, tf_lab, d, c, kind = CASES[name]
     ir = GraphIR.from_metagraph(zoo.build(name))
     lp = compile_graph(ir, tf_in, tf_lab)
@@ -48,7 +48,7 @@ def _setup(name, spec, lock=False, pull_mode="copy", served=False):
     w0 = GraphProgram(ir).init_weights(seed=1)
     master.load_weights(w0)
     if served:
-        master.start_applier(lock, scope_sys=False, grid=32)
+        master.start_applier(lock, scope_sys=False, grid=32, dbuf=dbuf)
     worker = DeviceWorker(ir, tf_in, tf_lab, spec, master, acquire_lock=lock, pull_mode=pull_mode, shared=False)
     return ir, master, worker, w0, (tf_in, tf_lab, d, c, kind)
 
@@ -125,12 +125,13 @@ def test_graph_replay_equals_eager(pull_mode):
         np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("lock", [False, True])
-def test_served_push_mailbox_applier_tracks_oracle(lock):
-    """push = post to the mailbox + persistent applier kernel on the master GPU; same numbers as direct mode."""
+@pytest.mark.parametrize("lock,dbuf", [(False, False), (True, False), (True, True)])
+def test_served_push_mailbox_applier_tracks_oracle(lock, dbuf):
+    """push = post to the mailbox + applier kernels on the master GPU; same numbers as direct mode.  dbuf: lock mode
+    with the double-buffered publish (pulls register with one atomic and copy the complete buffer, no RW lock)."""
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
-    ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, lock, served=True)
-    assert worker.served and master.applier.alive()
+    ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, lock, served=True, dbuf=dbuf)
+    assert worker.served and master.applier.alive() and worker.use_dbuf == dbuf and master.dbuf_active == dbuf
     X, Y = _data(256, d, c, kind)
     eng = B200Engine(worker)
     eng.load_partition(X, Y)
@@ -152,6 +153,15 @@ def test_served_push_mailbox_applier_tracks_oracle(lock):
         assert np.abs(a - b).max() < 5 * 0.001 * len(rows), v.name
         assert np.mean(np.abs(a - b)) < 0.35 * 0.001 * len(rows), v.name
     assert master.applier.alive()
+    if dbuf:
+        # stopping the applier settles the publish on buffer 0: it must equal the bf16 image of the final parameters
+        master.stop_applier()
+        lay = master.layout
+        pub = lay.publish_reference(lay.flatten(master.weights()))
+        np.testing.assert_allclose(master.shadow.float().cpu().numpy(), torch.from_numpy(pub).to(torch.bfloat16).float().numpy(), rtol=0, atol=1e-2)
+        flat = lay.flatten(master.weights())
+        np.testing.assert_array_equal(master.vec_pub[0][:lay.vec_count].cpu().numpy(), flat[lay.vec_offset:lay.vec_offset + lay.vec_count])
+        assert master.counters()["lock"] == 0 and int(master.ctrl[master.C.CTRL_PUB].item()) == 0
     master.close()
     assert master.applier is None
 
@@ -212,7 +222,7 @@ def test_train_contiguous_native_loop_tracks_oracle(mode, served, monkeypatch):
     else:
         monkeypatch.setenv("SPARKFLOW_H2D", mode)
     spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
-    ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, True, served=served)
+    ir, master, worker, w0, (tf_in, tf_lab, d, c, kind) = _setup("simple_dnn", spec, True, served=served, dbuf=served)
     X, Y = _data(640, d, c, kind)
     eng = B200Engine(worker)
     assert eng.partition_mode == "resident" if mode == "resident" else eng.h2d_mode == mode
