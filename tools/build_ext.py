@@ -87,6 +87,11 @@ def build(verbose_ptxas: bool = False, only: str | None = None) -> dict[str, Pat
         if only in (None, "host") and (CSRC / "hostlib.cpp").exists():
             jobs["hostlib"] = ex.submit(_compile_cxx, "hostlib", [CSRC / "hostlib.cpp"])
         objs = {k: f.result() for k, f in jobs.items()}
+    # keep only the objects just used: stale ones would otherwise travel with every gpurun snapshot
+    for k, keep in objs.items():
+        for old in BUILD.glob(f"{k}.*.o"):
+            if old != keep:
+                old.unlink()
 
     if "kernels" in objs:
         so = PKG / "_C.so"
