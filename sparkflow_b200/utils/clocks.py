@@ -12,7 +12,7 @@ _QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,
 
 
 class ClockSampler:
-    def __init__(self, gpu_index: int = 0, period_ms: int = 100):
+    def __init__(self, gpu_index: int = 0, period_ms: int = 25):
         self.gpu_index, self.period_ms = gpu_index, period_ms
         self.lines: List[str] = []
         self.proc: Optional[subprocess.Popen] = None
