@@ -44,6 +44,29 @@ def _port_key(url: str) -> str:
     return ":" + url.rsplit(":", 1)[-1]
 
 
+def handle_model(data, graph_json, tfInput, tfLabel=None, master_url="localhost:5000", iters=1000, mini_batch_size=-1, shuffle=True,
+                 mini_stochastic_iters=-1, verbose=0, loss_callback=None):
+    """The per-partition worker body (reference: HogwildSparkModel.py:38-100, the function shipped to
+    ``rdd.foreachPartition``): train on the rows of ONE partition against the parameter server registered at
+    ``master_url`` with the reference's loop semantics (modes A / B / C, ``n - 1`` clamp, per-iteration shuffle,
+    ``verbose`` print format, ``loss_callback(loss, iteration, partition_id)``).  ``graph_json`` must be the graph the
+    server was started with.  Returns the partition id."""
+    from .parallel.worker import run_partition
+
+    model = _SERVERS.get(master_url) or _SERVERS.get(_port_key(master_url))
+    if model is None:
+        raise ConnectionError(f"no parameter server is running at {master_url}")
+    sess = model._session
+    if graph_json is not None and graph_json != sess.graph_json:
+        raise ValueError("handle_model: graph_json differs from the graph the parameter server at %s was started with" % master_url)
+    features, labels = handle_features(data, tfLabel is not None)
+    if features.shape[0] == 0:
+        return None
+    engine = sess.make_engine(sess.local_devices()[0] if sess.use_cuda else __import__("torch").device("cpu"))
+    return run_partition(engine, features, labels, iters=iters, mini_batch_size=mini_batch_size, shuffle=shuffle,
+                         mini_stochastic_iters=mini_stochastic_iters, verbose=verbose, loss_callback=loss_callback)
+
+
 class HogwildSparkModel(object):
     """Hogwild! / locked asynchronous SGD: every partition is a worker that pulls the master
     parameters, computes a gradient on a minibatch and pushes it; the master applies one optimizer
@@ -91,6 +114,17 @@ class HogwildSparkModel(object):
         _SERVERS[self.master_url] = self
         _SERVERS[_port_key(self.master_url)] = self
         self.server = self._session
+
+    def start_service(self, metagraph=None, optimizer=None, port=None):
+        """Reference: the body of the Flask process (HogwildSparkModel.py:175-244).  There is no separate service
+        process here - the master state lives on the driver GPU (or in this process on CPU) - so this is
+        ``start_server`` under the reference's name; ``metagraph`` / ``optimizer`` / ``port`` must be the ones the model
+        was constructed with and are only checked."""
+        if metagraph is not None and metagraph != self.tensorflowGraph:
+            raise ValueError("start_service: a different graph than the one this model was built with")
+        if port is not None and int(port) != int(self.port):
+            raise ValueError("start_service: a different port than the one this model was built with")
+        self.start_server()
 
     def stop_server(self):
         """Release the master state. Idempotent."""

@@ -192,3 +192,33 @@ def test_loss_callback_and_counters(spark):
     m.train(rdd)
     assert len(seen) == 8 and {i for _, i, _ in seen} == {0, 1, 2, 3} and len({pid for _, _, pid in seen}) == 2
     assert all(np.isfinite(l) for l, _, _ in seen)
+
+
+def test_handle_model_foreach_partition_and_module_helpers(spark):
+    """the reference's own driver loop, spelled out: ``rdd.foreachPartition(handle_model)`` against a running server,
+    then ``get_server_weights`` / ``put_deltas_to_server`` by master url (HogwildSparkModel.py:22-100, 246-272)"""
+    from sparkflow.HogwildSparkModel import get_server_weights, handle_model, put_deltas_to_server
+
+    rdd = gaussians(spark).rdd.map(lambda r: (np.asarray(r["features"]), r["label"])).coalesce(2)
+    mg = build_graph(create_random_model)
+    m = HogwildSparkModel(tensorflowGraph=mg, iters=3, tfInput="x:0", tfLabel="y:0", optimizer=tf.train.AdamOptimizer(0.05),
+                          master_url="localhost:5011", port=5011, engine="torch", seed=3)
+    try:
+        w0 = get_server_weights("localhost:5011")
+        seen = []
+        rdd.foreachPartition(lambda part: handle_model(part, mg, "x:0", tfLabel="y:0", master_url="localhost:5011", iters=3,
+                                                       mini_batch_size=50, loss_callback=lambda l, i, pid: seen.append((i, pid))))
+        w1 = get_server_weights("localhost:5011")
+        assert len(seen) == 6 and len({pid for _, pid in seen}) == 2
+        assert any(not np.allclose(a, b) for a, b in zip(w0, w1))
+        # one explicit delta = one optimizer step on the master
+        put_deltas_to_server([np.ones_like(w) for w in w1], "localhost:5011")
+        w2 = get_server_weights("localhost:5011")
+        assert all(np.all(b < a) for a, b in zip(w1, w2))          # adam step against an all-ones gradient lowers every weight
+        with pytest.raises(ValueError):
+            handle_model(iter([]), mg + " ", "x:0", tfLabel="y:0", master_url="localhost:5011")
+        m.start_service(mg, None, 5011)                              # the reference's service entry point: idempotent here
+    finally:
+        m.stop_server()
+    with pytest.raises(ConnectionError):
+        get_server_weights("localhost:5011")
