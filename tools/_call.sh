@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-SANITIZE_TIMEOUT=45 tools/sanitize.sh racecheck "cast_transpose or test_gemm_bias_relu or softmax_xent or im2col" 2>&1 | tail -6
-SANITIZE_TIMEOUT=45 tools/sanitize.sh memcheck "push_matches or pull_copies or maxpool or gemm_pair_kernel_epilogues or gemm_fused" 2>&1 | tail -6
+timeout 100 python bench.py --steps 200 --warmup 20 2>gpurun_out/t37.err | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('dev',round(d['value']/1e6,2),'e2e',round(d['e2e']['value']/1e6,2),'clocks',d['clocks'])"
+tail -2 gpurun_out/t37.err | cut -c1-200
