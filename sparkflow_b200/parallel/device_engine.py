@@ -286,6 +286,7 @@ class DeviceWorker:
         self.use_graphs = use_graphs and os.environ.get("SPARKFLOW_NO_GRAPHS") != "1"
         self.use_branches = os.environ.get("SPARKFLOW_NO_BRANCHES") != "1"
         self.fuse_loss = os.environ.get("SPARKFLOW_NO_FUSED_LOSS") != "1"
+        self.use_mega = os.environ.get("SPARKFLOW_MEGAKERNEL") == "1"       # opt-in: whole GEMM chain as one launch
         self.C.set_pdl(0 if os.environ.get("SPARKFLOW_NO_PDL") == "1" else 1)
         self.stream = torch.cuda.Stream(device=self.device)
         self.copy_stream = torch.cuda.Stream(device=self.device)

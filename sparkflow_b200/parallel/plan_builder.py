@@ -75,6 +75,31 @@ def _split_k(tiles: int, kblocks: int) -> int:
     return max(1, min(148 // max(tiles, 1), kblocks // 4))
 
 
+def _emit_mega(plan, C, items: List[List[Any]], keep: List[Any]) -> None:
+    """Turn the recorded GEMM chain into ONE megakernel op (or, when a GEMM is not a plain 128x32-tile one, back into
+    individual launches).  Within a layer the dgrad goes before the wgrad in ticket order: it is on the critical path."""
+    order = list(range(len(items)))
+    k = 0
+    while k + 1 < len(order):
+        a, b = items[order[k]], items[order[k + 1]]
+        if a[1].startswith("wgrad") and b[1].startswith("dgrad") and order[k] not in b[2]:
+            order[k], order[k + 1] = order[k + 1], order[k]
+            k += 2
+        else:
+            k += 1
+    pos = {old: new for new, old in enumerate(order)}
+    gemms = [items[o][0] for o in order]
+    deps = [sorted(pos[d] for d in items[o][2]) for o in order]
+    ok = all(g.bn == 32 and g.split_k == 1 and g.pair == 0 for g in gemms) and len(gemms) <= 16 and all(len(d) <= 4 for d in deps)
+    if not ok:
+        for o in range(len(items)):
+            plan.add_gemm(items[o][0], items[o][1])
+        return
+    mega = C.Mega(gemms, deps, int(os.environ.get("SPARKFLOW_MEGA_CTAS", "0")))
+    keep.append(mega)
+    plan.add_mega(mega, "mega[" + ",".join(items[o][1] for o in order) + "]")
+
+
 def add_fetch_ops(plan, fetch: Dict[str, Any], B: int, D: int) -> None:
     """fetch node (linear zero-copy stream of the minibatch into fp32 staging) + the cast / transpose that turns it into
     the first layer's operands, both for the input set ``fetch['target']``."""
@@ -177,6 +202,25 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     cur: Dict[str, Any] = dict(kind="flat", buf=a0, bufT=a0T, feat=D, ld=a0.shape[1])
     rec: Dict[int, Dict[str, Any]] = {}        # per-layer tensors needed by backward
     gemms: List[Any] = []
+    # opt-in (SPARKFLOW_MEGAKERNEL=1): dense-only training steps run their whole GEMM chain as ONE persistent launch
+    use_mega = bool(train and getattr(worker, "use_mega", False) and all(l.kind == "dense" for l in layers))
+    mega_items: List[List[Any]] = []          # [gemm, name, deps (indices into mega_items)]
+    produced: Dict[int, int] = {}             # output buffer address -> index of the GEMM that writes it
+
+    def emit(g, name: str, d: Dict[str, Any], on_side: bool = False) -> None:
+        """Add a GEMM to the plan: its own launch (optionally on the wgrad branch), or a ticket range of the megakernel."""
+        gemms.append(g)
+        if use_mega:
+            deps = sorted({produced[p] for p in (d.get("a"), d.get("b"), d.get("aux")) if p in produced})
+            mega_items.append([g, name, deps])
+            for k in ("out_bf16", "outT_bf16"):
+                if d.get(k):
+                    produced[d[k]] = len(mega_items) - 1
+        elif on_side:
+            side(lambda: plan.add_gemm(g, name))
+        else:
+            plan.add_gemm(g, name)
+
     out_f32 = None
     dz_last = dzT_last = None
     fuse_loss = False
@@ -241,16 +285,14 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
                 out_f32 = zeros(B, ks.cols, dtype=f32)
                 d.update(out_f32=P(out_f32), ld_f32=ks.cols)
             g = C.Gemm(d)
-            gemms.append(g)
-            plan.add_gemm(g, f"fwd{i}" + ("+loss" if fuse_loss else ""))
+            emit(g, f"fwd{i}" + ("+loss" if fuse_loss else ""), d)
             rec[i]["N"] = ks.cols
             break
         nxt = zeros(B, round_up(ks.cols, 8))
         nxtT = zeros(ks.cols, ldB) if train else None
         d.update(out_bf16=P(nxt), ld_bf16=nxt.shape[1], outT_bf16=P(nxtT), ld_t=ldB if train else 0)
         g = C.Gemm(d)
-        gemms.append(g)
-        plan.add_gemm(g, f"fwd{i}")
+        emit(g, f"fwd{i}", d)
         cur = dict(kind="flat", buf=nxt, bufT=nxtT, feat=ks.cols, ld=nxt.shape[1])
 
     result = None
@@ -301,22 +343,22 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             r = rec[i]
             if r["a_inT"] is None:
                 raise UnsupportedGraph("dense layer input has no transposed copy")
-            wg = C.Gemm(dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
-                             out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols))
-            gemms.append(wg)
-            side(lambda wg=wg, i=i: plan.add_gemm(wg, f"wgrad{i}"))
+            wd = dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
+                      out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols)
+            wg = C.Gemm(wd)
+            emit(wg, f"wgrad{i}", wd, on_side=True)
             if i == first_trainable:
                 break
             prev = layers[i - 1]
             if prev.kind == "dense":
                 pb = lay.by_name(prev.bias) if prev.bias else None
                 ndz, ndzT = zeros(B, r["a_in_ld"]), zeros(ks.rows, ldB)
-                dg = C.Gemm(dict(a=P(g_dz), lda=g_dz.shape[1], b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=B, N=ks.rows, K=ks.cols,
-                                 aux=P(r["a_in"]), ld_aux=r["a_in_ld"], aux_act=ACT_IDS[prev.act], out_bf16=P(ndz),
-                                 ld_bf16=ndz.shape[1], outT_bf16=P(ndzT), ld_t=ldB,
-                                 colsum=P(worker.grads) + pb.offset * 4 if pb else 0))
-                gemms.append(dg)
-                plan.add_gemm(dg, f"dgrad{i}")
+                dd = dict(a=P(g_dz), lda=g_dz.shape[1], b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=B, N=ks.rows, K=ks.cols,
+                          aux=P(r["a_in"]), ld_aux=r["a_in_ld"], aux_act=ACT_IDS[prev.act], out_bf16=P(ndz),
+                          ld_bf16=ndz.shape[1], outT_bf16=P(ndzT), ld_t=ldB,
+                          colsum=P(worker.grads) + pb.offset * 4 if pb else 0)
+                dg = C.Gemm(dd)
+                emit(dg, f"dgrad{i}", dd)
                 g_dz, g_dzT = ndz, ndzT
             else:                                  # flatten over a pooled image: gradient wrt the pooled tensor
                 g_img = zeros(B, ks.rows)
@@ -360,7 +402,9 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             g_img = zeros(B, h * w * cin)
             plan.add_col2im(P(dpatch), r["ldK"], B, h, w, cin, l.ksize[0], l.ksize[1], P(g_img))
             continue
-    if branches:
+    if use_mega:
+        _emit_mega(plan, C, mega_items, keep)
+    elif branches:
         plan.join(2)
     if fetch is not None:
         plan.join(3)

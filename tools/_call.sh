@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 100 python bench.py --steps 200 --warmup 20 2>gpurun_out/t37.err | python -c "
-import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('dev',round(d['value']/1e6,2),'e2e',round(d['e2e']['value']/1e6,2),'clocks',d['clocks'])"
-tail -2 gpurun_out/t37.err | cut -c1-200
+SPARKFLOW_MEGAKERNEL=1 timeout 60 python bench.py --steps 200 --warmup 20 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('MEGA dev',round(d['ms_per_step']*1e3,1),'warm',round(d['warm_cache_ms_per_step']*1e3,1),'e2e',round(d['e2e']['ms_per_step']*1e3,1), d['config']['kernels_per_step'], d['final_loss'])"
+timeout 60 python bench.py --steps 200 --warmup 20 2>/dev/null | python -c "
+import json,sys;d=json.loads(sys.stdin.read().strip().splitlines()[-1]);print('BASE dev',round(d['ms_per_step']*1e3,1),'warm',round(d['warm_cache_ms_per_step']*1e3,1),'e2e',round(d['e2e']['ms_per_step']*1e3,1))"
