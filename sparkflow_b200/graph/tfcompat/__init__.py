@@ -20,6 +20,9 @@ from .ops import (abs, add, argmax, cast, concat, constant, constant_initializer
                   random_uniform_initializer, reduce_max, reduce_mean, reduce_sum, reshape, shape, sigmoid, size, sqrt,
                   square, squared_difference, squeeze, stop_gradient, subtract, tanh, trainable_variables, transpose,
                   truncated_normal_initializer, zeros_initializer)
+from .ops import (ceil, clip_by_value, equal, floor, greater, greater_equal, less, less_equal, log1p, logical_and,  # noqa: F401
+                  logical_not, not_equal, ones_like, reciprocal, reduce_min, reduce_prod, rsqrt, sign, stack, tile, where,
+                  zeros_like)
 from .session import InteractiveSession, Session, get_default_session  # noqa: F401
 
 __version__ = "1.10.0-sparkflow_b200"
@@ -70,6 +73,8 @@ nn = _types.SimpleNamespace(
     dropout=_ops.dropout, softmax_cross_entropy_with_logits=_ops.softmax_cross_entropy_with_logits,
     softmax_cross_entropy_with_logits_v2=_ops.softmax_cross_entropy_with_logits,
     sigmoid_cross_entropy_with_logits=_ops.sigmoid_cross_entropy_with_logits,
+    relu6=_ops.relu6, selu=_ops.selu, softsign=_ops.softsign, log_softmax=_ops.log_softmax, l2_loss=_ops.l2_loss,
+    l2_normalize=_ops.l2_normalize,
 )
 layers = _types.SimpleNamespace(
     dense=_ops.dense, conv2d=_ops.conv2d_layer, max_pooling2d=_ops.max_pooling2d, average_pooling2d=_ops.average_pooling2d,
@@ -78,7 +83,8 @@ layers = _types.SimpleNamespace(
 losses = _types.SimpleNamespace(
     softmax_cross_entropy=_ops.softmax_cross_entropy, mean_squared_error=_ops.mean_squared_error,
     sigmoid_cross_entropy=_ops.sigmoid_cross_entropy, absolute_difference=_ops.absolute_difference,
-    add_loss=_ops.add_loss, get_losses=_ops.get_losses,
+    add_loss=_ops.add_loss, get_losses=_ops.get_losses, log_loss=_ops.log_loss, hinge_loss=_ops.hinge_loss,
+    huber_loss=_ops.huber_loss,
 )
 initializers = _types.SimpleNamespace(
     glorot_uniform=glorot_uniform_initializer, glorot_normal=glorot_normal_initializer, zeros=zeros_initializer,

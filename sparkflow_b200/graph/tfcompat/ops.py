@@ -734,3 +734,153 @@ def add_loss(loss, loss_collection=GraphKeys.LOSSES):
 
 def get_losses(scope=None, loss_collection=GraphKeys.LOSSES):
     return _g().get_collection(loss_collection, scope)
+
+
+# -------------------------------------------------------------------------------------------------
+# More of the TF-1.x surface, emitted as the same op types real TF graphs use (all of them are executed by
+# graph/executor.py; graphs that use them train on the interpreter engine unless the compiler recognises them)
+# -------------------------------------------------------------------------------------------------
+def relu6(x, name=None): return unary("Relu6", x, name)
+def selu(x, name=None): return unary("Selu", x, name)
+def softsign(x, name=None): return unary("Softsign", x, name)
+def rsqrt(x, name=None): return unary("Rsqrt", x, name)
+def log1p(x, name=None): return unary("Log1p", x, name)
+def floor(x, name=None): return unary("Floor", x, name)
+def ceil(x, name=None): return unary("Ceil", x, name)
+def sign(x, name=None): return unary("Sign", x, name)
+def reciprocal(x, name=None): return unary("Reciprocal", x, name)
+def zeros_like(x, dtype=None, name=None): return unary("ZerosLike", x, name)
+def ones_like(x, dtype=None, name=None): return unary("OnesLike", x, name)
+
+
+def log_softmax(logits, axis=-1, name=None):
+    return unary("LogSoftmax", logits, name)
+
+
+def _compare(op: str, a, b, name) -> Tensor:
+    if isinstance(a, (Tensor, Variable)):
+        a = convert_to_tensor(a)
+        b = convert_to_tensor(b, dtype=a.dtype, name=(name or op) + "/y")
+    else:
+        b = convert_to_tensor(b)
+        a = convert_to_tensor(a, dtype=b.dtype, name=(name or op) + "/x")
+    return _g().add_node(op, name or op, [a, b], {"T": attr_type(a.dtype)}, [core.bool_], [_bshape(a._shape, b._shape)]).outputs[0]
+
+
+def greater(a, b, name=None): return _compare("Greater", a, b, name)
+def greater_equal(a, b, name=None): return _compare("GreaterEqual", a, b, name)
+def less(a, b, name=None): return _compare("Less", a, b, name)
+def less_equal(a, b, name=None): return _compare("LessEqual", a, b, name)
+def equal(a, b, name=None): return _compare("Equal", a, b, name)
+def not_equal(a, b, name=None): return _compare("NotEqual", a, b, name)
+
+
+def logical_not(x, name=None):
+    x = convert_to_tensor(x)
+    return _g().add_node("LogicalNot", name or "LogicalNot", [x], {}, [core.bool_], [x._shape]).outputs[0]
+
+
+def logical_and(a, b, name=None):
+    a, b = convert_to_tensor(a), convert_to_tensor(b)
+    return _g().add_node("LogicalAnd", name or "LogicalAnd", [a, b], {}, [core.bool_], [_bshape(a._shape, b._shape)]).outputs[0]
+
+
+def where(condition, x=None, y=None, name=None) -> Tensor:
+    """Element-wise select (the three-argument form of ``tf.where``)."""
+    if x is None or y is None:
+        raise NotImplementedError("tf.where(condition) without x / y (index form) is not supported")
+    c = convert_to_tensor(condition)
+    if isinstance(x, (Tensor, Variable)):
+        x = convert_to_tensor(x)
+        y = convert_to_tensor(y, dtype=x.dtype, name=(name or "Select") + "/e")
+    else:
+        y = convert_to_tensor(y)
+        x = convert_to_tensor(x, dtype=y.dtype, name=(name or "Select") + "/t")
+    return _g().add_node("Select", name or "Select", [c, x, y], {"T": attr_type(x.dtype)}, [x.dtype], [_bshape(x._shape, y._shape)]).outputs[0]
+
+
+def clip_by_value(t, clip_value_min, clip_value_max, name=None) -> Tensor:
+    with _g().name_scope(name or "clip_by_value"):
+        return binary("Maximum", binary("Minimum", t, clip_value_max, name="Minimum"), clip_value_min, name="Maximum")
+
+
+def reduce_min(x, axis=None, keepdims=False, name=None, keep_dims=None, reduction_indices=None):
+    return _reduce("Min", x, reduction_indices if axis is None else axis, bool(keep_dims if keep_dims is not None else keepdims), name)
+
+
+def reduce_prod(x, axis=None, keepdims=False, name=None, keep_dims=None, reduction_indices=None):
+    return _reduce("Prod", x, reduction_indices if axis is None else axis, bool(keep_dims if keep_dims is not None else keepdims), name)
+
+
+def l2_loss(t, name=None) -> Tensor:
+    """``sum(t ** 2) / 2`` (real TF has a fused L2Loss op; the composite is what its gradient expands to)."""
+    with _g().name_scope(name or "L2Loss"):
+        return binary("Mul", reduce_sum(square(t, name="Square"), name="Sum"), 0.5, name="mul")
+
+
+def l2_normalize(x, axis=None, epsilon=1e-12, name=None, dim=None) -> Tensor:
+    axis = dim if axis is None else axis
+    with _g().name_scope(name or "l2_normalize"):
+        sq = reduce_sum(square(x, name="Square"), axis=axis, keepdims=True, name="Sum")
+        return binary("Mul", x, rsqrt(binary("Maximum", sq, epsilon, name="Maximum"), name="Rsqrt"), name="mul")
+
+
+def tile(input, multiples, name=None) -> Tensor:  # noqa: A002
+    x = convert_to_tensor(input)
+    m = [int(v) for v in multiples]
+    mt = constant(np.asarray(m, dtype=np.int32), dtype=core.int32, name="Const")
+    oshape = None if x._shape is None else tuple(None if d is None else d * k for d, k in zip(x._shape, m))
+    return _g().add_node("Tile", name or "Tile", [x, mt], {"T": attr_type(x.dtype), "Tmultiples": attr_type(core.int32)}, [x.dtype],
+                         [oshape]).outputs[0]
+
+
+def stack(values, axis=0, name="stack") -> Tensor:
+    vals = [convert_to_tensor(v) for v in values]
+    s0 = vals[0]._shape
+    oshape = None
+    if s0 is not None:
+        ax = axis % (len(s0) + 1)
+        oshape = tuple(list(s0[:ax]) + [len(vals)] + list(s0[ax:]))
+    return _g().add_node("Pack", name or "stack", vals, {"T": attr_type(vals[0].dtype), "N": attr_i(len(vals)), "axis": attr_i(axis)},
+                         [vals[0].dtype], [oshape]).outputs[0]
+
+
+def log_loss(labels, predictions, weights=1.0, epsilon=1e-7, scope=None, loss_collection=GraphKeys.LOSSES, **_unused) -> Tensor:
+    """``-y log(p + eps) - (1 - y) log(1 - p + eps)``, mean over elements (tf.losses.log_loss)."""
+    g = _g()
+    with g.name_scope(scope or "log_loss"):
+        y, p = convert_to_tensor(labels), convert_to_tensor(predictions)
+        pos = binary("Mul", y, log(binary("Add", p, epsilon, name="add"), name="Log"), name="mul")
+        one_minus_y = binary("Sub", constant(1.0, dtype=y.dtype, name="sub/x"), y, name="sub")
+        neg = binary("Mul", one_minus_y, log(binary("Add", binary("Sub", constant(1.0, dtype=p.dtype, name="sub_1/x"), p, name="sub_1"),
+                                                    epsilon, name="add_1"), name="Log_1"), name="mul_1")
+        per = negative(binary("Add", pos, neg, name="add_2"), name="Neg")
+        if not (isinstance(weights, (int, float)) and float(weights) == 1.0):
+            per = binary("Mul", per, weights, name="Mul")
+        return _finish_loss(per, loss_collection)
+
+
+def hinge_loss(labels, logits, weights=1.0, scope=None, loss_collection=GraphKeys.LOSSES, **_unused) -> Tensor:
+    """``max(0, 1 - (2 y - 1) * logits)``, mean over elements (tf.losses.hinge_loss, labels in {0, 1})."""
+    g = _g()
+    with g.name_scope(scope or "hinge_loss"):
+        y, z = convert_to_tensor(labels), convert_to_tensor(logits)
+        signed = binary("Sub", binary("Mul", y, 2.0, name="mul"), 1.0, name="sub")
+        per = relu(binary("Sub", constant(1.0, dtype=z.dtype, name="sub_1/x"), binary("Mul", signed, z, name="mul_1"), name="sub_1"), name="Relu")
+        if not (isinstance(weights, (int, float)) and float(weights) == 1.0):
+            per = binary("Mul", per, weights, name="Mul")
+        return _finish_loss(per, loss_collection)
+
+
+def huber_loss(labels, predictions, weights=1.0, delta=1.0, scope=None, loss_collection=GraphKeys.LOSSES, **_unused) -> Tensor:
+    """Quadratic inside ``|e| <= delta``, linear outside (tf.losses.huber_loss), mean over elements."""
+    g = _g()
+    with g.name_scope(scope or "huber_loss"):
+        err = binary("Sub", convert_to_tensor(predictions), convert_to_tensor(labels), name="Sub")
+        a = abs(err, name="Abs")
+        quad = binary("Minimum", a, delta, name="Minimum")
+        lin = binary("Sub", a, quad, name="Sub_1")
+        per = binary("Add", binary("Mul", binary("Mul", quad, quad, name="Mul"), 0.5, name="Mul_1"), binary("Mul", lin, delta, name="Mul_2"), name="Add")
+        if not (isinstance(weights, (int, float)) and float(weights) == 1.0):
+            per = binary("Mul", per, weights, name="Mul_3")
+        return _finish_loss(per, loss_collection)

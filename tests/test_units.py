@@ -442,3 +442,71 @@ def test_fault_injection_dropped_and_failed_pushes_are_not_fatal():
     tight.fault_hook = lambda k: "raise"
     with pytest.raises(TooManyFailures):
         run_partition(TorchEngine(ir, "x:0", "y:0", LocalTransport(tight)), x, y, iters=5, mini_batch_size=60)
+
+
+# ---------------------------------------------------------------------------------------------
+# wider TF-1.x builder surface (ops beyond what the reference's own examples use)
+# ---------------------------------------------------------------------------------------------
+def _run(fetch_fn, feeds):
+    g = tf.Graph()
+    with g.as_default():
+        phs = {k: tf.placeholder(tf.float32, shape=[None] + list(v.shape[1:]), name=k) for k, v in feeds.items()}
+        out = fetch_fn(**phs)
+        with tf.Session(graph=g) as sess:
+            return sess.run(out, feed_dict={k + ":0": v for k, v in feeds.items()})
+
+
+def test_builder_elementwise_comparison_and_reduction_ops():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((6, 5)).astype(np.float32)
+    b = rng.standard_normal((6, 5)).astype(np.float32)
+    np.testing.assert_allclose(_run(lambda a: tf.nn.relu6(a * 4.0), dict(a=a)), np.clip(a * 4, 0, 6), rtol=1e-6)
+    np.testing.assert_allclose(_run(lambda a: tf.nn.softsign(a), dict(a=a)), a / (1 + np.abs(a)), rtol=1e-6)
+    np.testing.assert_allclose(_run(lambda a: tf.nn.log_softmax(a), dict(a=a)), a - np.log(np.exp(a).sum(1, keepdims=True)), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(_run(lambda a: tf.nn.l2_loss(a), dict(a=a)), (a ** 2).sum() / 2, rtol=1e-5)
+    np.testing.assert_allclose(_run(lambda a: tf.nn.l2_normalize(a, axis=1), dict(a=a)), a / np.sqrt((a ** 2).sum(1, keepdims=True)), rtol=1e-5)
+    np.testing.assert_allclose(_run(lambda a: tf.clip_by_value(a, -0.5, 0.25), dict(a=a)), np.clip(a, -0.5, 0.25))
+    np.testing.assert_allclose(_run(lambda a, b: tf.where(tf.greater(a, b), a, b), dict(a=a, b=b)), np.maximum(a, b))
+    np.testing.assert_allclose(_run(lambda a, b: tf.where(tf.logical_and(tf.less_equal(a, b), tf.not_equal(a, b)), tf.zeros_like(a), tf.ones_like(a)),
+                                    dict(a=a, b=b)), (a >= b).astype(np.float32))
+    np.testing.assert_allclose(_run(lambda a: tf.reduce_min(a, axis=1), dict(a=a)), a.min(1))
+    np.testing.assert_allclose(_run(lambda a: tf.reduce_prod(a, axis=0, keepdims=True), dict(a=a)), a.prod(0, keepdims=True), rtol=1e-5)
+    np.testing.assert_allclose(_run(lambda a: tf.floor(a) + tf.ceil(a) + tf.sign(a), dict(a=a)), np.floor(a) + np.ceil(a) + np.sign(a))
+    np.testing.assert_allclose(_run(lambda a: tf.rsqrt(tf.abs(a) + 1.0) + tf.log1p(tf.abs(a)) + tf.reciprocal(a * a + 1.0), dict(a=a)),
+                               1 / np.sqrt(np.abs(a) + 1) + np.log1p(np.abs(a)) + 1 / (a * a + 1), rtol=1e-5)
+    np.testing.assert_allclose(_run(lambda a: tf.tile(a, [2, 3]), dict(a=a)), np.tile(a, (2, 3)))
+    np.testing.assert_allclose(_run(lambda a, b: tf.stack([a, b], axis=1), dict(a=a, b=b)), np.stack([a, b], 1))
+
+
+def test_builder_extra_losses_match_closed_forms_and_train():
+    rng = np.random.default_rng(1)
+    y = rng.integers(0, 2, (32, 1)).astype(np.float32)
+    p = rng.uniform(0.05, 0.95, (32, 1)).astype(np.float32)
+    z = rng.standard_normal((32, 1)).astype(np.float32)
+    np.testing.assert_allclose(_run(lambda y, p: tf.losses.log_loss(y, p), dict(y=y, p=p)),
+                               np.mean(-y * np.log(p + 1e-7) - (1 - y) * np.log(1 - p + 1e-7)), rtol=1e-5)
+    np.testing.assert_allclose(_run(lambda y, z: tf.losses.hinge_loss(y, z), dict(y=y, z=z)), np.mean(np.maximum(0, 1 - (2 * y - 1) * z)), rtol=1e-5)
+    e = np.abs(z * 2 - y)
+    np.testing.assert_allclose(_run(lambda y, z: tf.losses.huber_loss(y, z * 2.0, delta=0.7), dict(y=y, z=z)),
+                               np.mean(np.where(e <= 0.7, 0.5 * e * e, 0.5 * 0.49 + 0.7 * (e - 0.7))), rtol=1e-5)
+
+    # a graph built from these trains through the public session API (interpreter engine: not a compiled-family graph)
+    def model():
+        x = tf.placeholder(tf.float32, shape=[None, 4], name="x")
+        yy = tf.placeholder(tf.float32, shape=[None, 1], name="y")
+        h = tf.nn.selu(tf.layers.dense(x, 8))
+        out = tf.layers.dense(h, 1, activation=tf.nn.sigmoid, name="outer")
+        return tf.losses.log_loss(yy, out)
+
+    from sparkflow_b200.parallel.session import TrainingSession
+
+    X = rng.standard_normal((128, 4)).astype(np.float32)
+    Y = (X[:, :1] + X[:, 1:2] > 0).astype(np.float32)
+    spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.05))
+    sess = TrainingSession(build_graph(model), "x:0", "y:0", spec, iters=40, mini_batch=32, engine="torch", seed=0).open()
+    prog = GraphProgram(GraphIR.from_metagraph(build_graph(model)))
+    l0 = prog.loss({"x:0": X, "y:0": Y}, sess.weights())
+    sess.train_partitions([(X, Y)])
+    l1 = prog.loss({"x:0": X, "y:0": Y}, sess.weights())
+    sess.close()
+    assert l1 < 0.6 * l0, (l0, l1)
