@@ -91,9 +91,12 @@ def _placeholder_default(n, ins, c):
 
 @op("VariableV2", "Variable", "VarHandleOp")
 def _variable(n, ins, c):
-    if n.name not in c.weights:
-        raise KeyError(f"no value bound for variable '{n.name}'")
-    return (c.weights[n.name],)
+    if n.name in c.weights:
+        return (c.weights[n.name],)
+    # not one of the trained variables (moving statistics, step counters, frozen layers): the engine never runs
+    # update ops on it - exactly like the reference, which only feeds gradients of trainable_variables - so it keeps
+    # the value its initializer produces
+    return (c.p.frozen_variable(n.name),)
 
 
 @op("Identity", "ReadVariableOp", "StopGradient", "PreventGradient", "Snapshot", "CheckNumerics")
@@ -514,6 +517,19 @@ class GraphProgram:
         else:
             self._gen = torch.Generator(device=self.device)
             self._gen.manual_seed(int(seed))
+
+    def frozen_variable(self, name: str) -> torch.Tensor:
+        """Value of a variable that is not in ``trainable_variables``: its initializer, evaluated once and cached."""
+        cache = self.__dict__.setdefault("_frozen", {})
+        if name not in cache:
+            assign = self.ir.nodes.get(f"{name}/Assign")
+            if assign is None or len(assign.inputs) < 2:
+                raise KeyError(f"no value bound for variable '{name}' and it has no initializer")
+            src, idx = assign.inputs[1]
+            with torch.no_grad():
+                val = self.run([f"{src}:{idx}"], {}, {})[0]
+            cache[name] = (val if isinstance(val, torch.Tensor) else torch.as_tensor(np.asarray(val), device=self.device)).detach()
+        return cache[name]
 
     def init_weights(self, seed: Optional[int] = None) -> List[np.ndarray]:
         """Evaluate every trainable variable's initializer sub-graph (``global_variables_initializer``)."""

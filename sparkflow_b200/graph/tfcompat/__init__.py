@@ -78,7 +78,7 @@ nn = _types.SimpleNamespace(
 )
 layers = _types.SimpleNamespace(
     dense=_ops.dense, conv2d=_ops.conv2d_layer, max_pooling2d=_ops.max_pooling2d, average_pooling2d=_ops.average_pooling2d,
-    flatten=_ops.flatten, dropout=_ops.dropout_layer,
+    flatten=_ops.flatten, dropout=_ops.dropout_layer, batch_normalization=_ops.batch_normalization,
 )
 losses = _types.SimpleNamespace(
     softmax_cross_entropy=_ops.softmax_cross_entropy, mean_squared_error=_ops.mean_squared_error,

@@ -884,3 +884,47 @@ def huber_loss(labels, predictions, weights=1.0, delta=1.0, scope=None, loss_col
         if not (isinstance(weights, (int, float)) and float(weights) == 1.0):
             per = binary("Mul", per, weights, name="Mul_3")
         return _finish_loss(per, loss_collection)
+
+
+def batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, center=True, scale=True, beta_initializer=None,
+                        gamma_initializer=None, moving_mean_initializer=None, moving_variance_initializer=None, training=False,
+                        trainable=True, name=None, **_unused) -> Tensor:
+    """``tf.layers.batch_normalization``: variables ``<scope>/gamma, beta`` (trainable) and ``<scope>/moving_mean,
+    moving_variance`` (not trainable).  ``training=True`` normalises with the statistics of the batch, ``False`` with the
+    moving statistics.  As in the reference (which only ever applies gradients of the trainable variables and never runs
+    ``UPDATE_OPS``) the moving statistics keep their initial values."""
+    x = convert_to_tensor(inputs)
+    g = _g()
+    rank = len(x._shape)
+    ax = axis % rank
+    c = x._shape[ax]
+    if c is None:
+        raise ValueError("batch_normalization needs a static size on the normalised axis")
+    if training not in (True, False):
+        raise NotImplementedError("batch_normalization(training=<tensor>) is not supported; pass a Python bool")
+    with g.name_scope(name or "batch_normalization") as scope:
+        sc = scope[:-1]
+        gamma = _make_variable(f"{sc}/gamma", (c,), x.dtype, gamma_initializer or _Ones(), trainable) if scale else None
+        beta = _make_variable(f"{sc}/beta", (c,), x.dtype, beta_initializer or _Zeros(), trainable) if center else None
+        mm = _make_variable(f"{sc}/moving_mean", (c,), x.dtype, moving_mean_initializer or _Zeros(), False)
+        mv = _make_variable(f"{sc}/moving_variance", (c,), x.dtype, moving_variance_initializer or _Ones(), False)
+        red = [i for i in range(rank) if i != ax]
+        bshape = [1] * rank
+        bshape[ax] = c
+
+        def per_channel(t):
+            return t if ax == rank - 1 else reshape(t, bshape)
+
+        if training:
+            mean = reduce_mean(x, axis=red, keepdims=True, name="moments/mean")
+            var = reduce_mean(squared_difference(x, stop_gradient(mean, name="moments/StopGradient"), name="moments/SquaredDifference"),
+                              axis=red, keepdims=True, name="moments/variance")
+        else:
+            mean, var = per_channel(mm.value()), per_channel(mv.value())
+        inv = rsqrt(binary("Add", var, epsilon, name="batchnorm/add"), name="batchnorm/Rsqrt")
+        if gamma is not None:
+            inv = binary("Mul", inv, per_channel(gamma.value()), name="batchnorm/mul")
+        out = binary("Mul", binary("Sub", x, mean, name="batchnorm/sub"), inv, name="batchnorm/mul_1")
+        if beta is not None:
+            out = binary("Add", out, per_channel(beta.value()), name="batchnorm/add_1")
+        return out

@@ -510,3 +510,45 @@ def test_builder_extra_losses_match_closed_forms_and_train():
     l1 = prog.loss({"x:0": X, "y:0": Y}, sess.weights())
     sess.close()
     assert l1 < 0.6 * l0, (l0, l1)
+
+
+def test_batch_normalization_layer_and_frozen_variables():
+    """tf.layers.batch_normalization: batch statistics when training, frozen moving statistics otherwise; the moving
+    statistics are variables outside trainable_variables and keep their initial values (no update ops, as in the reference)"""
+    rng = np.random.default_rng(2)
+    X = (rng.standard_normal((64, 6)) * 3 + 1).astype(np.float32)
+
+    def model(training):
+        def fn():
+            x = tf.placeholder(tf.float32, shape=[None, 6], name="x")
+            y = tf.placeholder(tf.float32, shape=[None, 1], name="y")
+            h = tf.layers.batch_normalization(x, training=training, name="bn")
+            tf.identity(h, name="normed")
+            out = tf.layers.dense(h, 1, name="outer")
+            return tf.losses.mean_squared_error(y, out)
+        return build_graph(fn)
+
+    ir = GraphIR.from_metagraph(model(True))
+    assert [v.name for v in ir.trainable] == ["bn/gamma", "bn/beta", "outer/kernel", "outer/bias"]
+    assert {v.name for v in ir.variables} >= {"bn/moving_mean", "bn/moving_variance"}
+    prog = GraphProgram(ir)
+    w = prog.init_weights(seed=0)
+    normed = prog.run(["normed:0"], {"x:0": X}, prog.bind(w))[0].numpy()
+    ref = (X - X.mean(0)) / np.sqrt(X.var(0) + 1e-3)
+    np.testing.assert_allclose(normed, ref, rtol=1e-4, atol=1e-4)
+    # inference form: moving_mean = 0, moving_variance = 1 -> x / sqrt(1 + eps)
+    prog_inf = GraphProgram(GraphIR.from_metagraph(model(False)))
+    normed_inf = prog_inf.run(["normed:0"], {"x:0": X}, prog_inf.bind(prog_inf.init_weights(seed=0)))[0].numpy()
+    np.testing.assert_allclose(normed_inf, X / np.sqrt(1 + 1e-3), rtol=1e-5)
+    # gradients reach gamma / beta and the graph trains through the public session API
+    Y = (X[:, :1] * 0.3 - X[:, 2:3] * 0.2).astype(np.float32)
+    loss, grads = prog.loss_and_grads({"x:0": X, "y:0": Y}, w)
+    assert all(float(g.abs().sum()) > 0 for g in grads)
+    from sparkflow_b200.parallel.session import TrainingSession
+
+    sess = TrainingSession(model(True), "x:0", "y:0", OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.05)), iters=60, mini_batch=32,
+                           engine="torch", seed=0).open()
+    sess.train_partitions([(X, Y)])
+    l1 = prog.loss({"x:0": X, "y:0": Y}, sess.weights())
+    sess.close()
+    assert l1 < 0.3 * loss, (loss, l1)
