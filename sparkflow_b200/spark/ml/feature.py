@@ -8,7 +8,7 @@ import numpy as np
 
 from ..context import keyword_only
 from ..sql import DataFrame, Row
-from .base import DefaultParamsPersistence, Transformer, java_class
+from .base import DefaultParamsPersistence, Estimator, Model, Transformer, java_class
 from .linalg import DenseVector, SparseVector, Vector, Vectors
 from .param import HasInputCol, HasInputCols, HasOutputCol, Param, Params, TypeConverters
 
@@ -140,3 +140,213 @@ class StopWordsRemover(Transformer, HasInputCol, HasOutputCol, DefaultParamsPers
         cs = self.getOrDefault(self.caseSensitive)
         stop = set(self.getStopWords() if cs else [w.lower() for w in self.getStopWords()])
         return _append_column(dataset, out, lambda r: [w for w in r[i] if (w if cs else w.lower()) not in stop])
+
+
+# -------------------------------------------------------------------------------------------------
+# Common pre-processing stages seen next to SparkAsyncDL in user pipelines.  Fitted state (labels, statistics) is kept in
+# Params so the metadata-only persistence of this shim round-trips it (real Spark writes a parquet `data/` directory).
+# -------------------------------------------------------------------------------------------------
+def _as_array(v) -> np.ndarray:
+    return np.asarray(v.toArray() if isinstance(v, Vector) else v, dtype=np.float64).reshape(-1)
+
+
+@java_class("org.apache.spark.ml.feature.Binarizer")
+class Binarizer(Transformer, HasInputCol, HasOutputCol, DefaultParamsPersistence):
+    threshold = Param(Params._dummy(), "threshold", "features greater than the threshold become 1.0, the others 0.0",
+                      typeConverter=TypeConverters.toFloat)
+
+    @keyword_only
+    def __init__(self, threshold=0.0, inputCol=None, outputCol=None):
+        super().__init__()
+        self._setDefault(threshold=0.0)
+        self.setParams(**self._input_kwargs)
+
+    @keyword_only
+    def setParams(self, threshold=0.0, inputCol=None, outputCol=None):
+        return self._set(**self._input_kwargs)
+
+    def _transform(self, dataset: DataFrame) -> DataFrame:
+        i, thr = dataset.columns.index(self.getInputCol()), float(self.getOrDefault(self.threshold))
+
+        def build(r):
+            v = r[i]
+            if isinstance(v, Vector) or isinstance(v, (list, tuple, np.ndarray)):
+                return DenseVector((_as_array(v) > thr).astype(np.float64))
+            return 1.0 if float(v) > thr else 0.0
+
+        return _append_column(dataset, self.getOutputCol(), build)
+
+
+@java_class("org.apache.spark.ml.feature.StringIndexerModel")
+class StringIndexerModel(Model, HasInputCol, HasOutputCol, DefaultParamsPersistence):
+    labels = Param(Params._dummy(), "labels", "ordered list of labels, index = position", typeConverter=TypeConverters.toListString)
+    handleInvalid = Param(Params._dummy(), "handleInvalid", "error | skip | keep", typeConverter=TypeConverters.toString)
+
+    @keyword_only
+    def __init__(self, inputCol=None, outputCol=None, labels=None, handleInvalid="error"):
+        super().__init__()
+        self._setDefault(labels=[], handleInvalid="error")
+        self._set(**self._input_kwargs)
+
+    def _transform(self, dataset: DataFrame) -> DataFrame:
+        i = dataset.columns.index(self.getInputCol())
+        labels = list(self.getOrDefault(self.labels))
+        index = {l: float(k) for k, l in enumerate(labels)}
+        invalid = self.getOrDefault(self.handleInvalid)
+        if invalid == "skip":
+            dataset = DataFrame([[r for r in p if str(r[i]) in index] for p in dataset._parts], dataset.columns, dataset.ctx)
+
+        def build(r):
+            key = str(r[i])
+            if key in index:
+                return index[key]
+            if invalid == "keep":
+                return float(len(labels))
+            raise ValueError(f"Unseen label: {key}")
+
+        return _append_column(dataset, self.getOutputCol(), build)
+
+
+@java_class("org.apache.spark.ml.feature.StringIndexer")
+class StringIndexer(Estimator, HasInputCol, HasOutputCol, DefaultParamsPersistence):
+    """Most frequent label -> 0.0 (ties broken alphabetically, Spark's ``frequencyDesc``)."""
+    handleInvalid = Param(Params._dummy(), "handleInvalid", "error | skip | keep", typeConverter=TypeConverters.toString)
+    stringOrderType = Param(Params._dummy(), "stringOrderType", "frequencyDesc | frequencyAsc | alphabetDesc | alphabetAsc",
+                            typeConverter=TypeConverters.toString)
+
+    @keyword_only
+    def __init__(self, inputCol=None, outputCol=None, handleInvalid="error", stringOrderType="frequencyDesc"):
+        super().__init__()
+        self._setDefault(handleInvalid="error", stringOrderType="frequencyDesc")
+        self.setParams(**self._input_kwargs)
+
+    @keyword_only
+    def setParams(self, inputCol=None, outputCol=None, handleInvalid="error", stringOrderType="frequencyDesc"):
+        return self._set(**self._input_kwargs)
+
+    def _fit(self, dataset: DataFrame) -> StringIndexerModel:
+        i = dataset.columns.index(self.getInputCol())
+        counts: dict = {}
+        for p in dataset._parts:
+            for r in p:
+                counts[str(r[i])] = counts.get(str(r[i]), 0) + 1
+        order = self.getOrDefault(self.stringOrderType)
+        if order == "frequencyDesc":
+            labels = sorted(counts, key=lambda l: (-counts[l], l))
+        elif order == "frequencyAsc":
+            labels = sorted(counts, key=lambda l: (counts[l], l))
+        elif order == "alphabetDesc":
+            labels = sorted(counts, reverse=True)
+        else:
+            labels = sorted(counts)
+        m = StringIndexerModel(inputCol=self.getInputCol(), outputCol=self.getOutputCol(), labels=labels,
+                               handleInvalid=self.getOrDefault(self.handleInvalid))
+        return m
+
+
+class _ScalerModelBase(Model, HasInputCol, HasOutputCol, DefaultParamsPersistence):
+    def _stats(self, name):
+        return np.asarray(self.getOrDefault(getattr(self, name)), dtype=np.float64)
+
+
+@java_class("org.apache.spark.ml.feature.StandardScalerModel")
+class StandardScalerModel(_ScalerModelBase):
+    mean = Param(Params._dummy(), "mean", "per-feature mean", typeConverter=TypeConverters.toListFloat)
+    std = Param(Params._dummy(), "std", "per-feature (unbiased) standard deviation", typeConverter=TypeConverters.toListFloat)
+    withMean = Param(Params._dummy(), "withMean", "center with the mean", typeConverter=TypeConverters.toBoolean)
+    withStd = Param(Params._dummy(), "withStd", "scale to unit standard deviation", typeConverter=TypeConverters.toBoolean)
+
+    @keyword_only
+    def __init__(self, inputCol=None, outputCol=None, mean=None, std=None, withMean=False, withStd=True):
+        super().__init__()
+        self._setDefault(mean=[], std=[], withMean=False, withStd=True)
+        self._set(**self._input_kwargs)
+
+    def _transform(self, dataset: DataFrame) -> DataFrame:
+        i = dataset.columns.index(self.getInputCol())
+        mean, std = self._stats("mean"), self._stats("std")
+        wm, ws = self.getOrDefault(self.withMean), self.getOrDefault(self.withStd)
+        inv = np.where(std > 0, 1.0 / np.where(std > 0, std, 1.0), 0.0)
+
+        def build(r):
+            v = _as_array(r[i])
+            if wm:
+                v = v - mean
+            if ws:
+                v = v * inv
+            return DenseVector(v)
+
+        return _append_column(dataset, self.getOutputCol(), build)
+
+
+@java_class("org.apache.spark.ml.feature.StandardScaler")
+class StandardScaler(Estimator, HasInputCol, HasOutputCol, DefaultParamsPersistence):
+    withMean = Param(Params._dummy(), "withMean", "center with the mean", typeConverter=TypeConverters.toBoolean)
+    withStd = Param(Params._dummy(), "withStd", "scale to unit standard deviation", typeConverter=TypeConverters.toBoolean)
+
+    @keyword_only
+    def __init__(self, withMean=False, withStd=True, inputCol=None, outputCol=None):
+        super().__init__()
+        self._setDefault(withMean=False, withStd=True)
+        self.setParams(**self._input_kwargs)
+
+    @keyword_only
+    def setParams(self, withMean=False, withStd=True, inputCol=None, outputCol=None):
+        return self._set(**self._input_kwargs)
+
+    def _fit(self, dataset: DataFrame) -> StandardScalerModel:
+        i = dataset.columns.index(self.getInputCol())
+        X = np.stack([_as_array(r[i]) for p in dataset._parts for r in p])
+        std = X.std(axis=0, ddof=1) if X.shape[0] > 1 else np.zeros(X.shape[1])
+        return StandardScalerModel(inputCol=self.getInputCol(), outputCol=self.getOutputCol(), mean=[float(v) for v in X.mean(axis=0)],
+                                   std=[float(v) for v in std], withMean=self.getOrDefault(self.withMean), withStd=self.getOrDefault(self.withStd))
+
+
+@java_class("org.apache.spark.ml.feature.MinMaxScalerModel")
+class MinMaxScalerModel(_ScalerModelBase):
+    originalMin = Param(Params._dummy(), "originalMin", "per-feature minimum seen in fit", typeConverter=TypeConverters.toListFloat)
+    originalMax = Param(Params._dummy(), "originalMax", "per-feature maximum seen in fit", typeConverter=TypeConverters.toListFloat)
+    min = Param(Params._dummy(), "min", "lower bound after transformation", typeConverter=TypeConverters.toFloat)  # noqa: A003
+    max = Param(Params._dummy(), "max", "upper bound after transformation", typeConverter=TypeConverters.toFloat)  # noqa: A003
+
+    @keyword_only
+    def __init__(self, inputCol=None, outputCol=None, originalMin=None, originalMax=None, min=0.0, max=1.0):  # noqa: A002
+        super().__init__()
+        self._setDefault(originalMin=[], originalMax=[], min=0.0, max=1.0)
+        self._set(**self._input_kwargs)
+
+    def _transform(self, dataset: DataFrame) -> DataFrame:
+        i = dataset.columns.index(self.getInputCol())
+        lo, hi = self._stats("originalMin"), self._stats("originalMax")
+        a, b = float(self.getOrDefault(self.min)), float(self.getOrDefault(self.max))
+        span = hi - lo
+
+        def build(r):
+            v = _as_array(r[i])
+            unit = np.where(span > 0, (v - lo) / np.where(span > 0, span, 1.0), 0.5)      # constant features map to the middle (Spark)
+            return DenseVector(unit * (b - a) + a)
+
+        return _append_column(dataset, self.getOutputCol(), build)
+
+
+@java_class("org.apache.spark.ml.feature.MinMaxScaler")
+class MinMaxScaler(Estimator, HasInputCol, HasOutputCol, DefaultParamsPersistence):
+    min = Param(Params._dummy(), "min", "lower bound after transformation", typeConverter=TypeConverters.toFloat)  # noqa: A003
+    max = Param(Params._dummy(), "max", "upper bound after transformation", typeConverter=TypeConverters.toFloat)  # noqa: A003
+
+    @keyword_only
+    def __init__(self, min=0.0, max=1.0, inputCol=None, outputCol=None):  # noqa: A002
+        super().__init__()
+        self._setDefault(min=0.0, max=1.0)
+        self.setParams(**self._input_kwargs)
+
+    @keyword_only
+    def setParams(self, min=0.0, max=1.0, inputCol=None, outputCol=None):  # noqa: A002
+        return self._set(**self._input_kwargs)
+
+    def _fit(self, dataset: DataFrame) -> MinMaxScalerModel:
+        i = dataset.columns.index(self.getInputCol())
+        X = np.stack([_as_array(r[i]) for p in dataset._parts for r in p])
+        return MinMaxScalerModel(inputCol=self.getInputCol(), outputCol=self.getOutputCol(), originalMin=[float(v) for v in X.min(axis=0)],
+                                 originalMax=[float(v) for v in X.max(axis=0)], min=float(self.getOrDefault(self.min)),
+                                 max=float(self.getOrDefault(self.max)))

@@ -552,3 +552,49 @@ def test_batch_normalization_layer_and_frozen_variables():
     l1 = prog.loss({"x:0": X, "y:0": Y}, sess.weights())
     sess.close()
     assert l1 < 0.3 * loss, (loss, l1)
+
+
+def test_shim_feature_stages_and_evaluators(tmp_path):
+    """StringIndexer / StandardScaler / MinMaxScaler / Binarizer and the regression / binary evaluators of the pyspark shim"""
+    from sklearn.metrics import average_precision_score, roc_auc_score
+
+    from sparkflow_b200.spark import SparkSession
+    from sparkflow_b200.spark.ml.base import Pipeline, PipelineModel
+    from sparkflow_b200.spark.ml.evaluation import BinaryClassificationEvaluator, RegressionEvaluator
+    from sparkflow_b200.spark.ml.feature import Binarizer, MinMaxScaler, StandardScaler, StringIndexer
+    from sparkflow_b200.spark.ml.linalg import Vectors
+
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((40, 3)) * [1.0, 5.0, 0.0] + [0.0, 2.0, 7.0]
+    cats = rng.choice(["b", "a", "c"], 40, p=[0.5, 0.3, 0.2])
+    spark = SparkSession.builder.master("local[2]").getOrCreate()
+    df = spark.createDataFrame([(str(c), Vectors.dense(x), float(x[0] > 0), float(x[0] + 0.1 * x[1])) for c, x in zip(cats, X)],
+                               ["cat", "features", "label", "score"])
+    pipe = Pipeline(stages=[StringIndexer(inputCol="cat", outputCol="cat_idx"),
+                            StandardScaler(inputCol="features", outputCol="std", withMean=True),
+                            MinMaxScaler(inputCol="features", outputCol="mm"),
+                            Binarizer(threshold=0.0, inputCol="score", outputCol="score_bin")])
+    model = pipe.fit(df)
+    model.write().overwrite().save(str(tmp_path / "prep"))
+    model = PipelineModel.load(str(tmp_path / "prep"))
+    out = model.transform(df).collect()
+    counts = {c: int((cats == c).sum()) for c in "abc"}
+    order = sorted(counts, key=lambda l: (-counts[l], l))
+    assert [r["cat_idx"] for r in out] == [float(order.index(c)) for c in cats]
+    std = np.stack([r["std"].toArray() for r in out])
+    np.testing.assert_allclose(std[:, :2].mean(0), 0, atol=1e-9)
+    np.testing.assert_allclose(std[:, :2].std(0, ddof=1), 1, rtol=1e-9)
+    assert np.all(std[:, 2] == 0)                                   # constant feature
+    mm = np.stack([r["mm"].toArray() for r in out])
+    assert mm[:, :2].min() == 0.0 and mm[:, :2].max() == 1.0 and np.all(mm[:, 2] == 0.5)
+    assert [r["score_bin"] for r in out] == [1.0 if r["score"] > 0 else 0.0 for r in out]
+    y = np.asarray([r["label"] for r in out])
+    s = np.asarray([r["score"] for r in out])
+    ev = BinaryClassificationEvaluator(rawPredictionCol="score", labelCol="label")
+    assert abs(ev.evaluate(model.transform(df)) - roc_auc_score(y, s)) < 1e-9
+    assert abs(BinaryClassificationEvaluator(rawPredictionCol="score", labelCol="label", metricName="areaUnderPR").evaluate(model.transform(df))
+               - average_precision_score(y, s)) < 0.05           # trapezoid vs step interpolation
+    reg = RegressionEvaluator(predictionCol="score", labelCol="label")
+    assert abs(reg.evaluate(model.transform(df)) - np.sqrt(np.mean((y - s) ** 2))) < 1e-12
+    assert RegressionEvaluator(predictionCol="score", labelCol="label", metricName="r2").isLargerBetter()
+    spark.stop()
