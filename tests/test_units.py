@@ -598,3 +598,82 @@ def test_shim_feature_stages_and_evaluators(tmp_path):
     assert abs(reg.evaluate(model.transform(df)) - np.sqrt(np.mean((y - s) ** 2))) < 1e-12
     assert RegressionEvaluator(predictionCol="score", labelCol="label", metricName="r2").isLargerBetter()
     spark.stop()
+
+
+def test_double_buffered_publish_protocol_model():
+    """Executable model of the served-push publish protocol (csrc/sf_api.h: SF_CTRL_PUB; applier_kernel / pull_kernel):
+    one word = [bit 31: current buffer | low bits: pulls in flight].  A pull registers with ONE fetch-add (which also names
+    the complete buffer), copies it, deregisters; the writer waits for an instant with no pull in flight, overwrites the
+    OTHER buffer, then flips bit 31.  Readers must never observe a torn version and must observe monotone versions."""
+    import random
+
+    class Word:
+        def __init__(self):
+            self.v, self.lock = 0, threading.Lock()
+
+        def fetch_add(self, d):
+            with self.lock:
+                old = self.v
+                self.v = (self.v + d) & 0xFFFFFFFF
+                return old
+
+        def fetch_xor(self, m):
+            with self.lock:
+                old = self.v
+                self.v ^= m
+                return old
+
+        def load(self):
+            with self.lock:
+                return self.v
+
+    pub = Word()
+    bufs = [np.zeros(64, dtype=np.int64), np.zeros(64, dtype=np.int64)]
+    stop = threading.Event()
+    errors, seen_max = [], [0] * 4
+    passes = [0]
+
+    def writer():
+        rng = random.Random(0)
+        version = 0
+        while not stop.is_set():
+            while pub.load() & 0xFFFF:                  # one instant without a pull in flight since the last flip
+                time.sleep(0)
+            b = (pub.load() >> 31) ^ 1
+            version += 1
+            for i in range(0, 64, 8):                   # a deliberately slow, interruptible overwrite of the stale buffer
+                bufs[b][i:i + 8] = version
+                if rng.random() < 0.3:
+                    time.sleep(0)
+            pub.fetch_xor(0x80000000)                   # publish
+            passes[0] = version
+
+    def reader(k):
+        rng = random.Random(100 + k)
+        last = 0
+        while not stop.is_set():
+            cur = pub.fetch_add(1) >> 31                # register + learn the complete buffer
+            snap = np.empty(64, dtype=np.int64)
+            for i in range(0, 64, 16):
+                snap[i:i + 16] = bufs[cur][i:i + 16]
+                if rng.random() < 0.3:
+                    time.sleep(0)
+            pub.fetch_add(-1)                           # deregister
+            if snap.min() != snap.max():
+                errors.append(("torn", k, snap.min(), snap.max()))
+            if snap[0] < last:
+                errors.append(("went back", k, last, snap[0]))
+            last = int(snap[0])
+            seen_max[k] = last
+            time.sleep(0.002 * rng.random())            # the worker's forward / backward between two pulls
+
+    ts = [threading.Thread(target=writer)] + [threading.Thread(target=reader, args=(k,)) for k in range(4)]
+    for t in ts:
+        t.start()
+    time.sleep(1.0)
+    stop.set()
+    for t in ts:
+        t.join(5)
+    assert not errors, errors[:3]
+    assert passes[0] > 20 and min(seen_max) > 5, (passes, seen_max)      # neither side starved (pulls are a small duty cycle)
+    assert pub.load() & 0xFFFF == 0
