@@ -11,7 +11,7 @@ import os
 
 from .graph import pbwire
 from .graph.ir import GraphIR
-from .io.bundle import read_bundle, read_checkpoint_state
+from .io.bundle import read_bundle, read_checkpoint_state, write_bundle, write_checkpoint_state
 from .spark.ml.base import PipelineModel
 from .tensorflow_async import SparkAsyncDLModel
 
@@ -36,3 +36,25 @@ def attach_tensorflow_model_to_pipeline(path, pipelineModel, inputCol, tfInput, 
                                         tfDropout=None, toKeepDropout=False):
     spark_model = load_tensorflow_model(path, inputCol, tfInput, tfOutput, predictionCol, tfDropout, toKeepDropout)
     return PipelineModel(stages=[pipelineModel, spark_model])
+
+
+def save_tensorflow_model(model, path) -> str:
+    """The inverse of :func:`load_tensorflow_model` (an extension - the reference can only import): write a fitted
+    ``SparkAsyncDLModel`` as a TensorFlow V2 checkpoint that TF-1.x ``Saver.restore`` / ``import_meta_graph`` reads -
+    ``<path>.meta`` (binary MetaGraphDef), ``<path>.index`` + ``<path>.data-00000-of-00001`` (one fp32 tensor per
+    trainable variable, under its variable name) and the ``checkpoint`` state file next to them.  Returns ``path``."""
+    import numpy as np
+
+    graph = model.getOrDefault(model.modelJson)
+    meta = json.loads(graph) if isinstance(graph, str) else graph
+    weights = json.loads(model.getOrDefault(model.modelWeights))
+    ir = GraphIR.from_metagraph(meta)
+    if len(weights) != len(ir.trainable):
+        raise ValueError(f"the model carries {len(weights)} weight arrays for {len(ir.trainable)} trainable variables")
+    tensors = {v.name: np.asarray(w, dtype=np.float32).reshape(v.shape) for v, w in zip(ir.trainable, weights)}
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    write_bundle(path, tensors)
+    with open(path + ".meta", "wb") as fh:
+        fh.write(pbwire.encode("MetaGraphDef", meta))
+    write_checkpoint_state(os.path.dirname(os.path.abspath(path)), os.path.basename(path))
+    return path

@@ -677,3 +677,25 @@ def test_double_buffered_publish_protocol_model():
     assert not errors, errors[:3]
     assert passes[0] > 20 and min(seen_max) > 5, (passes, seen_max)      # neither side starved (pulls are a small duty cycle)
     assert pub.load() & 0xFFFF == 0
+
+
+def test_save_tensorflow_model_roundtrip(tmp_path):
+    """extension: a fitted SparkAsyncDLModel goes out as a TF V2 checkpoint and comes back through load_tensorflow_model"""
+    from sparkflow_b200.ml_util import run_inference
+    from sparkflow_b200.tensorflow_async import SparkAsyncDLModel
+    from sparkflow_b200.tensorflow_model_loader import load_tensorflow_model, save_tensorflow_model
+
+    graph = zoo.build("test_mlp")
+    prog = GraphProgram(GraphIR.from_metagraph(graph))
+    w = prog.init_weights(seed=7)
+    m = SparkAsyncDLModel(inputCol="features", modelJson=graph, modelWeights=json.dumps([a.tolist() for a in w]), tfInput="x:0",
+                          tfOutput="outer/Sigmoid:0", predictionCol="predicted")
+    prefix = save_tensorflow_model(m, str(tmp_path / "export" / "model"))
+    assert sorted(os.listdir(tmp_path / "export")) == ["checkpoint", "model.data-00000-of-00001", "model.index", "model.meta"]
+    back = load_tensorflow_model(prefix, inputCol="features", tfInput="x:0", tfOutput="outer/Sigmoid:0")
+    w2 = [np.asarray(a, np.float32) for a in json.loads(back.getOrDefault(back.modelWeights))]
+    for a, b in zip(w, w2):
+        np.testing.assert_array_equal(a, b)
+    x = np.random.default_rng(0).random((5, 10), dtype=np.float32)
+    np.testing.assert_allclose(run_inference(back.getOrDefault(back.modelJson), w2, x, "x:0", "outer/Sigmoid:0"),
+                               run_inference(graph, w, x, "x:0", "outer/Sigmoid:0"), rtol=1e-6)
