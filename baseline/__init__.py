@@ -1,0 +1,1 @@
+"""baseline package of sparkflow_b200."""

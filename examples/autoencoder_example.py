@@ -1,43 +1,44 @@
-"""784-256-128-256-784 auto-encoder trained unsupervised (tfLabel=None), counterpart of
-examples/autoencoder_example.py: the model's ``out/Sigmoid:0`` bottleneck is the prediction."""
-import os
-import sys
+"""Unsupervised auto-encoder 784-256-128-256-784 on L1-normalised MNIST rows (tfLabel=None: the input is the target);
+the 128-wide sigmoid bottleneck (`out/Sigmoid:0`) is what transform() writes into the prediction column.
+Same workload as the reference's autoencoder example.
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from sparkflow_b200 import compat
-
-compat.install()
+    python examples/autoencoder_example.py [--rows N] [--iters K]
+"""
+from _common import Stopwatch, mnist_frame, parse_args, pixel_columns
 
 import tensorflow as tf
 from pyspark.ml.feature import Normalizer, VectorAssembler
-from pyspark.sql import SparkSession
-from pyspark.sql.functions import rand
 from sparkflow.graph_utils import build_graph
 from sparkflow.tensorflow_async import SparkAsyncDL
 
-from _data import mnist_csv
+BATCH = 256
+# (units, activation, layer name); the layer called "out" is the code the fitted model emits
+ENCODER = ((256, "relu", None), (128, "sigmoid", "out"))
+DECODER = ((256, "relu", None), (784, "sigmoid", None))
 
 
-def small_model():
-    x = tf.placeholder("float", shape=[None, 784], name="x")
-    layer1 = tf.layers.dense(x, 256, activation=tf.nn.relu)
-    layer2 = tf.layers.dense(layer1, 128, activation=tf.nn.sigmoid, name="out")
-    layer3 = tf.layers.dense(layer2, 256, activation=tf.nn.relu)
-    layer4 = tf.layers.dense(layer3, 784, activation=tf.nn.sigmoid)
-    return tf.losses.mean_squared_error(layer4, x)
+def autoencoder():
+    pixels = tf.placeholder("float", shape=[None, 784], name="x")
+    h = pixels
+    for units, act, name in ENCODER + DECODER:
+        h = tf.layers.dense(h, units, activation=getattr(tf.nn, act), name=name)
+    return tf.losses.mean_squared_error(h, pixels)
+
+
+def main():
+    args = parse_args(__doc__.splitlines()[0], iters=10)
+    spark, frame = mnist_frame(args)
+    assembled = VectorAssembler(inputCols=pixel_columns(frame), outputCol="raw").transform(frame).select(["raw"])
+    rows = Normalizer(inputCol="raw", outputCol="features", p=1.0).transform(assembled).select(["features"])
+    estimator = SparkAsyncDL(inputCol="features", predictionCol="predicted", tensorflowGraph=build_graph(autoencoder), tfInput="x:0",
+                             tfLabel=None, tfOutput="out/Sigmoid:0", tfOptimizer="adam", tfLearningRate=0.001, iters=args.iters,
+                             partitions=args.partitions, miniBatchSize=BATCH, verbose=0 if args.quiet else 1)
+    with Stopwatch("autoencoder", rows.count(), args.iters, BATCH):
+        model = estimator.fit(rows)
+    code = model.transform(rows).take(1)[0]["predicted"]
+    print("bottleneck code of the first row:", code)
+    spark.stop()
 
 
 if __name__ == "__main__":
-    rows = int(sys.argv[sys.argv.index("--rows") + 1]) if "--rows" in sys.argv else None
-    spark = SparkSession.builder.appName("examples").master("local[4]").config("spark.driver.memory", "2g").getOrCreate()
-    df = spark.read.option("inferSchema", "true").csv(mnist_csv()).orderBy(rand(seed=1))
-    if rows:
-        df = df.limit(rows).repartition(4)
-    mg = build_graph(small_model)
-    va = VectorAssembler(inputCols=df.columns[1:785], outputCol="feats").transform(df).select(["feats"])
-    na = Normalizer(inputCol="feats", outputCol="features", p=1.0).transform(va).select(["features"])
-    spark_model = SparkAsyncDL(inputCol="features", tensorflowGraph=mg, tfInput="x:0", tfLabel=None, tfOutput="out/Sigmoid:0",
-                               tfOptimizer="adam", tfLearningRate=.001, iters=10, predictionCol="predicted", partitions=4,
-                               miniBatchSize=256, verbose=1).fit(na)
-    t = spark_model.transform(na).take(1)
-    print(t[0]["predicted"])
+    main()

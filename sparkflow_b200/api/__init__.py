@@ -1,0 +1,1 @@
+"""api package of sparkflow_b200."""

@@ -1,0 +1,1 @@
+"""io package of sparkflow_b200."""

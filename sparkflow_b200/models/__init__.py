@@ -1,0 +1,1 @@
+"""models package of sparkflow_b200."""

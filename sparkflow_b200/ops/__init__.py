@@ -1,0 +1,1 @@
+"""ops package of sparkflow_b200."""

@@ -1,0 +1,1 @@
+"""parallel package of sparkflow_b200."""

@@ -1,0 +1,1 @@
+"""utils package of sparkflow_b200."""
