@@ -434,7 +434,15 @@ def _pool(kind):
         if n.attrs.get("padding", "VALID") == "SAME":
             ph, pw = _same_pad(xt.shape[2], ks[1], st[1]), _same_pad(xt.shape[3], ks[2], st[2])
             xt = F.pad(xt, (pw[0], pw[1], ph[0], ph[1]), value=float("-inf") if kind == "max" else 0.0)
-        y = F.max_pool2d(xt, (ks[1], ks[2]), (st[1], st[2])) if kind == "max" else F.avg_pool2d(xt, (ks[1], ks[2]), (st[1], st[2]))
+        if kind == "max":
+            y = F.max_pool2d(xt, (ks[1], ks[2]), (st[1], st[2]))
+        else:
+            y = F.avg_pool2d(xt, (ks[1], ks[2]), (st[1], st[2]))
+            if n.attrs.get("padding", "VALID") == "SAME":
+                # TF excludes the padded cells from the divisor: rescale by window / (number of real cells in the window)
+                ones = F.pad(torch.ones_like(x.permute(0, 3, 1, 2)[:1, :1]), (pw[0], pw[1], ph[0], ph[1]))
+                frac = F.avg_pool2d(ones, (ks[1], ks[2]), (st[1], st[2]))
+                y = y / frac
         return (y.permute(0, 2, 3, 1),)
     return run
 

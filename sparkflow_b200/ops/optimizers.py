@@ -50,6 +50,7 @@ NUM_SLOTS = {
 SLOT_NAMES = {
     "momentum": ["Momentum"],
     "adam": ["Adam", "Adam_1"],
+    # internal slot order is (rms, momentum, mg); TF creates rms, [mg when centered], momentum - see slot_names()
     "rmsprop": ["RMSProp", "RMSProp_1", "RMSProp_2"],
     "adagrad": ["Adagrad"],
     "adadelta": ["Adadelta", "Adadelta_1"],
@@ -116,6 +117,14 @@ class OptimizerSpec:
         if self.name == "adagrad_da" and slot == 1:
             return float(self.hyper.get("init_accum", 0.1))
         return 0.0
+
+    def slot_names(self) -> List[str]:
+        """TF checkpoint names of the slots, in this package's internal slot order.  Centered RMSProp creates
+        ``rms, mg, momentum`` (so momentum is ``RMSProp_2``); the internal order is ``rms, momentum, mg``."""
+        names = list(SLOT_NAMES.get(self.name, []))
+        if self.name == "rmsprop" and self.hyper.get("centered", 0):
+            return ["RMSProp", "RMSProp_2", "RMSProp_1"]
+        return names
 
     def native_hyper(self) -> Dict[str, Any]:
         h = dict(self.hyper)

@@ -63,12 +63,16 @@ class ParameterServer:
                 return self.p.clone().contiguous()
         return self.p.clone().contiguous()
 
+    def _bump(self, field: str) -> None:
+        with self._count_lock:
+            setattr(self, field, getattr(self, field) + 1)
+
     def update_parameters(self, grad_flat: torch.Tensor) -> str:
         with self._count_lock:
             idx = next(self._counter)
         action = self.fault_hook(idx) if self.fault_hook else None
         if action == "drop":
-            self.dropped += 1
+            self._bump("dropped")
             return "dropped"
         if action and action.startswith("delay:"):
             time.sleep(float(action.split(":", 1)[1]))
@@ -83,24 +87,33 @@ class ParameterServer:
             else:
                 self._apply(grad_flat)
         except Exception:
-            self.errors += 1
+            self._bump("errors")
             if self.errors >= self.max_errors:
                 raise TooManyFailures("Too many failures during training")
             return "failed"
         return "completed"
 
+    HOGWILD_CHUNK = 8192      # elements per read-modify-write of a Hogwild push
+
     def _apply(self, g: torch.Tensor) -> None:
-        self.pushes += 1
+        # the optimizer step number comes from an atomic counter: two racing pushes never share a bias-correction step
+        with self._count_lock:
+            self.pushes += 1
+            step = self.pushes
         if self.lock is not None:
-            apply_update(self.spec, self.p, g, self.slots, self.pushes)
+            apply_update(self.spec, self.p, g, self.slots, step)
             return
-        # Hogwild: like TF's fused Apply* kernels (and the GPU push kernel) every element's (p, slots) tuple is
-        # read once, updated together in private storage and written back.  Concurrent pushes may lose each
-        # other's updates - that is the algorithm - but no thread ever combines its momentum with another
-        # thread's half-written second moment (which divides by ~0 and blows the model up).
-        local = self.state.clone()
-        apply_update(self.spec, local[:, 0], g, [local[:, 1 + i] for i in range(self.spec.num_slots)], self.pushes)
-        self.state.copy_(local)
+        # Hogwild: like TF's in-place Apply* kernels (use_locking=False) and the GPU push kernel, pushes race PER ELEMENT.
+        # The state is walked in small chunks; each chunk's (p, slots) tuples are read, updated together in private
+        # storage and written back, so a concurrent push can only lose the updates of the chunk both are inside at the
+        # same instant (not the whole push, which a clone-everything / copy-everything-back scheme would lose), and no
+        # thread ever combines its momentum with another thread's half-written second moment.
+        ns, n, ck = self.spec.num_slots, self.state.shape[0], self.HOGWILD_CHUNK
+        for lo in range(0, n, ck):
+            hi = min(lo + ck, n)
+            local = self.state[lo:hi].clone()
+            apply_update(self.spec, local[:, 0], g[lo:hi], [local[:, 1 + i] for i in range(ns)], step)
+            self.state[lo:hi] = local
 
     def slot_arrays(self) -> List[List[np.ndarray]]:
         return [self.unflatten(s.clone().contiguous()) for s in self.slots]
@@ -200,14 +213,19 @@ class GlooTransport:
         self.shapes = [tuple(s) for s in shapes]
         self.sizes = [int(np.prod(s)) if s else 1 for s in self.shapes]
         self.n = int(sum(self.sizes))
+        # ONE transport per rank: the partitions of a rank run on threads, and the server has one service thread per
+        # rank, so every pull / push exchange (header, payload, reply share the rank's tags) is done under this mutex
+        self._mutex = threading.Lock()
+        self._closed = False
 
     def _hdr(self, op: int) -> None:
         self.dist.send(torch.tensor([op, self.n], dtype=torch.int64), dst=0, group=self.group, tag=self.rank)
 
     def pull(self) -> List[np.ndarray]:
-        self._hdr(_OP_PULL)
-        flat = torch.empty(self.n, dtype=torch.float32)
-        self.dist.recv(flat, src=0, group=self.group, tag=1000 + self.rank)
+        with self._mutex:
+            self._hdr(_OP_PULL)
+            flat = torch.empty(self.n, dtype=torch.float32)
+            self.dist.recv(flat, src=0, group=self.group, tag=1000 + self.rank)
         arr, out, off = flat.numpy(), [], 0
         for shp, n in zip(self.shapes, self.sizes):
             out.append(arr[off:off + n].reshape(shp).copy())
@@ -215,14 +233,20 @@ class GlooTransport:
         return out
 
     def push(self, grads: Sequence) -> str:
-        self._hdr(_OP_PUSH)
-        self.dist.send(flatten_grads(grads), dst=0, group=self.group, tag=self.rank)
-        code = torch.zeros(1, dtype=torch.int64)
-        self.dist.recv(code, src=0, group=self.group, tag=1000 + self.rank)
+        flat = flatten_grads(grads)
+        with self._mutex:
+            self._hdr(_OP_PUSH)
+            self.dist.send(flat, dst=0, group=self.group, tag=self.rank)
+            code = torch.zeros(1, dtype=torch.int64)
+            self.dist.recv(code, src=0, group=self.group, tag=1000 + self.rank)
         status = {0: "completed", 1: "failed", 2: "dropped", 3: "fatal"}[int(code)]
         if status == "fatal":
             raise TooManyFailures("Too many failures during training")
         return status
 
     def close(self) -> None:
-        self._hdr(_OP_DONE)
+        """Tell the rank's service thread to exit: exactly once per rank, whether or not it trained a partition."""
+        with self._mutex:
+            if not self._closed:
+                self._closed = True
+                self._hdr(_OP_DONE)

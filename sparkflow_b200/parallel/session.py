@@ -77,7 +77,9 @@ class TrainingSession:
             raise RuntimeError("engine='b200' requested but no CUDA device is available")
         self.master = None           # MasterState (GPU) or ParameterServer (host)
         self.gloo_server: Optional[GlooServer] = None
+        self._gloo_transport: Optional[GlooTransport] = None      # one per non-master rank, shared by its partitions
         self._workers: List[object] = []
+        self._dev_workers: dict = {}
         self._opened = False
 
     # -------------------------------------------------------------------------------------------
@@ -142,6 +144,8 @@ class TrainingSession:
                 if ctx.is_master:
                     self.master = ParameterServer(self._init_weights(), self.spec, self.acquire_lock, max_errors=max(self.iters, 1))
                     self.gloo_server = GlooServer(self.master, ctx.world, ctx.control_group)
+                else:
+                    self._gloo_transport = GlooTransport(ctx.rank, [v.shape for v in self.ir.trainable], ctx.control_group)
                 D.barrier(ctx)
             else:
                 self.master = ParameterServer(self._init_weights(), self.spec, self.acquire_lock, max_errors=max(self.iters, 1))
@@ -209,17 +213,23 @@ class TrainingSession:
         if self.engine_kind == "b200":
             from .device_engine import DeviceWorker, MasterState
 
-            master = self.master
-            if master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
-                master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base, n_mailboxes=self.master.ml.n_mailboxes)
-            shared = self.ctx.world > 1 or len(self.local_devices()) > 1
-            widx = self.ctx.rank if self.ctx.world > 1 else (device.index or 0)
-            w = DeviceWorker(self.ir, self.tf_input, self.tf_label, self.spec, master, acquire_lock=self.acquire_lock,
-                             pull_mode=self.pull_mode, device=device, shared=shared, worker_index=widx)
-            self._workers.append(w)
+            # one DeviceWorker per device for the whole session: it owns the replica, gradient buffers, streams and
+            # captured CUDA graphs, all of which are reusable across partitions and partition_shuffles rounds
+            w = self._dev_workers.get(device)
+            if w is None:
+                master = self.master
+                if master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
+                    master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base, n_mailboxes=self.master.ml.n_mailboxes)
+                shared = self.ctx.world > 1 or len(self.local_devices()) > 1
+                # mailbox index = position of the device in the session's device list (NOT its CUDA ordinal)
+                widx = self.ctx.rank if self.ctx.world > 1 else self.local_devices().index(device)
+                w = DeviceWorker(self.ir, self.tf_input, self.tf_label, self.spec, master, acquire_lock=self.acquire_lock,
+                                 pull_mode=self.pull_mode, device=device, shared=shared, worker_index=widx)
+                self._dev_workers[device] = w
+                self._workers.append(w)
             return B200Engine(w)
         if self.ctx.world > 1 and not self.ctx.is_master:
-            transport = GlooTransport(self.ctx.rank, [v.shape for v in self.ir.trainable], self.ctx.control_group)
+            transport = self._gloo_transport
         else:
             transport = LocalTransport(self.master)
         eng = TorchEngine(self.ir, self.tf_input, self.tf_label, transport, device=str(device) if device.type == "cuda" else "cpu",
@@ -258,8 +268,6 @@ class TrainingSession:
                               mini_stochastic_iters=self.msi, verbose=self.verbose, loss_callback=self.loss_callback,
                               partition_id=f"partition-{pid}", seed=None if self.seed is None else self.seed + pid,
                               on_iteration=self.maybe_snapshot if (pid == 0 and self.checkpoint_every) else None)
-                if isinstance(engine, TorchEngine) and isinstance(engine.transport, GlooTransport):
-                    pass
 
         active = [i for i, l in enumerate(lanes) if l]
         if len(active) <= 1:
@@ -311,9 +319,9 @@ class TrainingSession:
         if not self._opened:
             return
         ctx = self.ctx
-        for w in self._workers:
-            if isinstance(w, TorchEngine) and isinstance(w.transport, GlooTransport):
-                w.transport.close()
+        if self._gloo_transport is not None:
+            self._gloo_transport.close()       # _OP_DONE exactly once per rank, also when it had no partition
+            self._gloo_transport = None
         D.barrier(ctx)
         if self.gloo_server is not None:
             self.gloo_server.join(timeout=10)
@@ -328,5 +336,6 @@ class TrainingSession:
             D.barrier(ctx)
             self.master.close()
         self._workers.clear()
+        self._dev_workers.clear()
         self.master = None
         self._opened = False

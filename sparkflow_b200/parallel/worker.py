@@ -90,14 +90,17 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
                     sel = rng.choice(n, mbs, replace=False)
                 engine.train(rows_of(sel), pull=(j == 0))
         elif mini_batch_size >= 1:
+            # the reference strides by the ORIGINAL mini_batch_size and only clamps the slice length
+            # (HogwildSparkModel.py:73-74 + ml_util.py:105-106): mbs > n means ONE batch of n-1 rows per iteration
             mbs = max(clamp_batch(n, mini_batch_size), 1)
-            if fast and order is None:
+            stride = max(mini_batch_size, 1)
+            if fast and order is None and stride == mbs:
                 full = n // mbs
                 engine.train_contiguous([k * mbs for k in range(full)], mbs, pull=True)
                 if full * mbs < n:
                     engine.train(slice(full * mbs, n), pull=True)
             else:
-                for r in range(0, n, mbs):
+                for r in range(0, n, stride):
                     engine.train(rows_of(slice(r, min(r + mbs, n))), pull=True)
         else:
             engine.train(rows_of(slice(0, n)), pull=True)

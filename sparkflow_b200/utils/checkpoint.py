@@ -14,7 +14,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 
 from ..io.bundle import read_bundle, write_bundle, write_checkpoint_state
-from ..ops.optimizers import SLOT_NAMES, OptimizerSpec
+from ..ops.optimizers import OptimizerSpec
 
 STEP_KEY = "sparkflow_b200/optimizer_step"
 
@@ -24,7 +24,7 @@ def save_master_state(prefix: str, var_names: Sequence[str], weights: Sequence[n
     tensors: Dict[str, np.ndarray] = {}
     for name, w in zip(var_names, weights):
         tensors[name] = np.asarray(w, dtype=np.float32)
-    for si, slot_name in enumerate(SLOT_NAMES.get(spec.name, [])[: len(slots)]):
+    for si, slot_name in enumerate(spec.slot_names()[: len(slots)]):
         for name, arr in zip(var_names, slots[si]):
             tensors[f"{name}/{slot_name}"] = np.asarray(arr, dtype=np.float32)
     if spec.name == "adam":
@@ -51,7 +51,7 @@ def load_master_state(prefix: str, var_names: Sequence[str], spec: OptimizerSpec
             raise KeyError(f"checkpoint {prefix} has no variable '{name}'")
         weights.append(tensors[name])
     slots: List[List[np.ndarray]] = []
-    for si, slot_name in enumerate(SLOT_NAMES.get(spec.name, [])):
+    for si, slot_name in enumerate(spec.slot_names()):
         keys = [f"{n}/{slot_name}" for n in var_names]
         if all(k in tensors for k in keys):
             slots.append([tensors[k] for k in keys])

@@ -38,3 +38,27 @@ def pytest_runtest_makereport(item, call):
             rep.sections.append(("sparkflow_b200 device error channel", native.describe_device_error()))
         except Exception:
             pass
+
+
+@pytest.fixture(scope="session")
+def tf_checkpoint(tmp_path_factory):
+    """A self-generated TF-V2 checkpoint of the reference fixture's architecture (2-10 tanh-10 tanh-1 sigmoid, Adam
+    slots, beta powers: the key set of /root/reference/tests/test_model/to_load.index) written by this package's own
+    bundle writer - the suite does not depend on the reference tree being mounted."""
+    import numpy as np
+
+    from sparkflow_b200.graph.executor import GraphProgram
+    from sparkflow_b200.graph.ir import GraphIR
+    from sparkflow_b200.models import zoo
+    from sparkflow_b200.ops.optimizers import OptimizerSpec
+    from sparkflow_b200.utils.checkpoint import save_master_state
+
+    d = tmp_path_factory.mktemp("test_model")
+    graph = zoo.build("fixture_mlp")
+    ir = GraphIR.from_metagraph(graph)
+    w = GraphProgram(ir).init_weights(seed=11)
+    rng = np.random.default_rng(5)
+    slots = [[rng.normal(0, 0.01, a.shape).astype(np.float32) for a in w], [np.abs(rng.normal(0, 0.01, a.shape)).astype(np.float32) for a in w]]
+    spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.1))
+    prefix = save_master_state(str(d / "to_load"), [v.name for v in ir.trainable], w, slots, spec, step=37, graph_json=graph)
+    return dict(prefix=prefix, weights=w, slots=slots, graph=graph)

@@ -287,6 +287,62 @@ def test_bundle_reader_and_writer_are_byte_exact(tmp_path):
         read_bundle(str(tmp_path / "rt"))
 
 
+def test_self_generated_checkpoint_roundtrip(tf_checkpoint, tmp_path):
+    """The shipped-by-construction fixture: same key set / shapes as the reference's to_load bundle, byte-stable rewrite,
+    and loadable through the public loader API (reference: tensorflow_model_loader.py:8-45)."""
+    from sparkflow_b200.io.bundle import read_bundle, read_checkpoint_state, write_bundle
+    from sparkflow_b200.tensorflow_model_loader import load_tensorflow_model
+
+    prefix = tf_checkpoint["prefix"]
+    t = read_bundle(prefix)
+    keys = {k for k in t if not k.startswith("sparkflow_b200/")}
+    expect = {"beta1_power", "beta2_power"}
+    for v in ("dense/kernel", "dense/bias", "dense_1/kernel", "dense_1/bias", "out/kernel", "out/bias"):
+        expect |= {v, v + "/Adam", v + "/Adam_1"}
+    assert keys == expect and t["dense/kernel"].shape == (2, 10) and t["out/kernel/Adam_1"].shape == (10, 1)
+    assert sum(v.size for k, v in t.items() if k in expect) == 455          # the reference fixture's 1820 bytes
+    assert read_checkpoint_state(os.path.dirname(prefix)) == prefix
+    write_bundle(str(tmp_path / "rt"), t)
+    for ext in (".index", ".data-00000-of-00001"):
+        assert open(str(tmp_path / "rt") + ext, "rb").read() == open(prefix + ext, "rb").read()
+    model = load_tensorflow_model(prefix, inputCol="features", tfInput="x:0", tfOutput="out/Sigmoid:0")
+    got = json.loads(model.getOrDefault(model.modelWeights))
+    for a, b in zip(got, tf_checkpoint["weights"]):
+        assert np.allclose(np.asarray(a, np.float32), b)
+
+
+def test_centered_rmsprop_slot_names_follow_tf_creation_order():
+    plain = OptimizerSpec.from_tf_kwargs("rmsprop", dict(learning_rate=0.1))
+    cent = OptimizerSpec.from_tf_kwargs("rmsprop", dict(learning_rate=0.1, centered=True))
+    assert plain.slot_names()[:2] == ["RMSProp", "RMSProp_1"]              # rms, momentum
+    assert cent.slot_names() == ["RMSProp", "RMSProp_2", "RMSProp_1"]      # internal (rms, momentum, mg) -> TF (rms, mg, momentum)
+
+
+def test_hogwild_host_pushes_race_per_element_not_per_push():
+    """4 threads x 100 SGD pushes (lr 1, grad 1): chunked in-place application must keep (nearly) every push."""
+    from sparkflow_b200.parallel.param_server import ParameterServer
+
+    ps = ParameterServer([np.zeros((40000,), np.float32)], OptimizerSpec.from_tf_kwargs("gradient_descent", dict(learning_rate=1.0)))
+    g = torch.ones(40000)
+    ts = [threading.Thread(target=lambda: [ps.update_parameters(g) for _ in range(100)]) for _ in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert ps.pushes == 400
+    applied = -ps.p.mean().item()
+    assert applied > 200, applied          # a whole-state clone / copy-back keeps ~1/4 of them (~100)
+
+
+def test_avgpool_same_excludes_padding_from_the_divisor():
+    from sparkflow_b200.graph.executor import OPS
+
+    class N:
+        attrs = dict(ksize=[1, 2, 2, 1], strides=[1, 2, 2, 1], padding="SAME")
+
+    x = torch.ones(1, 3, 3, 1)
+    (y,) = OPS["AvgPool"](N, [x], None)
+    assert y.shape == (1, 2, 2, 1) and torch.allclose(y, torch.ones_like(y))
+
+
 def test_large_bundle_spans_multiple_blocks(tmp_path):
     from sparkflow_b200.io.bundle import read_bundle, write_bundle
 
