@@ -29,7 +29,7 @@ im2col_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c, 
   const int oh = h - kh + 1, ow = w - kw + 1;
   const int M = n * oh * ow, K = kh * kw * c;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int k0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  const int k0 = blockIdx.y * 32, m0 = blockIdx.x * 32;      // M tiles on x: a 4096-row evaluation chunk has > 65535 of them
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty + 8 * i, k = k0 + tx;
@@ -206,7 +206,7 @@ extern "C" int sf_im2col_nhwc(const __nv_bfloat16* in, int n, int h, int w, int 
                               int ld_out, __nv_bfloat16* outT, int ld_t, cudaStream_t st) {
   const int M = n * (h - kh + 1) * (w - kw + 1), K = kh * kw * c;
   const int span_k = (out && ld_out > K) ? ld_out : K;
-  dim3 grid((span_k + 31) / 32, (M + 31) / 32);
+  dim3 grid((M + 31) / 32, (span_k + 31) / 32);
   return static_cast<int>(sf::launch(sf::im2col_kernel, grid, dim3(256), 0, st, in, n, h, w, c, kh, kw, out, ld_out, outT, ld_t));
 }
 

@@ -146,8 +146,19 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
       if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, r[0]);
     }
 
-    if (ep.out_f32 != nullptr && row_ok) {
-      float* op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+    if ((ep.out_f32 != nullptr || ep.route != nullptr) && row_ok) {
+      float* op;
+      if (ep.route != nullptr) {
+        // push fused into the wgrad epilogue: this 32-column chunk lies inside ONE 32 x 64 push tile; its gradient goes
+        // straight into this worker's mailbox on the GPU that owns the tile (NVLink peer stores / reds)
+        const int tile = ep.route_tile0 + (row >> 5) * ep.route_tiles_c + (col0 >> 6);
+        int owner = 0;
+#pragma unroll
+        for (int r = 1; r < SF_MAX_SHARDS; ++r) owner += (r < ep.route->n_shards && tile >= ep.route->bounds[r]) ? 1 : 0;
+        op = ep.route->mailbox[owner] + ep.route_off + static_cast<size_t>(row) * ep.ld_f32 + col0;
+      } else {
+        op = ep.out_f32 + static_cast<size_t>(row) * ep.ld_f32 + col0;
+      }
       if (ep.accumulate) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)

@@ -222,6 +222,14 @@ __device__ __forceinline__ void st_shadow8(__nv_bfloat16* dst, uint2 q, bool mc)
                  : "memory");
   }
 }
+__device__ __forceinline__ void st_vec_f32(float* dst, float v, bool mc) {
+  if (mc) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+  else asm volatile("st.global.relaxed.sys.f32 [%0], %1;" ::"l"(dst), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_u32_pub(uint32_t* dst, uint32_t v, bool mc) {
+  if (mc) asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(v) : "memory");
+  else asm volatile("st.global.relaxed.sys.u32 [%0], %1;" ::"l"(dst), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc) {
   if (mc) multimem_st_u4(reinterpret_cast<uint4*>(dst), q);
   else asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
@@ -322,6 +330,16 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
         }
       }
     }
+    if (a.mb_zero) {
+      // accumulating wgrad epilogues (split-K conv) add into the mailbox: hand it back zeroed
+      for (int k = 0; k < n_grads; ++k)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (nv[half] == 0) continue;
+          if (vec) *reinterpret_cast<float4*>(grads[k] + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+          else for (int j = 0; j < nv[half]; ++j) grads[k][e[half] + j] = 0.f;
+        }
+    }
     // ---- phase 3: stores ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -336,7 +354,12 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
             w[j] = q.p;
             float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
             st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
-            if (a.n_vec_pub > 0 && e[half] + j >= a.vec_offset) {       // 1-D variables: fp32 publish copy / copies
+            if (a.n_vec_dst > 0) {                                      // sharded master: every replica's fp32 tail
+              if (e[half] + j >= a.vec_offset) {
+                const long long vi = e[half] + j - a.vec_offset;
+                for (int d = 0; d < a.n_vec_dst; ++d) st_vec_f32(a.vec_dst[d] + vi, q.p, mc);
+              }
+            } else if (a.n_vec_pub > 0 && e[half] + j >= a.vec_offset) {       // 1-D variables: fp32 publish copy / copies
               const long long vi = e[half] + j - a.vec_offset;
               vec0[vi] = q.p;
               if (a.n_vec_pub > 1) a.vec_pub[1][vi] = q.p;
@@ -667,6 +690,12 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
               buf = (pub >> 31) ^ 1u;
             }
             t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
+            if (a.n_ver > 0) {
+              // seqlock: stamp `begin` in every replica before the first publish store of this pass can land
+              const uint32_t ver = a.sync[6] + 1;
+              for (int d = 0; d < a.n_ver; ++d) st_u32_pub(a.ver_begin[d], ver, a.ver_mc != 0);
+              asm volatile("fence.acq_rel.sys;" ::: "memory");
+            }
           }
           a.sync[1] = m_ready;
           a.sync[2] = t;
@@ -704,10 +733,15 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
     const int n = s_n;
     __nv_bfloat16* const pub0 = (a.dbuf && s_buf) ? a.shadow_alt : a.push.shadow_dst[0];
     float* const vec0 = (a.dbuf && s_buf) ? a.vec_pub_alt : a.push.vec_pub[0];
-    for (int tile = blockIdx.x; tile < a.push.num_tiles; tile += gridDim.x)
+    const int tile_lo = a.tile_end > a.tile_begin ? a.tile_begin : 0;
+    const int tile_hi = a.tile_end > a.tile_begin ? a.tile_end : a.push.num_tiles;
+    for (int tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x)
       push_tile<OPT, false>(a.push, s_grads, n, tile, &s_t, false, s_tr, pub0, vec0);
     __syncthreads();
-    if (tid == 0) lk_red_release<false>(a.sync + 3, 1u);
+    if (tid == 0) {
+      if (a.n_ver > 0) asm volatile("fence.acq_rel.sys;" ::: "memory");     // this CTA's publish stores are performed everywhere
+      lk_red_release<false>(a.sync + 3, 1u);
+    }
     if (leader && tid < 32) {
       if (tid == 0) {
         const unsigned long long t0 = gtime_ns();
@@ -719,6 +753,14 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         // the freshly written buffer becomes the current one (release: after every CTA's publish stores, which the
         // acquire of the done counter above made visible to this thread)
         if (a.dbuf) (void)atom_xor_release_sys(a.push.ctrl + SF_CTRL_PUB, 0x80000000u);
+        if (a.n_ver > 0) {
+          // every CTA fenced its publish stores before arriving: the pass is complete in every replica -> stamp `end`
+          const uint32_t ver = a.sync[6] + 1;
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+          for (int d = 0; d < a.n_ver; ++d) st_u32_pub(a.ver_end[d], ver, a.ver_mc != 0);
+          a.sync[6] = ver;
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+        }
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_STEP, static_cast<uint32_t>(n));
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, static_cast<uint32_t>(n));
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, static_cast<uint32_t>(n));
@@ -729,10 +771,171 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
       if (mask >> tid & 1u) {
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         st_release_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED, posted);
+        // sharded master: the acknowledgement lands in the worker's OWN memory (its next step spins locally)
+        if (a.ack[tid] != nullptr) {
+          asm volatile("fence.acq_rel.sys;" ::: "memory");
+          st_release_sys(a.ack[tid], posted);
+        }
       }
     }
     __syncthreads();
   }
+}
+
+
+// ---------------------------------------------------------------------------
+// Sharded master, worker side (see sf_api.h).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_local_u4(const uint4* p) {
+  // the inbox replica is LOCAL memory written by remote multimem / peer stores: bypass L1 (may hold a stale line)
+  uint4 r;
+  asm volatile("ld.global.relaxed.sys.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+// copy the publish slices (W block, W^T block, fp32 tail elements) of one 32 x 64 push tile: inbox -> working replica
+__device__ __forceinline__ void copy_tile_publish(const SfSyncPullArgs& a, int tile) {
+  const int tid = threadIdx.x;
+  const SfTensorSeg sg = a.segs[a.tile_map[tile * 3 + 0]];
+  const int r0 = a.tile_map[tile * 3 + 1] * kTileR, c0 = a.tile_map[tile * 3 + 2] * kTileC;
+  if (sg.w_off >= 0) {
+    const int row = r0 + (tid >> 3), col = c0 + (tid & 7) * 8;
+    if (row < sg.rows && col < sg.w_ld) {
+      const int64_t o = sg.w_off + static_cast<int64_t>(row) * sg.w_ld + col;
+      *reinterpret_cast<uint4*>(a.dst + o) = ld_local_u4(reinterpret_cast<const uint4*>(a.src + o));
+    }
+  }
+  if (sg.wt_off >= 0) {
+    const int trow = c0 + (tid >> 2), el = r0 + (tid & 3) * 8;
+    if (trow < sg.cols && el < sg.wt_ld) {
+      const int64_t o = sg.wt_off + static_cast<int64_t>(trow) * sg.wt_ld + el;
+      *reinterpret_cast<uint4*>(a.dst + o) = ld_local_u4(reinterpret_cast<const uint4*>(a.src + o));
+    }
+  }
+  if (sg.rows == 1 && a.dst_vec != nullptr && tid < kTileC && c0 + tid < sg.cols) {
+    const long long vi = sg.offset + c0 + tid - a.vec_offset;
+    a.dst_vec[vi] = ld_relaxed_sys_f32(a.src_vec + vi);
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+sync_pull_kernel(const SfSyncPullArgs a) {
+  __shared__ uint32_t s_e;
+  __shared__ uint32_t s_ok;
+  TraceScope trace;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.mark();
+  const int tid = threadIdx.x;
+  const int cps = a.ctas_per_shard;
+  const int shard = blockIdx.x / cps, part = blockIdx.x % cps;
+  // ---- read-your-writes: this shard's applier has consumed my last post (it acknowledges into MY memory) ----
+  if (tid == 0) {
+    const uint32_t want = *a.my_posted;
+    const unsigned long long t0 = gtime_ns();
+    while (static_cast<int32_t>(ld_acquire_sys(a.applied + shard * 16) - want) < 0) {
+      __nanosleep(32);
+      if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x405);
+    }
+  }
+  __syncthreads();
+  if (!a.copy) {
+    trace.end(KID_PULL);
+    return;
+  }
+  // ---- consistent snapshot of the shard (seqlock; every CTA of the shard must have copied the SAME version) ----
+  uint32_t* sy = a.sync + shard * 8;          // 0 arrivals, 1 min version, 2 max version / dirty, 3 result (round << 1 | ok), 4 round
+  const unsigned long long t0 = gtime_ns();
+  while (true) {
+    if (tid == 0) {
+      uint32_t e;
+      while ((e = ld_acquire_sys(a.ver_end + shard * a.ver_stride)) != ld_acquire_sys(a.ver_begin + shard * a.ver_stride)) {
+        __nanosleep(32);                       // an update of this shard is landing right now
+        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40A);
+      }
+      s_e = e;
+    }
+    __syncthreads();
+    for (int tile = a.bounds[shard] + part; tile < a.bounds[shard + 1]; tile += cps) copy_tile_publish(a, tile);
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("fence.acq_rel.sys;" ::: "memory");
+      const uint32_t e = s_e;
+      const bool clean = ld_acquire_sys(a.ver_begin + shard * a.ver_stride) == e;
+      uint32_t ok;
+      if (cps == 1) {
+        ok = clean ? 1u : 0u;
+      } else {
+        // agreement round: min / max over the CTAs' versions (a dirty CTA poisons max), last arriver publishes the verdict
+        const uint32_t round = ld_acquire_gpu(sy + 4);
+        atomicMin(sy + 1, e);
+        atomicMax(sy + 2, clean ? e : 0xFFFFFFFFu);
+        if (lk_add_release<false>(sy + 0, 1u) == static_cast<uint32_t>(cps) - 1u) {
+          (void)ld_acquire_gpu(sy + 0);
+          ok = (sy[1] == sy[2]) ? 1u : 0u;
+          sy[0] = 0; sy[1] = 0xFFFFFFFFu; sy[2] = 0;
+          st_release_gpu(sy + 4, round + 1);
+          st_release_gpu(sy + 3, ((round + 1) << 1) | ok);
+        } else {
+          uint32_t r;
+          while (((r = ld_acquire_gpu(sy + 3)) >> 1) != round + 1) {
+            if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40B);
+          }
+          ok = r & 1u;
+        }
+      }
+      s_ok = ok;
+    }
+    __syncthreads();
+    if (s_ok) break;
+    if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40C);
+  }
+  trace.end(KID_PULL);
+}
+
+__global__ void __launch_bounds__(256, 1)
+post_flags_kernel(const SfPostFlagsArgs a) {
+  TraceScope trace;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.mark();
+  const int tid = threadIdx.x;
+  // ---- 1-D tail (bias gradients were accumulated locally by atomics): forward each 64-element tile to its owner ----
+  for (int i = tid >> 6; i < a.n_vec_tiles; i += blockDim.x >> 6) {
+    const long long tile = a.vec_tiles[i * 3 + 0], off = a.vec_tiles[i * 3 + 1], cnt = a.vec_tiles[i * 3 + 2];
+    int owner = 0;
+    for (int r = 1; r < a.n_shards; ++r) owner += tile >= a.bounds[r] ? 1 : 0;
+    const int l = tid & 63;
+    if (l < cnt) {
+      const float g = a.grad[off + l];
+      a.grad[off + l] = 0.f;
+      if (!a.drop) asm volatile("st.global.relaxed.sys.f32 [%0], %1;" ::"l"(a.mailbox[owner] + off + l), "f"(g) : "memory");
+    }
+  }
+  if (a.drop && a.mb_zero) {
+    // the wgrad epilogues already ADDED this step's tiles into the mailboxes: a dropped push must take them out again
+    for (int r = 0; r < a.n_shards; ++r)
+      for (long long i = tid; i < a.total / 4; i += blockDim.x)
+        st_weak_f4(a.mailbox[r] + i * 4, 0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (a.loss_acc != nullptr) {
+      *a.loss_out = *a.loss_acc;
+      *a.loss_acc = 0.f;
+    }
+    signal_done(a.loss_out, a.done_dev);
+  }
+  if (!a.drop && tid < a.n_shards) {
+    // the matrix gradients were stored by the wgrad kernels this kernel depends on (kernel boundary = performed);
+    // the release below orders them, and the tail stores above (bar.sync), before the post becomes visible
+    const uint32_t seq = *a.my_posted + 1;
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    st_release_sys(a.posted[tid], seq);
+  }
+  __syncthreads();
+  if (!a.drop && tid == 0) *a.my_posted = *a.my_posted + 1;
+  trace.end(KID_PUSH);
 }
 
 // single-thread lock exerciser used by the GPU tests (op: 0 = acquire_read, 1 = release_read,
@@ -820,6 +1023,19 @@ extern "C" int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int g
     case SF_OPT_PROXIMAL_SGD: return launch_applier<SF_OPT_PROXIMAL_SGD>(a, seq, grid, st);
   }
   return -4;
+}
+
+
+extern "C" int sf_sync_pull_launch(const SfSyncPullArgs* a, cudaStream_t st) {
+  if (a->n_shards < 1 || a->n_shards > SF_MAX_SHARDS || a->ctas_per_shard < 1) return -6;
+  const int grid = a->n_shards * a->ctas_per_shard;
+  if (grid > 148) return -6;            // the agreement round needs every CTA of a shard resident
+  return static_cast<int>(sf::launch(sf::sync_pull_kernel, dim3(grid), dim3(256), 0, st, *a));
+}
+
+extern "C" int sf_post_flags_launch(const SfPostFlagsArgs* a, cudaStream_t st) {
+  if (a->n_shards < 1 || a->n_shards > SF_MAX_SHARDS) return -6;
+  return static_cast<int>(sf::launch(sf::post_flags_kernel, dim3(1), dim3(256), 0, st, *a));
 }
 
 extern "C" int sf_lock_test(uint32_t* ctrl, int op, cudaStream_t st) {

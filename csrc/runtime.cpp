@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "sf_api.h"
+#include "vmm.h"
 
 namespace py = pybind11;
 
@@ -85,6 +86,10 @@ struct Gemm {
     g.ep.target = P<const float>(getd<uintptr_t>(d, "target", 0));
     g.ep.ld_target = getd<int>(d, "ld_target", 0);
     g.ep.loss = P<float>(getd<uintptr_t>(d, "loss", 0));
+    g.ep.route = P<const SfRoute>(getd<uintptr_t>(d, "route", 0));
+    g.ep.route_tile0 = getd<int>(d, "route_tile0", 0);
+    g.ep.route_tiles_c = getd<int>(d, "route_tiles_c", 1);
+    g.ep.route_off = getd<long long>(d, "route_off", 0);
     if ((g.lda % 8) || (g.ldb % 8)) throw std::runtime_error("gemm: lda/ldb must be multiples of 8 (16-byte TMA strides)");
     if (g.ep.out_bf16 && (g.ep.ld_bf16 % 8)) throw std::runtime_error("gemm: ld_bf16 must be a multiple of 8");
     if (g.ep.aux && (g.ep.ld_aux % 8)) throw std::runtime_error("gemm: ld_aux must be a multiple of 8");
@@ -191,6 +196,11 @@ SfPushArgs parse_push(const py::dict& d) {
   for (size_t i = 0; i < vps.size(); ++i) a.vec_pub[i] = P<float>(vps[i]);
   a.vec_offset = getd<long long>(d, "vec_offset", 0);
   a.shadow_is_mc = getd<int>(d, "shadow_is_mc", 0);
+  auto vds = getd<std::vector<uintptr_t>>(d, "vec_dst", {});
+  if (vds.size() > 8) throw std::runtime_error("push: at most 8 vec_dst targets");
+  a.n_vec_dst = static_cast<int>(vds.size());
+  for (size_t i = 0; i < vds.size(); ++i) a.vec_dst[i] = P<float>(vds[i]);
+  a.mb_zero = getd<int>(d, "mb_zero", 0);
   a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
   a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
   a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
@@ -259,6 +269,79 @@ SfFetchArgs parse_fetch(const py::dict& d) {
   if (!a.desc || !a.sched || !a.counter || !a.sync || !a.x_out || a.rows <= 0 || a.cols <= 0)
     throw std::runtime_error("fetch: desc/sched/counter/sync/x_out/rows/cols are required");
   return a;
+}
+
+
+void fill_bounds(const py::dict& d, int n_shards, int* bounds) {
+  auto b = getd<std::vector<int>>(d, "bounds", {});
+  if (static_cast<int>(b.size()) != n_shards + 1) throw std::runtime_error("sharded: bounds must have n_shards + 1 entries");
+  for (int i = 0; i <= n_shards; ++i) bounds[i] = b[i];
+  for (int i = n_shards + 1; i <= SF_MAX_SHARDS; ++i) bounds[i] = b[n_shards];
+}
+
+SfSyncPullArgs parse_sync_pull(const py::dict& d) {
+  SfSyncPullArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n_shards = getd<int>(d, "n_shards", 0);
+  if (a.n_shards < 1 || a.n_shards > SF_MAX_SHARDS) throw std::runtime_error("sync_pull: n_shards in [1, 8]");
+  fill_bounds(d, a.n_shards, a.bounds);
+  a.applied = P<const uint32_t>(getd<uintptr_t>(d, "applied", 0));
+  a.my_posted = P<const uint32_t>(getd<uintptr_t>(d, "my_posted", 0));
+  a.copy = getd<int>(d, "copy", 0);
+  a.ver_begin = P<const uint32_t>(getd<uintptr_t>(d, "ver_begin", 0));
+  a.ver_end = P<const uint32_t>(getd<uintptr_t>(d, "ver_end", 0));
+  a.ver_stride = getd<int>(d, "ver_stride", 16);
+  a.src = P<const __nv_bfloat16>(getd<uintptr_t>(d, "src", 0));
+  a.dst = P<__nv_bfloat16>(getd<uintptr_t>(d, "dst", 0));
+  a.src_vec = P<const float>(getd<uintptr_t>(d, "src_vec", 0));
+  a.dst_vec = P<float>(getd<uintptr_t>(d, "dst_vec", 0));
+  a.vec_offset = getd<long long>(d, "vec_offset", 0);
+  a.segs = P<const SfTensorSeg>(getd<uintptr_t>(d, "segs", 0));
+  a.tile_map = P<const int32_t>(getd<uintptr_t>(d, "tile_map", 0));
+  a.ctas_per_shard = getd<int>(d, "ctas_per_shard", 1);
+  a.sync = P<uint32_t>(getd<uintptr_t>(d, "sync", 0));
+  if (!a.applied || !a.my_posted) throw std::runtime_error("sync_pull: applied / my_posted are required");
+  if (a.copy && (!a.ver_begin || !a.ver_end || !a.src || !a.dst || !a.segs || !a.tile_map || !a.sync))
+    throw std::runtime_error("sync_pull: copy needs ver_begin/ver_end/src/dst/segs/tile_map/sync");
+  return a;
+}
+
+SfPostFlagsArgs parse_post_flags(const py::dict& d) {
+  SfPostFlagsArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.n_shards = getd<int>(d, "n_shards", 0);
+  if (a.n_shards < 1 || a.n_shards > SF_MAX_SHARDS) throw std::runtime_error("post_flags: n_shards in [1, 8]");
+  fill_bounds(d, a.n_shards, a.bounds);
+  auto posted = getd<std::vector<uintptr_t>>(d, "posted", {});
+  auto mbs = getd<std::vector<uintptr_t>>(d, "mailbox", {});
+  if (static_cast<int>(posted.size()) != a.n_shards || static_cast<int>(mbs.size()) != a.n_shards)
+    throw std::runtime_error("post_flags: one posted word and one mailbox per shard");
+  for (int i = 0; i < a.n_shards; ++i) { a.posted[i] = P<uint32_t>(posted[i]); a.mailbox[i] = P<float>(mbs[i]); }
+  a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
+  a.vec_tiles = P<const long long>(getd<uintptr_t>(d, "vec_tiles", 0));
+  a.n_vec_tiles = getd<int>(d, "n_vec_tiles", 0);
+  a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
+  a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
+  a.done_dev = P<unsigned int>(getd<uintptr_t>(d, "done_dev", 0));
+  a.my_posted = P<uint32_t>(getd<uintptr_t>(d, "my_posted", 0));
+  a.drop = getd<int>(d, "drop", 0);
+  a.total = getd<long long>(d, "total", 0);
+  a.mb_zero = getd<int>(d, "mb_zero", 0);
+  if (!a.grad || !a.my_posted || (a.n_vec_tiles > 0 && !a.vec_tiles)) throw std::runtime_error("post_flags: grad / my_posted / vec_tiles are required");
+  return a;
+}
+
+// device-resident routing table of one worker (kept alive by the Python side)
+py::bytes pack_route(int n_shards, const std::vector<int>& bounds, const std::vector<uintptr_t>& mailboxes) {
+  SfRoute r;
+  std::memset(&r, 0, sizeof(r));
+  if (n_shards < 1 || n_shards > SF_MAX_SHARDS || static_cast<int>(bounds.size()) != n_shards + 1 || static_cast<int>(mailboxes.size()) != n_shards)
+    throw std::runtime_error("pack_route: n_shards in [1, 8], n_shards + 1 bounds, n_shards mailboxes");
+  r.n_shards = n_shards;
+  for (int i = 0; i <= n_shards; ++i) r.bounds[i] = bounds[i];
+  for (int i = n_shards + 1; i <= SF_MAX_SHARDS; ++i) r.bounds[i] = bounds[n_shards];
+  for (int i = 0; i < n_shards; ++i) r.mailbox[i] = P<float>(mailboxes[i]);
+  return py::bytes(reinterpret_cast<const char*>(&r), sizeof(r));
 }
 
 SfPullArgs parse_pull(const py::dict& d) {
@@ -703,7 +786,8 @@ class StepDriver {
 class Applier {
  public:
   Applier(const py::dict& push, uintptr_t mailboxes, size_t mailbox_stride, uintptr_t flags, int n_workers, uintptr_t sync,
-          double poll_window_s, int grid, int depth, int max_batch, uintptr_t shadow_alt, uintptr_t vec_pub_alt) : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
+          double poll_window_s, int grid, int depth, int max_batch, uintptr_t shadow_alt, uintptr_t vec_pub_alt, const py::dict& shard)
+      : grid_(grid), depth_(depth < 1 ? 1 : (depth > 16 ? 16 : depth)) {
     py::dict d(push);
     std::memset(&args_, 0, sizeof(args_));
     args_.push = parse_push(d);
@@ -718,6 +802,20 @@ class Applier {
     args_.vec_pub_alt = P<float>(vec_pub_alt);
     args_.dbuf = shadow_alt != 0 ? 1 : 0;
     if (args_.dbuf && args_.push.n_vec_pub > 0 && !args_.vec_pub_alt) throw std::runtime_error("applier: dbuf needs vec_pub_alt");
+    // sharded master (optional): tile range, remote acknowledgement words, seqlock stamps
+    args_.tile_begin = getd<int>(shard, "tile_begin", 0);
+    args_.tile_end = getd<int>(shard, "tile_end", 0);
+    {
+      auto acks = getd<std::vector<uintptr_t>>(shard, "ack", {});
+      if (acks.size() > 8) throw std::runtime_error("applier: at most 8 ack words");
+      for (size_t i = 0; i < acks.size(); ++i) args_.ack[i] = P<uint32_t>(acks[i]);
+      auto vb = getd<std::vector<uintptr_t>>(shard, "ver_begin", {});
+      auto ve = getd<std::vector<uintptr_t>>(shard, "ver_end", {});
+      if (vb.size() != ve.size() || vb.size() > 8) throw std::runtime_error("applier: ver_begin / ver_end lists must match (<= 8)");
+      args_.n_ver = static_cast<int>(vb.size());
+      for (size_t i = 0; i < vb.size(); ++i) { args_.ver_begin[i] = P<uint32_t>(vb[i]); args_.ver_end[i] = P<uint32_t>(ve[i]); }
+      args_.ver_mc = getd<int>(shard, "ver_mc", 0);
+    }
     ck(cudaGetDevice(&device_), "cudaGetDevice");
     int lo = 0, hi = 0;
     ck(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
@@ -951,6 +1049,14 @@ PYBIND11_MODULE(_C, m) {
              const SfPostArgs a = parse_post(d);
              p.add("post", [=](cudaStream_t st) { return sf_post_launch(&a, P<uint32_t>(local_sync), grid, st); });
            })
+      .def("add_sync_pull", [](Plan& p, const py::dict& d) {
+        const SfSyncPullArgs a = parse_sync_pull(d);
+        p.add("sync_pull", [=](cudaStream_t st) { return sf_sync_pull_launch(&a, st); });
+      })
+      .def("add_post_flags", [](Plan& p, const py::dict& d) {
+        const SfPostFlagsArgs a = parse_post_flags(d);
+        p.add("post_flags", [=](cudaStream_t st) { return sf_post_flags_launch(&a, st); });
+      })
       .def("add_fetch", [](Plan& p, const py::dict& d, int grid) {
         const SfFetchArgs a = parse_fetch(d);
         p.add("fetch", [=](cudaStream_t st) { return sf_fetch_launch(&a, grid, st); });
@@ -961,9 +1067,10 @@ PYBIND11_MODULE(_C, m) {
       });
 
   py::class_<Applier>(m, "Applier")
-      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int, int, uintptr_t, uintptr_t>(), py::arg("push"), py::arg("mailboxes"),
+      .def(py::init<const py::dict&, uintptr_t, size_t, uintptr_t, int, uintptr_t, double, int, int, int, uintptr_t, uintptr_t, const py::dict&>(), py::arg("push"), py::arg("mailboxes"),
            py::arg("mailbox_stride"), py::arg("flags"), py::arg("n_workers"), py::arg("sync"), py::arg("poll_window_s") = 30e-6,
-           py::arg("grid") = 96, py::arg("depth") = 3, py::arg("max_batch") = 8, py::arg("shadow_alt") = 0, py::arg("vec_pub_alt") = 0)
+           py::arg("grid") = 96, py::arg("depth") = 3, py::arg("max_batch") = 8, py::arg("shadow_alt") = 0, py::arg("vec_pub_alt") = 0,
+           py::arg("shard") = py::dict())
       .def("alive", &Applier::alive)
       .def("launches", &Applier::launches)
       .def("stop", &Applier::stop);
@@ -1058,6 +1165,31 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("read_host_error_code", &sf_read_host_error_code);
   m.def("pack_segs", &pack_segs);
+
+  m.def("pack_route", &pack_route);
+  m.attr("MAX_SHARDS") = static_cast<int>(SF_MAX_SHARDS);
+  m.def("sync_pull", [](const py::dict& d, uintptr_t stream) {
+    const SfSyncPullArgs a = parse_sync_pull(d);
+    ck_rc(sf_sync_pull_launch(&a, S(stream)), "sync_pull");
+  });
+  m.def("post_flags", [](const py::dict& d, uintptr_t stream) {
+    const SfPostFlagsArgs a = parse_post_flags(d);
+    ck_rc(sf_post_flags_launch(&a, S(stream)), "post_flags");
+  });
+  // symmetric (VMM) memory + NVSwitch multicast
+  m.def("vmm_granularity", &sfvmm::granularity, py::arg("device"), py::arg("multicast") = false, py::arg("n_devices") = 1);
+  m.def("vmm_multicast_supported", &sfvmm::multicast_supported);
+  m.def("vmm_create", &sfvmm::create);
+  m.def("vmm_release", &sfvmm::release);
+  m.def("vmm_export_fd", &sfvmm::export_fd);
+  m.def("vmm_import_fd", &sfvmm::import_fd);
+  m.def("vmm_map", &sfvmm::map);
+  m.def("vmm_unmap", &sfvmm::unmap);
+  m.def("mc_create", &sfvmm::mc_create);
+  m.def("mc_add_device", &sfvmm::mc_add_device);
+  m.def("mc_bind", &sfvmm::mc_bind);
+  m.def("mc_unbind", &sfvmm::mc_unbind);
+  m.def("memset_d8", [](uintptr_t p, int value, size_t bytes) { ck(cudaMemset(P<void>(p), value, bytes), "cudaMemset"); });
 
   m.def("ipc_alloc", &ipc_alloc);
   m.def("ipc_free", &ipc_free);

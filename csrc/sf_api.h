@@ -25,6 +25,16 @@ enum SfLockMode { SF_LOCK_NONE = 0 /* Hogwild */, SF_LOCK_RW = 1 /* writer-prior
 // ---------------------------------------------------------------------------
 // GEMM
 // ---------------------------------------------------------------------------
+// Sharded master: the flat parameter state is partitioned by push tile (32 x 64 elements of one variable); shard r
+// (living on GPU r) owns push tiles [bounds[r], bounds[r + 1]).  A worker's gradient tile is written straight into its
+// mailbox on the owning GPU (peer-mapped NVLink stores from the wgrad epilogue: the "push" is fused into the GEMM).
+#define SF_MAX_SHARDS 8
+struct SfRoute {
+  int n_shards;
+  int bounds[SF_MAX_SHARDS + 1];
+  float* mailbox[SF_MAX_SHARDS];  // this worker's mailbox on every shard owner (flat gradient layout)
+};
+
 struct SfGemmEpilogue {
   float* out_f32;                 // [M, ld_f32] optional
   __nv_bfloat16* out_bf16;        // [M, ld_bf16] optional (ld multiple of 8, pad columns get 0)
@@ -45,9 +55,16 @@ struct SfGemmEpilogue {
   const float* target;            // [M, ld_target] labels (one-hot / soft) or regression targets
   int ld_target;
   float* loss;                    // scalar accumulator (mean loss)
+  // sharded push fused into a wgrad epilogue: when `route` is set the fp32 output element (row, col) is stored to
+  // route->mailbox[owner] + route_off + row * ld_f32 + col, owner = shard of push tile
+  // route_tile0 + (row / 32) * route_tiles_c + col / 64 (out_f32 is ignored).
+  const SfRoute* route;           // device memory
+  int route_tile0, route_tiles_c;
+  long long route_off;
 };
 
 enum SfLossMode { SF_LOSS_NONE = 0, SF_LOSS_SOFTMAX_XENT = 1, SF_LOSS_MSE = 2 };
+
 
 struct SfGemm {
   CUtensorMap tmA, tmB;           // filled by sf_gemm_prepare
@@ -190,6 +207,9 @@ struct SfPushArgs {
   int n_vec_pub;                  // vec_offset; the worker-applied push writes both copies, the applier one per pass
   long long vec_offset;
   int shadow_is_mc;
+  float* vec_dst[8];              // sharded master: fp32 publish of the 1-D variables into every replica (one multicast
+  int n_vec_dst;                  // alias when shadow_is_mc); indexed from vec_offset.  0 = use vec_pub
+  int mb_zero;                    // applier: zero the consumed mailbox elements (accumulating wgrad epilogues add into them)
   float* grad;                    // local flat gradient (consumed, then zeroed for the next step)
   float* loss_acc;                // local: loss accumulated by the loss kernel (consumed + zeroed)
   float* loss_out;                // last step's loss for the host to read (device or pinned host memory)
@@ -280,8 +300,66 @@ struct SfApplierArgs {
   __nv_bfloat16* shadow_alt;      // and (shadow_alt, vec_pub_alt); SF_CTRL_PUB bit 31 names the complete one
   float* vec_pub_alt;
   int max_batch;                  // pushes fused into one pass over the state (1..8; 0 = 8)
+  // ---- sharded master: this applier owns push tiles [tile_begin, tile_end) (0, 0 = all) ----
+  int tile_begin, tile_end;
+  uint32_t* ack[8];               // per worker: APPLIED word of THIS shard inside the worker's own memory (peer mapped);
+                                  // nullptr = acknowledge through flags[w][SF_MB_APPLIED] only
+  // seqlock stamps of this shard in every replica's publish segment: begin is bumped before the first publish store of a
+  // pass, end after the last one; a reader's snapshot of the shard is consistent iff it read end == e before and
+  // begin == e after copying.  n_ver = 1 + ver_mc: one multimem.st reaches every replica; else one store per peer.
+  uint32_t* ver_begin[8];
+  uint32_t* ver_end[8];
+  int n_ver;
+  int ver_mc;
 };
 int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// Sharded master, worker side.
+// sync_pull: the step's "pull".  Per shard: wait until that shard's applier has acknowledged this worker's last post
+// (read-your-writes, a LOCAL spin: the applier stores the acknowledgement into this worker's memory), then - lock mode -
+// take a consistent snapshot of the shard's slice of the multicast-fed inbox replica into the working replica
+// (seqlock; all CTAs of a shard agree on one version).  Hogwild: no copy at all, the GEMMs read the inbox in place.
+// post_flags: the step's "push" epilogue.  The wgrad epilogues already stored the matrix gradients into the owners'
+// mailboxes; this forwards the (tiny) 1-D tail, then publishes the post with one release store per shard.
+// ---------------------------------------------------------------------------
+struct SfSyncPullArgs {
+  int n_shards;
+  int bounds[SF_MAX_SHARDS + 1];
+  const uint32_t* applied;        // local: word r * 16 = APPLIED sequence of shard r for this worker
+  const uint32_t* my_posted;      // local: sequence number of my last post
+  int copy;                       // 1: snapshot inbox -> working replica
+  const uint32_t* ver_begin;      // local inbox stamps: word r * ver_stride
+  const uint32_t* ver_end;
+  int ver_stride;
+  const __nv_bfloat16* src;       // inbox publish buffer (local copy fed by the appliers' multicast stores)
+  __nv_bfloat16* dst;             // working replica
+  const float* src_vec;           // inbox fp32 copy of the 1-D tail (indexed from vec_offset)
+  float* dst_vec;
+  long long vec_offset;
+  const SfTensorSeg* segs;        // device tables
+  const int32_t* tile_map;
+  int ctas_per_shard;
+  uint32_t* sync;                 // local: 8 words per shard (arrivals, min version, max version, result, round)
+};
+int sf_sync_pull_launch(const SfSyncPullArgs* a, cudaStream_t st);
+
+struct SfPostFlagsArgs {
+  int n_shards;
+  int bounds[SF_MAX_SHARDS + 1];
+  uint32_t* posted[SF_MAX_SHARDS];   // POSTED word of this worker on every shard owner (peer mapped)
+  float* mailbox[SF_MAX_SHARDS];     // this worker's mailbox on every shard owner
+  float* grad;                       // local flat gradient buffer (only the 1-D tail is accumulated here)
+  const long long* vec_tiles;        // device: [n_vec_tiles][3] = (push tile index, flat element offset, count <= 64)
+  int n_vec_tiles;
+  float* loss_acc; float* loss_out;
+  unsigned int* done_dev;
+  uint32_t* my_posted;               // local sequence word (incremented here)
+  int drop;                          // fault injection: consume the gradient, post nothing
+  long long total;                   // mailbox elements (drop + accumulate mode re-zeroes the mailboxes)
+  int mb_zero;
+};
+int sf_post_flags_launch(const SfPostFlagsArgs* a, cudaStream_t st);
 int sf_preload_kernels();
 
 // host-visible lock helpers for tests (single-thread kernels)

@@ -417,6 +417,7 @@ class DeviceWorker:
             self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result, built.idx)
             self._keep.append(built.keep)
             self.launches_per_step = len(built.plan)
+            self._last_names = list(built.plan.names())
         if key not in self._plans and fetch_slots > 0:
             built = plan_builder.build(self, B, train=True, with_pull=with_pull, with_push=with_push, inputs=self.input_set(B, slot),
                                        fetch=dict(args=self.fetch_args(B, (slot + 1) % fetch_slots),
@@ -425,12 +426,14 @@ class DeviceWorker:
             self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result)
             self._keep.append(built.keep)
             self.launches_per_step = len(built.plan)
+            self._last_names = list(built.plan.names())
         if key not in self._plans:
             built = plan_builder.build(self, B, train=True, with_pull=with_pull, with_push=with_push)
             self._plans[key] = built.plan
             self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result)
             self._keep.append(built.keep)
             self.launches_per_step = len(built.plan)
+            self._last_names = list(built.plan.names())
         return self._plans[key], self._bufs[key]
 
     def build_forward_plan(self, B: int, upto: Optional[int] = None, post: Optional[str] = None, with_loss: bool = False,
@@ -497,6 +500,10 @@ class DeviceWorker:
             if time.time() - t0 > timeout_s:
                 raise TimeoutError(f"applier did not consume post {posted} of worker {self.worker_index} (applied={applied})")
             time.sleep(0.0005)
+
+    def last_plan_names(self) -> List[str]:
+        """Kernel names (``name@branch``) of the most recently built training plan."""
+        return list(getattr(self, "_last_names", []))
 
     def need_w_map(self) -> Tuple[Dict[str, bool], Dict[str, bool]]:
         return plan_publish_needs(self.plan)

@@ -165,6 +165,15 @@ class TrainingSession:
 
         return (self.pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")) == "copy"
 
+    def master_desc(self) -> str:
+        """One-line description of where the master state lives (goes into benchmark / log records)."""
+        if self.engine_kind != "b200":
+            return "host parameter server"
+        n = self.ctx.world if self.ctx.world > 1 else len(self.local_devices())
+        if self.push_mode == "sharded":
+            return f"master sharded over {n} gpus, one applier per shard, multicast publish"
+        return "master on gpu0" + (", mailbox + applier" if self.push_mode == "served" else ", worker-applied push")
+
     def quiesce(self) -> None:
         """Collective: drain every worker, stop the applier, do a genuine device-wide ``torch.cuda.synchronize()``
         and bring the applier back.  Benchmarks bracket their timed regions with this (a device-wide synchronise

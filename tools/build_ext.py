@@ -83,7 +83,7 @@ def build(verbose_ptxas: bool = False, only: str | None = None) -> dict[str, Pat
     with ThreadPoolExecutor(max_workers=4) as ex:
         if only in (None, "cuda"):
             jobs["kernels"] = ex.submit(_compile_cuda, verbose_ptxas)
-            jobs["runtime"] = ex.submit(_compile_cxx, "runtime", [CSRC / "runtime.cpp", CSRC / "sf_api.h"])
+            jobs["runtime"] = ex.submit(_compile_cxx, "runtime", [CSRC / "runtime.cpp", CSRC / "sf_api.h", CSRC / "vmm.h"])
         if only in (None, "host") and (CSRC / "hostlib.cpp").exists():
             jobs["hostlib"] = ex.submit(_compile_cxx, "hostlib", [CSRC / "hostlib.cpp"])
         objs = {k: f.result() for k, f in jobs.items()}
