@@ -166,6 +166,12 @@ def run_ours(args, ctx) -> dict:
     sus_ms, _ = timed(eng_r, Ks, W + K)
     last_loss = eng_r.last_loss()
     sess.quiesce()
+    # exposed push / pull per step, measured on the device (%globaltimer) inside the pull / applier kernels
+    exposed = None
+    if getattr(eng.w, "sharded", False):
+        mine = dict(eng.w.exposed_latency(), **{"applier_" + k: v for k, v in sess.master.applier_latency().items()})
+        allr = D.all_gather_object(ctx, mine)
+        exposed = {k: max(r.get(k, 0) for r in allr) for k in mine}
     clocks = sampler.stop() if sampler else {}
     counters = sess.counters()
     w = eng.w
@@ -186,6 +192,7 @@ def run_ours(args, ctx) -> dict:
                 "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": int(d2h_per_step), "wall_ms_per_step": wall_ms / K,
                 "host_us_per_step": host_us, "final_loss": e2e_loss},
         "sustained": {"steps": Ks, "value": ctx.world * BATCH * Ks / (sus_ms / 1e3), "ms_per_step": sus_ms / Ks},
+        "exposed_push_pull_us_per_step": exposed,
         "gpu_launches": int(launches * K * ctx.world),
         "clocks": clocks, "final_loss": last_loss, "master_counters": counters,
     }

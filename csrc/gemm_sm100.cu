@@ -62,6 +62,21 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
     }
+    if (ep.drop_keep > 0.f && ep.drop_keep < 1.f) {
+      // fused dropout: keep with probability drop_keep, scale the survivors by 1 / drop_keep
+      const float inv_keep = 1.f / ep.drop_keep;
+      const uint32_t thr = static_cast<uint32_t>(fminf(ep.drop_keep * 4294967296.f, 4294967040.f));
+      const uint32_t stepc = ep.drop_ctr != nullptr ? *ep.drop_ctr : 0u;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint4 rnd = philox4x32_10(make_uint4(static_cast<uint32_t>(row), static_cast<uint32_t>(col0 >> 2) + g, stepc, ep.drop_stream),
+                                        make_uint2(ep.drop_seed, 0x5F3759DFu));
+        f[4 * g + 0] = rnd.x < thr ? f[4 * g + 0] * inv_keep : 0.f;
+        f[4 * g + 1] = rnd.y < thr ? f[4 * g + 1] * inv_keep : 0.f;
+        f[4 * g + 2] = rnd.z < thr ? f[4 * g + 2] * inv_keep : 0.f;
+        f[4 * g + 3] = rnd.w < thr ? f[4 * g + 3] * inv_keep : 0.f;
+      }
+    }
     if (kLoss && ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
       // whole row lives in this thread (host guarantees N <= 32): softmax + CE + gradient in registers
       float ysum = 0.f, zy = 0.f, mx = -INFINITY;
@@ -115,8 +130,15 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             const float2 a2 = __bfloat1622float2(h[t]);
-            f[g * 8 + 2 * t] *= act_bwd_from_out(a2.x, ep.aux_act);
-            f[g * 8 + 2 * t + 1] *= act_bwd_from_out(a2.y, ep.aux_act);
+            if (ep.aux_keep > 0.f && ep.aux_keep < 1.f) {
+              // aux = act(z) * mask / keep: the dropout mask is (aux != 0), the activation output is aux * keep
+              const float ik = 1.f / ep.aux_keep;
+              f[g * 8 + 2 * t] *= a2.x != 0.f ? act_bwd_from_out(a2.x * ep.aux_keep, ep.aux_act) * ik : 0.f;
+              f[g * 8 + 2 * t + 1] *= a2.y != 0.f ? act_bwd_from_out(a2.y * ep.aux_keep, ep.aux_act) * ik : 0.f;
+            } else {
+              f[g * 8 + 2 * t] *= act_bwd_from_out(a2.x, ep.aux_act);
+              f[g * 8 + 2 * t + 1] *= act_bwd_from_out(a2.y, ep.aux_act);
+            }
           }
         }
       }

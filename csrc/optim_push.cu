@@ -23,6 +23,7 @@ constexpr uint32_t kLockWriter = 1u << 16;
 constexpr uint32_t kLockWaitOne = 1u << 17;
 constexpr uint32_t kLockReaders = 0xFFFFu;
 constexpr unsigned long long kLockTimeoutNs = 20ull * 1000 * 1000 * 1000;  // 20 s
+constexpr unsigned long long kStaleReaderNs = 2ull * 1000 * 1000 * 1000;   // 2 s: a registered pull that never finishes is dead
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
@@ -685,7 +686,15 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
               const unsigned long long t0 = gtime_ns();
               uint32_t pub;
               while (((pub = ld_acquire_sys(a.push.ctrl + SF_CTRL_PUB)) & 0xFFFFu) != 0u) {
-                if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x409);
+                if (gtime_ns() - t0 > kStaleReaderNs) {
+                  // watchdog: a pull registered and never deregistered (its worker died mid-pull).  Drop the stale
+                  // registrations instead of stalling every other worker: clear the reader count, record the event
+                  // (the reference tolerates dead workers the same way: the server simply stops hearing from them).
+                  (void)atomicAnd(a.push.ctrl + SF_CTRL_PUB, 0xFFFF0000u);
+                  lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_ERRORS, 1u);
+                  pub = ld_acquire_sys(a.push.ctrl + SF_CTRL_PUB);
+                  break;
+                }
               }
               buf = (pub >> 31) ^ 1u;
             }
@@ -697,6 +706,7 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
               asm volatile("fence.acq_rel.sys;" ::: "memory");
             }
           }
+          if (a.stats != nullptr) a.sync[8] = static_cast<uint32_t>(gtime_ns()), a.sync[9] = static_cast<uint32_t>(gtime_ns() >> 32);
           a.sync[1] = m_ready;
           a.sync[2] = t;
           a.sync[5] = buf;
@@ -748,6 +758,7 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         while (ld_acquire_gpu(a.sync + 3) != gridDim.x) {
           if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x407);
         }
+        const unsigned long long t_tiles = a.stats != nullptr ? gtime_ns() : 0ull;
         a.sync[3] = 0;                                  // everybody has arrived; the next decision is published after this
         a.sync[4] = static_cast<uint32_t>(32 - __clz(mask));     // cursor: one past the highest worker served
         // the freshly written buffer becomes the current one (release: after every CTA's publish stores, which the
@@ -765,6 +776,13 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_PUSHES, static_cast<uint32_t>(n));
         lk_red_relaxed<SYS>(a.push.ctrl + SF_CTRL_VERSION, static_cast<uint32_t>(n));
         if (locked) rw_release_write<SYS>(a.push.ctrl + SF_CTRL_LOCK);
+        if (a.stats != nullptr) {
+          const unsigned long long t_dec = static_cast<unsigned long long>(a.sync[8]) | (static_cast<unsigned long long>(a.sync[9]) << 32);
+          a.stats[0] += t_tiles - t_dec;
+          a.stats[2] += 1ull;
+          a.stats[3] += static_cast<unsigned long long>(n);
+          a.sync[10] = static_cast<uint32_t>(t_dec), a.sync[11] = static_cast<uint32_t>(t_dec >> 32);
+        }
       }
       __syncwarp();
       // lane w acknowledges worker w (release: ordered after lane 0's acquire of the done counter by the warp barrier)
@@ -775,6 +793,13 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         if (a.ack[tid] != nullptr) {
           asm volatile("fence.acq_rel.sys;" ::: "memory");
           st_release_sys(a.ack[tid], posted);
+        }
+      }
+      if (a.stats != nullptr) {
+        __syncwarp();
+        if (tid == 0) {
+          const unsigned long long t_dec = static_cast<unsigned long long>(a.sync[10]) | (static_cast<unsigned long long>(a.sync[11]) << 32);
+          a.stats[1] += gtime_ns() - t_dec;
         }
       }
     }
@@ -793,28 +818,47 @@ __device__ __forceinline__ uint4 ld_local_u4(const uint4* p) {
   return r;
 }
 
-// copy the publish slices (W block, W^T block, fp32 tail elements) of one 32 x 64 push tile: inbox -> working replica
-__device__ __forceinline__ void copy_tile_publish(const SfSyncPullArgs& a, int tile) {
+// copy the publish slices (W block, W^T block, fp32 tail elements) of up to kCopyBatch push tiles: inbox -> working
+// replica.  All loads of the batch are issued before the first store (the copy is latency-, not bandwidth-bound).
+constexpr int kCopyBatch = 4;
+__device__ __forceinline__ void copy_tiles_publish(const SfSyncPullArgs& a, int tile0, int tile_end, int stride) {
   const int tid = threadIdx.x;
-  const SfTensorSeg sg = a.segs[a.tile_map[tile * 3 + 0]];
-  const int r0 = a.tile_map[tile * 3 + 1] * kTileR, c0 = a.tile_map[tile * 3 + 2] * kTileC;
-  if (sg.w_off >= 0) {
-    const int row = r0 + (tid >> 3), col = c0 + (tid & 7) * 8;
-    if (row < sg.rows && col < sg.w_ld) {
-      const int64_t o = sg.w_off + static_cast<int64_t>(row) * sg.w_ld + col;
-      *reinterpret_cast<uint4*>(a.dst + o) = ld_local_u4(reinterpret_cast<const uint4*>(a.src + o));
+  uint4 vw[kCopyBatch], vt[kCopyBatch];
+  float vv[kCopyBatch];
+  int64_t ow[kCopyBatch], ot[kCopyBatch];
+  long long ov[kCopyBatch];
+#pragma unroll
+  for (int b = 0; b < kCopyBatch; ++b) {
+    const int tile = tile0 + b * stride;
+    ow[b] = ot[b] = -1;
+    ov[b] = -1;
+    if (tile >= tile_end) continue;
+    const SfTensorSeg sg = a.segs[a.tile_map[tile * 3 + 0]];
+    const int r0 = a.tile_map[tile * 3 + 1] * kTileR, c0 = a.tile_map[tile * 3 + 2] * kTileC;
+    if (sg.w_off >= 0) {
+      const int row = r0 + (tid >> 3), col = c0 + (tid & 7) * 8;
+      if (row < sg.rows && col < sg.w_ld) {
+        ow[b] = sg.w_off + static_cast<int64_t>(row) * sg.w_ld + col;
+        vw[b] = ld_local_u4(reinterpret_cast<const uint4*>(a.src + ow[b]));
+      }
+    }
+    if (sg.wt_off >= 0) {
+      const int trow = c0 + (tid >> 2), el = r0 + (tid & 3) * 8;
+      if (trow < sg.cols && el < sg.wt_ld) {
+        ot[b] = sg.wt_off + static_cast<int64_t>(trow) * sg.wt_ld + el;
+        vt[b] = ld_local_u4(reinterpret_cast<const uint4*>(a.src + ot[b]));
+      }
+    }
+    if (sg.rows == 1 && a.dst_vec != nullptr && tid < kTileC && c0 + tid < sg.cols) {
+      ov[b] = sg.offset + c0 + tid - a.vec_offset;
+      vv[b] = ld_relaxed_sys_f32(a.src_vec + ov[b]);
     }
   }
-  if (sg.wt_off >= 0) {
-    const int trow = c0 + (tid >> 2), el = r0 + (tid & 3) * 8;
-    if (trow < sg.cols && el < sg.wt_ld) {
-      const int64_t o = sg.wt_off + static_cast<int64_t>(trow) * sg.wt_ld + el;
-      *reinterpret_cast<uint4*>(a.dst + o) = ld_local_u4(reinterpret_cast<const uint4*>(a.src + o));
-    }
-  }
-  if (sg.rows == 1 && a.dst_vec != nullptr && tid < kTileC && c0 + tid < sg.cols) {
-    const long long vi = sg.offset + c0 + tid - a.vec_offset;
-    a.dst_vec[vi] = ld_relaxed_sys_f32(a.src_vec + vi);
+#pragma unroll
+  for (int b = 0; b < kCopyBatch; ++b) {
+    if (ow[b] >= 0) *reinterpret_cast<uint4*>(a.dst + ow[b]) = vw[b];
+    if (ot[b] >= 0) *reinterpret_cast<uint4*>(a.dst + ot[b]) = vt[b];
+    if (ov[b] >= 0) a.dst_vec[ov[b]] = vv[b];
   }
 }
 
@@ -830,12 +874,22 @@ sync_pull_kernel(const SfSyncPullArgs a) {
   const int cps = a.ctas_per_shard;
   const int shard = blockIdx.x / cps, part = blockIdx.x % cps;
   // ---- read-your-writes: this shard's applier has consumed my last post (it acknowledges into MY memory) ----
+  unsigned long long t_seen = 0;
   if (tid == 0) {
     const uint32_t want = *a.my_posted;
     const unsigned long long t0 = gtime_ns();
     while (static_cast<int32_t>(ld_acquire_sys(a.applied + shard * 16) - want) < 0) {
       __nanosleep(32);
       if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x405);
+    }
+    if (a.stats != nullptr && part == 0) {
+      t_seen = gtime_ns();
+      const unsigned long long t_post = a.stats[0];
+      if (t_post != 0 && t0 > t_post) {
+        a.stats[8 + 4 * shard] += t0 - t_post;
+        a.stats[9 + 4 * shard] += t_seen - t0;
+        a.stats[11 + 4 * shard] += 1ull;
+      }
     }
   }
   __syncthreads();
@@ -856,7 +910,8 @@ sync_pull_kernel(const SfSyncPullArgs a) {
       s_e = e;
     }
     __syncthreads();
-    for (int tile = a.bounds[shard] + part; tile < a.bounds[shard + 1]; tile += cps) copy_tile_publish(a, tile);
+    for (int tile = a.bounds[shard] + part; tile < a.bounds[shard + 1]; tile += cps * kCopyBatch)
+      copy_tiles_publish(a, tile, a.bounds[shard + 1], cps);
     __syncthreads();
     if (tid == 0) {
       asm volatile("fence.acq_rel.sys;" ::: "memory");
@@ -890,6 +945,7 @@ sync_pull_kernel(const SfSyncPullArgs a) {
     if (s_ok) break;
     if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40C);
   }
+  if (tid == 0 && a.stats != nullptr && part == 0 && t_seen != 0) a.stats[10 + 4 * shard] += gtime_ns() - t_seen;
   trace.end(KID_PULL);
 }
 
@@ -935,6 +991,12 @@ post_flags_kernel(const SfPostFlagsArgs a) {
   }
   __syncthreads();
   if (!a.drop && tid == 0) *a.my_posted = *a.my_posted + 1;
+  if (tid == 0 && a.stats != nullptr) a.stats[0] = gtime_ns();
+  if (tid == 0 && a.heartbeat != nullptr) {
+    // liveness: (%globaltimer ns, steps so far) in this worker's symmetric segment, readable by every peer / the host
+    a.heartbeat[0] = gtime_ns();
+    a.heartbeat[1] = a.heartbeat[1] + 1ull;
+  }
   trace.end(KID_PUSH);
 }
 

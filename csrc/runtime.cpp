@@ -7,7 +7,10 @@
 #include <pybind11/numpy.h>
 #include <pybind11/stl.h>
 
+#include <array>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
@@ -86,6 +89,11 @@ struct Gemm {
     g.ep.target = P<const float>(getd<uintptr_t>(d, "target", 0));
     g.ep.ld_target = getd<int>(d, "ld_target", 0);
     g.ep.loss = P<float>(getd<uintptr_t>(d, "loss", 0));
+    g.ep.drop_keep = getd<float>(d, "drop_keep", 0.0f);
+    g.ep.drop_seed = getd<unsigned int>(d, "drop_seed", 0u);
+    g.ep.drop_stream = getd<unsigned int>(d, "drop_stream", 0u);
+    g.ep.drop_ctr = P<const unsigned int>(getd<uintptr_t>(d, "drop_ctr", 0));
+    g.ep.aux_keep = getd<float>(d, "aux_keep", 0.0f);
     g.ep.route = P<const SfRoute>(getd<uintptr_t>(d, "route", 0));
     g.ep.route_tile0 = getd<int>(d, "route_tile0", 0);
     g.ep.route_tiles_c = getd<int>(d, "route_tiles_c", 1);
@@ -300,6 +308,7 @@ SfSyncPullArgs parse_sync_pull(const py::dict& d) {
   a.tile_map = P<const int32_t>(getd<uintptr_t>(d, "tile_map", 0));
   a.ctas_per_shard = getd<int>(d, "ctas_per_shard", 1);
   a.sync = P<uint32_t>(getd<uintptr_t>(d, "sync", 0));
+  a.stats = P<unsigned long long>(getd<uintptr_t>(d, "stats", 0));
   if (!a.applied || !a.my_posted) throw std::runtime_error("sync_pull: applied / my_posted are required");
   if (a.copy && (!a.ver_begin || !a.ver_end || !a.src || !a.dst || !a.segs || !a.tile_map || !a.sync))
     throw std::runtime_error("sync_pull: copy needs ver_begin/ver_end/src/dst/segs/tile_map/sync");
@@ -327,6 +336,8 @@ SfPostFlagsArgs parse_post_flags(const py::dict& d) {
   a.drop = getd<int>(d, "drop", 0);
   a.total = getd<long long>(d, "total", 0);
   a.mb_zero = getd<int>(d, "mb_zero", 0);
+  a.heartbeat = P<unsigned long long>(getd<uintptr_t>(d, "heartbeat", 0));
+  a.stats = P<unsigned long long>(getd<uintptr_t>(d, "stats", 0));
   if (!a.grad || !a.my_posted || (a.n_vec_tiles > 0 && !a.vec_tiles)) throw std::runtime_error("post_flags: grad / my_posted / vec_tiles are required");
   return a;
 }
@@ -383,8 +394,7 @@ class Plan {
   ~Plan() {
     reset_graph();
     for (int i = 0; i < kMaxBranches; ++i) {
-      if (side_[i]) cudaStreamDestroy(side_[i]);
-      if (ev_[i]) cudaEventDestroy(ev_[i]);
+      if (ev_[i]) cudaEventDestroy(ev_[i]);      // branch streams are pooled per main stream and live for the process
     }
     if (ev_main_) cudaEventDestroy(ev_main_);
   }
@@ -423,6 +433,7 @@ class Plan {
 
   void run(uintptr_t stream) {
     cudaStream_t main = S(stream);
+    cur_main_ = main;
     for (auto& it : items_) {
       if (it.kind == 0) {
         const int rc = it.op(it.branch ? side(it.branch) : main);
@@ -481,10 +492,20 @@ class Plan {
     items_.push_back(Item{name, nullptr, b, kind});
     reset_graph();
   }
-  cudaStream_t side(int b) {
-    if (!side_[b]) ck(cudaStreamCreateWithFlags(&side_[b], cudaStreamNonBlocking), "cudaStreamCreate(side)");
-    return side_[b];
+  // Branch streams are POOLED per main stream (not per plan): a worker owns a handful of plans (staging slots, batch
+  // shapes, forward-only variants) and the GPU has a limited number of hardware launch queues
+  // (CUDA_DEVICE_MAX_CONNECTIONS): when more streams than queues exist, unrelated streams share a queue, and a kernel
+  // that spins on a flag (a pull waiting for an applier) at the head of a queue blocks the launch of the very applier
+  // kernel it is waiting for, if that one was mapped to the same queue.  Few streams -> no aliasing.
+  static cudaStream_t pooled_side(cudaStream_t main, int b) {
+    static std::mutex mu;
+    static std::map<cudaStream_t, std::array<cudaStream_t, kMaxBranches>> pool;
+    std::lock_guard<std::mutex> lk(mu);
+    auto& arr = pool[main];          // value-initialised to nullptr on first use
+    if (!arr[b]) ck(cudaStreamCreateWithFlags(&arr[b], cudaStreamNonBlocking), "cudaStreamCreate(side)");
+    return arr[b];
   }
+  cudaStream_t side(int b) { return pooled_side(cur_main_, b); }
   void reset_graph() {
     if (exec_) { cudaGraphExecDestroy(exec_); exec_ = nullptr; }
     if (graph_) { cudaGraphDestroy(graph_); graph_ = nullptr; }
@@ -492,6 +513,7 @@ class Plan {
   std::vector<Item> items_;
   int cur_branch_ = 0;
   cudaStream_t side_[kMaxBranches];
+  cudaStream_t cur_main_ = nullptr;
   cudaEvent_t ev_[kMaxBranches];
   cudaEvent_t ev_main_ = nullptr;
   cudaGraph_t graph_ = nullptr;
@@ -666,8 +688,12 @@ class StepDriver {
       const auto t0 = clk::now();
       if (e.primed && e.pending >= 0) wait_done(e);
       const auto t1 = clk::now();
-      ck(cudaMemcpyAsync(e.x_stage, perm + sp[k], static_cast<size_t>(e.batch) * sizeof(int32_t), cudaMemcpyDeviceToDevice, compute_),
+      // the row ids of step k are staged on the COPY stream (the slot is free: its previous step has retired), so the
+      // copy overlaps the steps still in flight and the step graph only waits on an event that has usually fired already
+      ck(cudaMemcpyAsync(e.x_stage, perm + sp[k], static_cast<size_t>(e.batch) * sizeof(int32_t), cudaMemcpyDeviceToDevice, copy_),
          "cudaMemcpyAsync(minibatch row ids)");
+      ck(cudaEventRecord(e.ready, copy_), "cudaEventRecord(ready)");
+      ck(cudaStreamWaitEvent(compute_, e.ready, 0), "cudaStreamWaitEvent");
       const auto t2 = clk::now();
       e.plan->replay(reinterpret_cast<uintptr_t>(compute_));
       const auto t3 = clk::now();
@@ -815,6 +841,7 @@ class Applier {
       args_.n_ver = static_cast<int>(vb.size());
       for (size_t i = 0; i < vb.size(); ++i) { args_.ver_begin[i] = P<uint32_t>(vb[i]); args_.ver_end[i] = P<uint32_t>(ve[i]); }
       args_.ver_mc = getd<int>(shard, "ver_mc", 0);
+      args_.stats = P<unsigned long long>(getd<uintptr_t>(shard, "stats", 0));
     }
     ck(cudaGetDevice(&device_), "cudaGetDevice");
     int lo = 0, hi = 0;

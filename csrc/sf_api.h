@@ -61,6 +61,15 @@ struct SfGemmEpilogue {
   const SfRoute* route;           // device memory
   int route_tile0, route_tiles_c;
   long long route_off;
+  // fused dropout (reference: the tfDropout keep-prob placeholder of tf.nn.dropout, ml_util.py:70-71): after the
+  // activation every element is kept with probability drop_keep and scaled by 1 / drop_keep.  The mask is
+  // Philox4x32-10 keyed by drop_seed over the counter (row, column / 4, *drop_ctr, drop_stream), so it is a pure
+  // function of (sample row, feature, step number, layer) - no mask tensor is stored: the backward pass recovers it
+  // from the stored activation (aux_keep: aux holds act(z) * mask / keep, so mask = aux != 0).
+  float drop_keep;                // 0 or >= 1: no dropout
+  unsigned int drop_seed, drop_stream;
+  const unsigned int* drop_ctr;   // device word that changes every step (nullptr: 0)
+  float aux_keep;                 // dgrad: keep probability of the dropout that produced aux (0 = none)
 };
 
 enum SfLossMode { SF_LOSS_NONE = 0, SF_LOSS_SOFTMAX_XENT = 1, SF_LOSS_MSE = 2 };
@@ -311,6 +320,7 @@ struct SfApplierArgs {
   uint32_t* ver_end[8];
   int n_ver;
   int ver_mc;
+  unsigned long long* stats;      // optional: [0] sum(ns decide -> tiles done), [1] sum(ns decide -> acknowledged), [2] passes, [3] pushes
 };
 int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st);
 
@@ -341,6 +351,9 @@ struct SfSyncPullArgs {
   const int32_t* tile_map;
   int ctas_per_shard;
   uint32_t* sync;                 // local: 8 words per shard (arrivals, min version, max version, result, round)
+  // optional latency accounting (%globaltimer ns): [0] = time of my last post (written by post_flags), per shard s:
+  // [8 + 4s] sum(wait start - post), [9 + 4s] sum(ack seen - wait start), [10 + 4s] sum(snapshot done - ack seen), [11 + 4s] steps
+  unsigned long long* stats;
 };
 int sf_sync_pull_launch(const SfSyncPullArgs* a, cudaStream_t st);
 
@@ -358,6 +371,8 @@ struct SfPostFlagsArgs {
   int drop;                          // fault injection: consume the gradient, post nothing
   long long total;                   // mailbox elements (drop + accumulate mode re-zeroes the mailboxes)
   int mb_zero;
+  unsigned long long* heartbeat;     // optional: 2 words in this worker's symmetric segment (time of last post, posts)
+  unsigned long long* stats;         // optional: [0] = %globaltimer of this post (see SfSyncPullArgs.stats)
 };
 int sf_post_flags_launch(const SfPostFlagsArgs* a, cudaStream_t st);
 int sf_preload_kernels();

@@ -13,7 +13,14 @@ Layout
 ``utils/``     timing, clocks, tracing, metrics, fault injection
 ``csrc/``      (repo root) sm_100a kernels + C++ runtime
 """
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+import os as _os
+
+# One hardware launch queue per stream (the default is 8): device-side waits (a worker's pull spinning until the shard
+# appliers acknowledge its push) must never share a queue with the applier kernels they wait for.  Only effective when
+# set before the CUDA context is created, which importing this package normally precedes.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from .graph_utils import (build_adadelta_config, build_adagrad_config, build_adam_config, build_gradient_descent,  # noqa: F401
                           build_graph, build_momentum_config, build_rmsprop_config)

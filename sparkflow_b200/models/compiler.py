@@ -3,9 +3,10 @@
 The reference runs whatever graph the user serialised through a TF session.  The B200 engine
 instead executes a *compiled* plan: the forward chain between ``tfInput`` and the loss is pattern-
 matched into dense / conv / pool / reshape layers with fused bias+activation, the loss into
-softmax-cross-entropy or mean-squared-error, and ``tfOutput`` into "activation of layer k"
-(+ optional ArgMax / Softmax).  Graphs outside this family (custom losses, dropout, exotic ops) are
-reported as unsupported so the caller can use the generic interpreter engine instead.
+softmax-cross-entropy or mean-squared-error, ``tf.nn.dropout`` / ``tf.layers.dropout`` after a dense layer into a
+fused Philox mask in that layer's epilogue, and ``tfOutput`` into "activation of layer k" (+ optional ArgMax /
+Softmax).  Graphs outside this family (custom losses, exotic ops) are reported as unsupported so the caller can use the
+generic interpreter engine instead (loudly: a RuntimeWarning names the reason).
 
 Covers every model the reference ships: simple_dnn, cnn_example,
 autoencoder_example, the test MLPs / auto-encoder and the checkpoint fixture.
@@ -33,7 +34,8 @@ class Layer:
     in_shape: Tuple[int, ...] = ()              # per-sample shape (no batch dim)
     out_shape: Tuple[int, ...] = ()
     ksize: Tuple[int, int] = (0, 0)
-    tensors: Dict[str, str] = field(default_factory=dict)   # stage -> tensor name (linear / bias / act)
+    tensors: Dict[str, str] = field(default_factory=dict)   # stage -> tensor name (linear / bias / act / dropout)
+    dropout_keep: float = 0.0                   # dense: keep probability of a tf.nn.dropout applied to the layer's output (0 = none)
 
     @property
     def in_features(self) -> int:
@@ -86,6 +88,43 @@ def _var_of(ir: GraphIR, ref: Tuple[str, int]) -> Optional[str]:
         node = ir.nodes[node.inputs[0][0]]
         hops += 1
     return node.name if node.op in ("VariableV2", "Variable", "VarHandleOp") else None
+
+
+def _const_scalar(ir: GraphIR, ref: Tuple[str, int]) -> Optional[float]:
+    """Value of a scalar that is a Const, possibly behind Identity / PlaceholderWithDefault / `1 - rate` arithmetic."""
+    node = ir.nodes[ref[0]]
+    hops = 0
+    while node.op in ("Identity", "PlaceholderWithDefault", "Cast") and node.inputs and hops < 6:
+        node = ir.nodes[node.inputs[0][0]]
+        hops += 1
+    if node.op == "Const":
+        try:
+            return float(node.attrs["value"].reshape(-1)[0])
+        except Exception:
+            return None
+    if node.op == "Sub" and len(node.inputs) == 2:
+        a, b = _const_scalar(ir, node.inputs[0]), _const_scalar(ir, node.inputs[1])
+        return None if a is None or b is None else a - b
+    return None
+
+
+def _match_dropout(ir: GraphIR, node: Node) -> Optional[Tuple[Tuple[str, int], float]]:
+    """``tf.nn.dropout`` sub-graph: Mul(RealDiv(x, keep), Floor(Add(keep, RandomUniform(Shape(x))))) -> (x, keep)."""
+    if node.op != "Mul" or len(node.inputs) != 2:
+        return None
+    for a, b in ((node.inputs[0], node.inputs[1]), (node.inputs[1], node.inputs[0])):
+        div, flo = ir.nodes[a[0]], ir.nodes[b[0]]
+        if div.op not in ("RealDiv", "Div") or flo.op != "Floor":
+            continue
+        add = ir.nodes[flo.inputs[0][0]]
+        if add.op not in ("Add", "AddV2") or not any(ir.nodes[i[0]].op == "RandomUniform" for i in add.inputs):
+            continue
+        keep = _const_scalar(ir, div.inputs[1])
+        if keep is None:
+            raise UnsupportedGraph(f"dropout '{node.name}': keep_prob is a placeholder without a default - it is never fed during "
+                                   "training (reference: HogwildSparkModel.py never feeds tfDropout), use tf.placeholder_with_default")
+        return div.inputs[0], float(keep)
+    return None
 
 
 def _find_loss_core(ir: GraphIR, loss_ref: str) -> Tuple[str, Node]:
@@ -194,6 +233,7 @@ def compile_graph(ir: GraphIR, tf_input: str, tf_label: Optional[str], tf_output
     cur = chain_end
     pending_act: Optional[Tuple[str, str]] = None      # (act, tensor name)
     pending_bias: Optional[Tuple[str, str]] = None     # (var, tensor name)
+    pending_drop: Optional[Tuple[float, str]] = None   # (keep_prob, tensor name) of a dropout above the next layer found
     guard = 0
     while True:
         guard += 1
@@ -202,9 +242,21 @@ def compile_graph(ir: GraphIR, tf_input: str, tf_label: Optional[str], tf_output
         node = ir.nodes[cur[0]]
         tname = f"{node.name}:{cur[1]}"
         if node.name == input_node:
+            if pending_drop:
+                raise UnsupportedGraph("dropout applied directly to the input is not covered by the compiled plan")
             break
         if node.op in _PASS:
             cur = node.inputs[0]
+            continue
+        drop = _match_dropout(ir, node)
+        if drop is not None:
+            if pending_act or pending_bias or pending_drop:
+                raise UnsupportedGraph(f"dropout '{node.name}' is not directly on top of a layer output")
+            if drop[1] < 1.0:
+                if drop[1] <= 0.0:
+                    raise UnsupportedGraph("dropout with keep_prob <= 0")
+                pending_drop = (drop[1], tname)
+            cur = drop[0]
             continue
         if node.op in ("Relu", "Sigmoid", "Tanh"):
             if pending_act or pending_bias:
@@ -233,11 +285,16 @@ def compile_graph(ir: GraphIR, tf_input: str, tf_label: Optional[str], tf_output
                 tensors["bias"] = pending_bias[1]
             if pending_act:
                 tensors["act"] = pending_act[1]
+            if pending_drop:
+                tensors["dropout"] = pending_drop[1]
             layers_rev.append(Layer("dense", kernel=kvar, bias=pending_bias[0] if pending_bias else None,
-                                    act=pending_act[0] if pending_act else None, in_shape=(kin,), out_shape=(kout,), tensors=tensors))
-            pending_act = pending_bias = None
+                                    act=pending_act[0] if pending_act else None, in_shape=(kin,), out_shape=(kout,), tensors=tensors,
+                                    dropout_keep=pending_drop[0] if pending_drop else 0.0))
+            pending_act = pending_bias = pending_drop = None
             cur = node.inputs[0]
             continue
+        if pending_drop:
+            raise UnsupportedGraph(f"dropout on top of '{node.op}' ({node.name}): the compiled plan fuses dropout into dense layers only")
         if node.op == "Conv2D":
             if node.attrs.get("padding", "VALID") != "VALID" or list(node.attrs.get("strides", [1, 1, 1, 1])) != [1, 1, 1, 1] \
                     or node.attrs.get("data_format", "NHWC") != "NHWC" or list(node.attrs.get("dilations", [1, 1, 1, 1])) != [1, 1, 1, 1]:
@@ -336,6 +393,8 @@ def compile_graph(ir: GraphIR, tf_input: str, tf_label: Optional[str], tf_output
             raise UnsupportedGraph("label width does not match the network output width")
         if loss_kind == "softmax_xent" and layers[-1].act is not None:
             raise UnsupportedGraph("softmax cross-entropy expects raw logits")
+        if layers[-1].dropout_keep:
+            raise UnsupportedGraph("dropout on the network output is not covered by the compiled plan")
 
     # ---- output fetch ------------------------------------------------------------------------------
     out_spec: Optional[OutputSpec] = None
@@ -346,10 +405,10 @@ def compile_graph(ir: GraphIR, tf_input: str, tf_label: Optional[str], tf_output
             out_spec = OutputSpec(-1, "act", post)
         else:
             for i, l in enumerate(layers):
-                for stage in ("act", "bias", "linear"):
+                for stage in ("dropout", "act", "bias", "linear"):
                     if l.tensors.get(stage) == want:
                         # the fetched stage must be the layer's final stage (we do not keep pre-activations)
-                        final = "act" if l.act or l.kind in ("pool", "reshape") else ("bias" if l.bias else "linear")
+                        final = "dropout" if l.dropout_keep else ("act" if l.act or l.kind in ("pool", "reshape") else ("bias" if l.bias else "linear"))
                         if stage != final:
                             raise UnsupportedGraph(f"tfOutput '{tf_output}' fetches a pre-activation tensor")
                         out_spec = OutputSpec(i, stage, post)

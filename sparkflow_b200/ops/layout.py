@@ -125,6 +125,15 @@ class ParamLayout:
                     tiles.append((i, tr, tc))
         return np.asarray(tiles, dtype=np.int32).reshape(-1, 3)
 
+    def tile_prefix(self) -> List[int]:
+        """Index of each segment's first push tile in :meth:`tile_map` order (one extra entry: the tile count)."""
+        pre, acc = [], 0
+        for s in self.segments:
+            pre.append(acc)
+            acc += ((s.rows + TILE_R - 1) // TILE_R) * ((s.cols + TILE_C - 1) // TILE_C)
+        pre.append(acc)
+        return pre
+
     def publish_reference(self, flat: np.ndarray) -> np.ndarray:
         """What the publish buffer must contain for the given fp32 params (fp32 values, to be
         compared after bf16 rounding)."""

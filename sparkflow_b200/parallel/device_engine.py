@@ -271,6 +271,7 @@ class DeviceWorker:
         self.lock_mode = 1 if acquire_lock else 0
         self.scope_sys = 1 if shared else 0        # more than one GPU touches the master -> system-scope lock
         self.worker_index = worker_index
+        self.sharded = bool(getattr(master, "sharded", False))      # master state sharded over all GPUs (parallel/sharded.py)
         self.served = bool(master.served)          # push = post to my mailbox, the master-resident applier applies it
         self.pull_mode = pull_mode or os.environ.get("SPARKFLOW_PULL_MODE", "copy")
         # lock mode without a lock on the read side: pulls pick the complete one of two publish buffers (see start_applier)
@@ -281,6 +282,8 @@ class DeviceWorker:
                 raise RuntimeError("the applier publishes double-buffered (lock mode, replica pulls) but this worker was created with "
                                    f"pull_mode={self.pull_mode!r}, acquire_lock={acquire_lock}")
             self.use_dbuf = applier_dbuf
+        if self.sharded:
+            self.pull_mode = "copy" if self.lock_mode else "inbox"     # lock: seqlock snapshot; Hogwild: GEMMs read the inbox in place
         if self.pull_mode == "direct" and self.lock_mode:
             self.pull_mode = "copy"            # a locked pull must be a private snapshot
         self.use_graphs = use_graphs and os.environ.get("SPARKFLOW_NO_GRAPHS") != "1"
@@ -293,8 +296,37 @@ class DeviceWorker:
         dev = self.device
         lay = self.layout
         # local replica of what a pull fetches
-        self.replica = torch.zeros(lay.shadow_total, dtype=torch.bfloat16, device=dev)
-        self.vec_local = torch.zeros(max(lay.vec_count, 4), dtype=torch.float32, device=dev)
+        if self.sharded:
+            m = master
+            inbox_shadow, inbox_vec = m.view("shadow", worker_index, dev), m.view("vec", worker_index, dev)
+            if self.lock_mode:
+                self.replica, self.vec_local = inbox_shadow.clone(), inbox_vec.clone()      # working copy (pads / initial weights included)
+            else:
+                self.replica, self.vec_local = inbox_shadow, inbox_vec                       # zero-copy pull
+            self.inbox_shadow, self.inbox_vec = inbox_shadow, inbox_vec
+            # the worker's words inside its own symmetric segment: my_posted lives right behind the acknowledgement words
+            self.ack_words = m.view("ack", worker_index, dev)
+            self.my_posted = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.shard_stats = torch.zeros(64, dtype=torch.int64, device=dev)      # device-side latency accounting (SfSyncPullArgs.stats)
+            route = self.C.pack_route(m.n, m.bounds, [m.mailbox_ptr(r, worker_index) for r in range(m.n)])
+            self.route_dev = torch.frombuffer(bytearray(route), dtype=torch.uint8).to(dev)
+            vt = []
+            for i, sgm in enumerate(lay.segments):
+                if sgm.rows == 1:
+                    for tc in range((sgm.cols + 63) // 64):
+                        vt.append((m.tile_prefix[i] + tc, sgm.offset + tc * 64, min(64, sgm.cols - tc * 64)))
+            self.vec_tiles = torch.tensor(vt if vt else [(0, 0, 0)], dtype=torch.int64, device=dev)
+            self.n_vec_tiles = len(vt)
+            # snapshot pull: the copy is latency bound, so give every shard as many CTAs as it has tiles (all CTAs of the
+            # kernel must be co-resident for the per-shard version agreement: at most one CTA per SM in total)
+            tiles_per_shard = max(1, -(-m.n_tiles // m.n))
+            self.sync_cps = max(1, min(tiles_per_shard, 148 // m.n, int(os.environ.get("SPARKFLOW_PULL_CTAS_PER_SHARD", "64"))))
+            init = torch.zeros(8, 8, dtype=torch.int64)
+            init[:, 1] = 0xFFFFFFFF
+            self.sync_sp = torch.from_numpy(init.numpy().astype("uint32").view("int32").copy()).to(dev)
+        else:
+            self.replica = torch.zeros(lay.shadow_total, dtype=torch.bfloat16, device=dev)
+            self.vec_local = torch.zeros(max(lay.vec_count, 4), dtype=torch.float32, device=dev)
         self.grads = torch.zeros(lay.total, dtype=torch.float32, device=dev)
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sync_push = torch.zeros(8, dtype=torch.int32, device=dev)
@@ -336,6 +368,58 @@ class DeviceWorker:
         m = self.master
         return dict(grad=native.ptr(self.grads), mailbox=m.mailbox_ptr(self.worker_index), flags=m.flags_ptr(self.worker_index),
                     loss_acc=native.ptr(self.loss_acc), loss_out=native.ptr(loss_out), n=self.layout.total, drop=drop)
+
+    # ---- sharded master ------------------------------------------------------------------------------------
+    def _sync_pull_args(self, copy: bool) -> dict:
+        m, lay = self.master, self.layout
+        from .sharded import VER_STRIDE
+
+        stamps = m.pub_ptr(self.worker_index, m.o_stamps)
+        d = dict(n_shards=m.n, bounds=m.bounds, applied=native.ptr(self.ack_words), my_posted=native.ptr(self.my_posted),
+                 copy=1 if (copy and self.lock_mode) else 0, stats=native.ptr(self.shard_stats))
+        if d["copy"]:
+            d.update(ver_begin=stamps, ver_end=stamps + 16 * 4, ver_stride=VER_STRIDE, src=native.ptr(self.inbox_shadow), dst=native.ptr(self.replica),
+                     src_vec=native.ptr(self.inbox_vec) if lay.vec_count else 0, dst_vec=native.ptr(self.vec_local) if lay.vec_count else 0,
+                     vec_offset=lay.vec_offset, segs=native.ptr(self.segs_dev), tile_map=native.ptr(self.tile_map),
+                     ctas_per_shard=self.sync_cps, sync=native.ptr(self.sync_sp))
+        return d
+
+    def _post_flags_args(self, loss_out: torch.Tensor, drop: int = 0) -> dict:
+        m = self.master
+        return dict(n_shards=m.n, bounds=m.bounds, posted=[m.posted_ptr(r, self.worker_index) for r in range(m.n)],
+                    mailbox=[m.mailbox_ptr(r, self.worker_index) for r in range(m.n)], grad=native.ptr(self.grads),
+                    vec_tiles=native.ptr(self.vec_tiles), n_vec_tiles=self.n_vec_tiles, loss_acc=native.ptr(self.loss_acc),
+                    loss_out=native.ptr(loss_out), my_posted=native.ptr(self.my_posted), drop=drop, total=self.layout.total,
+                    mb_zero=1 if m.mb_zero else 0, heartbeat=m.heartbeat_ptr(self.worker_index), stats=native.ptr(self.shard_stats))
+
+    def exposed_latency(self, reset: bool = False) -> Dict[str, float]:
+        """Sharded master: device-measured (%globaltimer) per-step latencies of this worker, averaged since the last reset
+        and taken over the slowest shard: how long after its post the next step started waiting (`covered_us`: work that
+        hid the push), how long it then stalled for the acknowledgement (`exposed_push_us`: the exposed part of
+        push -> apply -> publish), and the snapshot copy of the pull (`exposed_pull_us`, lock mode only)."""
+        if not self.sharded:
+            return {}
+        self.stream.synchronize()
+        st = self.shard_stats.cpu().numpy()
+        out = {"covered_us": 0.0, "exposed_push_us": 0.0, "exposed_pull_us": 0.0, "steps": 0}
+        for sh in range(self.master.n):
+            n = int(st[11 + 4 * sh])
+            if n:
+                out["steps"] = max(out["steps"], n)
+                out["covered_us"] = max(out["covered_us"], st[8 + 4 * sh] / n / 1e3)
+                out["exposed_push_us"] = max(out["exposed_push_us"], st[9 + 4 * sh] / n / 1e3)
+                out["exposed_pull_us"] = max(out["exposed_pull_us"], st[10 + 4 * sh] / n / 1e3)
+        if reset:
+            with torch.cuda.stream(self.stream):
+                self.shard_stats[8:].zero_()
+            self.stream.synchronize()
+        return out
+
+    def route_args(self, seg) -> dict:
+        """Epilogue fields that send a wgrad's fp32 tiles to the owning shards' mailboxes (GEMM dict entries)."""
+        m = self.master
+        return dict(route=native.ptr(self.route_dev), route_tile0=m.tile_prefix[seg.index], route_tiles_c=(seg.cols + 63) // 64,
+                    route_off=seg.offset, ld_f32=seg.cols)
 
     def _pull_args(self) -> dict:
         lay, m = self.layout, self.master
@@ -429,6 +513,7 @@ class DeviceWorker:
             self._last_names = list(built.plan.names())
         if key not in self._plans:
             built = plan_builder.build(self, B, train=True, with_pull=with_pull, with_push=with_push)
+            self.last_debug = built.debug           # per-layer intermediate buffers of the newest plan (tests / tools)
             self._plans[key] = built.plan
             self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result)
             self._keep.append(built.keep)
@@ -486,6 +571,18 @@ class DeviceWorker:
     def drain(self, timeout_s: float = 30.0) -> None:
         """Served push: block until the applier has consumed every gradient this worker posted."""
         self.stream.synchronize()
+        if self.sharded:
+            import time
+
+            posted = int(self.my_posted[0])
+            t0 = time.time()
+            while True:
+                acks = self.ack_words.view(-1, 16)[: self.master.n, 0].cpu()
+                if all(((int(a) - posted) & 0xFFFFFFFF) < 0x80000000 for a in acks):
+                    return
+                if time.time() - t0 > timeout_s:
+                    raise TimeoutError(f"shard appliers did not consume post {posted} of worker {self.worker_index} (acks={acks.tolist()})")
+                time.sleep(0.0005)
         if not self.served:
             return
         import time

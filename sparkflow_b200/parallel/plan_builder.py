@@ -38,6 +38,7 @@ class BuiltPlan:
     result: Optional[torch.Tensor] = None
     keep: List[Any] = field(default_factory=list)
     idx: Optional[torch.Tensor] = None       # resident mode: int32 [B] row ids of the minibatch this plan trains on
+    debug: Optional[Dict[int, Dict[str, Any]]] = None     # per layer index: intermediate buffers (tests / tools)
 
 
 def check_grammar(lp: LayerPlan) -> None:
@@ -156,7 +157,18 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     wsrc = worker._weight_src()
     plan = C.Plan()
     branches = worker.use_branches and train
+    sharded = bool(getattr(worker, "sharded", False))
     do_pull = with_pull and (worker.pull_mode != "direct" or lay.vec_count > 0)
+    if sharded:
+        # the step always starts with the read-your-writes wait (it also protects the mailboxes the wgrad epilogues
+        # are about to overwrite); the seqlock snapshot is only taken when this step really pulls (lock mode)
+        do_pull = bool(train or with_pull)
+
+    def add_pull_op():
+        if sharded:
+            plan.add_sync_pull(worker._sync_pull_args(copy=with_pull))
+        else:
+            plan.add_pull(worker._pull_args(), P(worker.sync_pull), 0)
 
     layers = lp.layers
     dense_ids = [i for i, l in enumerate(layers) if l.kind == "dense"]
@@ -175,10 +187,10 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     if do_pull and branches:
         plan.fork(1)
         plan.branch(1)
-        plan.add_pull(worker._pull_args(), P(worker.sync_pull), 0)
+        add_pull_op()
         plan.branch(0)
     elif do_pull:
-        plan.add_pull(worker._pull_args(), P(worker.sync_pull), 0)
+        add_pull_op()
     first_is_dense = layers[first_trainable].kind == "dense"
     if inputs is not None:
         a0, a0T = inputs["a0"], inputs["a0T"]
@@ -203,7 +215,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     rec: Dict[int, Dict[str, Any]] = {}        # per-layer tensors needed by backward
     gemms: List[Any] = []
     # opt-in (SPARKFLOW_MEGAKERNEL=1): dense-only training steps run their whole GEMM chain as ONE persistent launch
-    use_mega = bool(train and getattr(worker, "use_mega", False) and all(l.kind == "dense" for l in layers))
+    use_mega = bool(train and getattr(worker, "use_mega", False) and not sharded and all(l.kind == "dense" for l in layers))
     mega_items: List[List[Any]] = []          # [gemm, name, deps (indices into mega_items)]
     produced: Dict[int, int] = {}             # output buffer address -> index of the GEMM that writes it
 
@@ -272,6 +284,11 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         last = i == stop_layer
         d = dict(a=P(cur["buf"]), lda=cur["ld"], b=P(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld, M=B, N=ks.cols, K=ks.rows,
                  bias=worker._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
+        if l.dropout_keep:
+            # fused Philox dropout: the mask is a function of (row, column, step counter of this plan, layer)
+            seed = (int(os.environ.get("SPARKFLOW_DROPOUT_SEED", "20260921")) ^ (0x9E3779B9 * (worker.worker_index + 1))
+                    ^ ((P(done_dev) >> 4) if done_dev is not None else 0)) & 0xFFFFFFFF
+            d.update(drop_keep=float(l.dropout_keep), drop_seed=seed, drop_stream=i, drop_ctr=P(done_dev) if done_dev is not None else 0)
         rec[i] = dict(a_in=cur["buf"], a_in_ld=cur["ld"], a_inT=cur.get("bufT"))
         if last:
             fuse_loss = train and worker.fuse_loss and (lp.loss == "mse" or ks.cols <= 32)
@@ -343,8 +360,11 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             r = rec[i]
             if r["a_inT"] is None:
                 raise UnsupportedGraph("dense layer input has no transposed copy")
-            wd = dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B,
-                      out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols)
+            wd = dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B)
+            if sharded:
+                wd.update(worker.route_args(ks))          # push fused into the epilogue: tiles go to the owners' mailboxes
+            else:
+                wd.update(out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols)
             wg = C.Gemm(wd)
             emit(wg, f"wgrad{i}", wd, on_side=True)
             if i == first_trainable:
@@ -354,7 +374,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
                 pb = lay.by_name(prev.bias) if prev.bias else None
                 ndz, ndzT = zeros(B, r["a_in_ld"]), zeros(ks.rows, ldB)
                 dd = dict(a=P(g_dz), lda=g_dz.shape[1], b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=B, N=ks.rows, K=ks.cols,
-                          aux=P(r["a_in"]), ld_aux=r["a_in_ld"], aux_act=ACT_IDS[prev.act], out_bf16=P(ndz),
+                          aux=P(r["a_in"]), ld_aux=r["a_in_ld"], aux_act=ACT_IDS[prev.act], aux_keep=float(prev.dropout_keep or 0.0), out_bf16=P(ndz),
                           ld_bf16=ndz.shape[1], outT_bf16=P(ndzT), ld_t=ldB,
                           colsum=P(worker.grads) + pb.offset * 4 if pb else 0)
                 dg = C.Gemm(dd)
@@ -387,8 +407,13 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             r = rec[i]
             kblocks = (r["M"] + 63) // 64
             tiles = ((r["K"] + 127) // 128) * max(1, (ks.cols + 63) // 64)
-            wg = C.Gemm(dict(a=P(r["patchesT"]), lda=r["ldM"], b=P(r["dzT"]), ldb=r["ldM"], M=r["K"], N=ks.cols, K=r["M"],
-                             out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols, split_k=_split_k(tiles, kblocks), accumulate=1))
+            cw = dict(a=P(r["patchesT"]), lda=r["ldM"], b=P(r["dzT"]), ldb=r["ldM"], M=r["K"], N=ks.cols, K=r["M"],
+                      split_k=_split_k(tiles, kblocks), accumulate=1)
+            if sharded:
+                cw.update(worker.route_args(ks))          # red.add into the owners' mailboxes (appliers hand them back zeroed)
+            else:
+                cw.update(out_f32=P(worker.grads) + ks.offset * 4, ld_f32=ks.cols)
+            wg = C.Gemm(cw)
             gemms.append(wg)
             side(lambda wg=wg, i=i: plan.add_gemm(wg, f"wgrad{i}"))
             if i == first_trainable:
@@ -410,9 +435,11 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         plan.join(3)
     if with_push:
         extra = dict(done_dev=P(done_dev)) if done_dev is not None else {}
-        if worker.served:
+        if sharded:
+            plan.add_post_flags(dict(worker._post_flags_args(loss_out), **extra))
+        elif worker.served:
             plan.add_post(dict(worker._post_args(loss_out), **extra), P(worker.sync_push), 0)
         else:
             plan.add_push(dict(worker._push_args(loss_out), **extra), P(worker.sync_push), 0)
     keep.append(gemms)
-    return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep, idx_stage)
+    return BuiltPlan(plan, x_stage, y_stage, loss_out, None, keep, idx_stage, rec)

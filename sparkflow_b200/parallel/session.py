@@ -117,9 +117,16 @@ class TrainingSession:
             n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
             shared = n_workers > 1
             if self.push_mode == "auto":
-                self.push_mode = "served" if shared else "direct"
+                self.push_mode = "sharded" if shared else "direct"
             n_mb = n_workers if self.push_mode == "served" else 0
-            if ctx.world > 1:
+            if self.push_mode == "sharded":
+                from .sharded import ShardedMaster
+
+                # accumulating (split-K) conv wgrads add into the mailboxes: the appliers hand them back zeroed
+                self.master = ShardedMaster(self.layout, self.spec, ctx, self.local_devices(), mb_zero=any(l.kind == "conv" for l in lp.layers))
+                w0 = self._init_weights() if (ctx.is_master or ctx.world == 1 or self.resume_from) else None
+                self.master.load_weights(w0 if (ctx.is_master or ctx.world == 1) else None)
+            elif ctx.world > 1:
                 if ctx.is_master:
                     self.master = MasterState(self.layout, self.spec, dev0, n_mailboxes=n_mb)
                     self.master.load_weights(self._init_weights())
@@ -149,10 +156,10 @@ class TrainingSession:
                 D.barrier(ctx)
             else:
                 self.master = ParameterServer(self._init_weights(), self.spec, self.acquire_lock, max_errors=max(self.iters, 1))
-        if self._resume_state is not None and self.master is not None and (self.ctx.is_master or self.ctx.world == 1):
+        if self._resume_state is not None and self.master is not None and (self.ctx.is_master or self.ctx.world == 1 or self.push_mode == "sharded"):
             slots, step = self._resume_state
             self.master.load_slots(slots, step)
-        if self.engine_kind == "b200" and self.push_mode == "served" and self.master.owner:
+        if self.engine_kind == "b200" and self.push_mode in ("served", "sharded") and self.master.owner:
             n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
             self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1, dbuf=self._dbuf())
         D.barrier(ctx)
@@ -183,9 +190,11 @@ class TrainingSession:
             if hasattr(w, "drain"):
                 w.drain()
         D.barrier(ctx)
-        served = self.engine_kind == "b200" and self.push_mode == "served"
+        served = self.engine_kind == "b200" and self.push_mode in ("served", "sharded")
         if served and self.master.owner:
             self.master.stop_applier()
+        if served:
+            D.barrier(ctx)                  # sharded: no applier anywhere may still be publishing into a peer's replica
         if self.use_cuda:
             for d in self.local_devices():
                 torch.cuda.synchronize(d)
@@ -218,23 +227,26 @@ class TrainingSession:
             self.snapshot(os.path.join(self.checkpoint_dir, f"master-{iteration + 1}"))
 
     # -------------------------------------------------------------------------------------------
-    def make_engine(self, device: torch.device, partition_id: str = "") -> Engine:
+    def make_engine(self, device: torch.device, partition_id: str = "", lane: Optional[int] = None) -> Engine:
         if self.engine_kind == "b200":
             from .device_engine import DeviceWorker, MasterState
 
             # one DeviceWorker per device for the whole session: it owns the replica, gradient buffers, streams and
             # captured CUDA graphs, all of which are reusable across partitions and partition_shuffles rounds
-            w = self._dev_workers.get(device)
+            devs = self.local_devices()
+            if lane is None:
+                lane = devs.index(device) if device in devs else 0
+            w = self._dev_workers.get(lane)
             if w is None:
                 master = self.master
-                if master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
+                if self.push_mode != "sharded" and master.device != device:        # single-process multi-GPU: alias of the master seen from `device`
                     master = MasterState(self.layout, self.spec, device, base_ptr=self.master.base, n_mailboxes=self.master.ml.n_mailboxes)
                 shared = self.ctx.world > 1 or len(self.local_devices()) > 1
                 # mailbox index = position of the device in the session's device list (NOT its CUDA ordinal)
-                widx = self.ctx.rank if self.ctx.world > 1 else self.local_devices().index(device)
+                widx = self.ctx.rank if self.ctx.world > 1 else lane
                 w = DeviceWorker(self.ir, self.tf_input, self.tf_label, self.spec, master, acquire_lock=self.acquire_lock,
                                  pull_mode=self.pull_mode, device=device, shared=shared, worker_index=widx)
-                self._dev_workers[device] = w
+                self._dev_workers[lane] = w
                 self._workers.append(w)
             return B200Engine(w)
         if self.ctx.world > 1 and not self.ctx.is_master:
@@ -251,7 +263,7 @@ class TrainingSession:
         takes the partitions ``i % world == rank``)."""
         self.open()
         ctx = self.ctx
-        if self.engine_kind == "b200" and self.push_mode == "served" and self.master.owner:
+        if self.engine_kind == "b200" and self.push_mode in ("served", "sharded") and self.master.owner:
             if self.master.applier is None or not self.master.applier.alive():      # idle timeout between rounds
                 n_workers = ctx.world if ctx.world > 1 else len(self.local_devices())
                 self.master.start_applier(self.acquire_lock, scope_sys=n_workers > 1, dbuf=self._dbuf())
@@ -272,7 +284,7 @@ class TrainingSession:
             if dev.type == "cuda":
                 torch.cuda.set_device(dev)
             for pid, (feat, lab) in lanes[lane_idx]:
-                engine = self.make_engine(dev, partition_id=f"partition-{pid}")
+                engine = self.make_engine(dev, partition_id=f"partition-{pid}", lane=lane_idx if self.use_cuda else None)
                 run_partition(engine, feat, lab, iters=self.iters, mini_batch_size=self.mini_batch, shuffle=self.shuffle,
                               mini_stochastic_iters=self.msi, verbose=self.verbose, loss_callback=self.loss_callback,
                               partition_id=f"partition-{pid}", seed=None if self.seed is None else self.seed + pid,
@@ -310,6 +322,8 @@ class TrainingSession:
     def push_external(self, grads) -> None:
         """One optimizer step on the master from an externally computed gradient list."""
         if self.engine_kind == "b200":
+            if self.push_mode == "sharded":
+                raise NotImplementedError("push_external on a sharded master: open the session with push_mode='served' or 'direct'")
             from .device_engine import external_push
 
             external_push(self.master, self.layout, self.spec, [np.asarray(g, dtype=np.float32) for g in grads], self.acquire_lock)
@@ -343,6 +357,9 @@ class TrainingSession:
                 except TimeoutError:
                     pass
             D.barrier(ctx)
+            if self.push_mode == "sharded":
+                self.master.stop_applier()      # nobody publishes into a peer's replica any more ...
+                D.barrier(ctx)                  # ... before any rank unmaps its segments
             self.master.close()
         self._workers.clear()
         self._dev_workers.clear()

@@ -91,6 +91,7 @@ class ShardedMaster:
         self.o_flags = take(self.n * C.MB_WORDS * 4)
         self.o_sync = take(64)
         self.o_ack = take(self.C.MAX_SHARDS * ACK_STRIDE * 4)
+        self.o_heart = take(64)                         # worker heartbeat: (globaltimer ns of the last post, posts so far)
         self.mb_stride = round_up(lay.total, 64)
         self.o_mail = take(self.n * self.mb_stride * 4)
         seg_bytes = off
@@ -99,6 +100,7 @@ class ShardedMaster:
         self.seg = SymmetricHeap(seg_bytes, ctx if self.spmd else None, idx, multicast=False, tag="seg")
         self.multicast = self.pub.multicast
         self.appliers: Dict[int, object] = {}
+        self._stats: Dict[int, torch.Tensor] = {}
         self._keep: List[object] = []
         self._owner_index: Optional[List[torch.Tensor]] = None
 
@@ -121,6 +123,50 @@ class ShardedMaster:
     def ack_ptr(self, worker: int, shard: int) -> int:
         """Where shard ``shard`` acknowledges worker ``worker``: a word inside the WORKER's segment."""
         return self.seg.base[worker] + self.o_ack + shard * ACK_STRIDE * 4
+
+    def heartbeat_ptr(self, worker: int) -> int:
+        return self.seg.base[worker] + self.o_heart
+
+    def worker_status(self, stale_after_s: float = 5.0) -> List[Dict[str, float]]:
+        """Watchdog view (failure detection): per worker the number of posts and the age of its last
+        one.  ``stale`` marks workers that posted before but have been silent for ``stale_after_s`` - the sharded
+        protocol needs no action for them (a dead worker simply stops posting; nothing waits on it), this is for
+        operators / the session log."""
+        dev = self.devices[0]
+        out = []
+        with torch.cuda.device(dev):
+            now = None
+            for w in range(self.n):
+                hb = _view(self.heartbeat_ptr(w), 16, torch.int64, dev).cpu()
+                t, n = int(hb[0]), int(hb[1])
+                now = max(now or 0, t)
+                out.append({"worker": w, "posts": n, "last_post_ns": t})
+        for o in out:
+            o["age_s"] = (now - o["last_post_ns"]) / 1e9 if o["posts"] else float("inf")
+            o["stale"] = bool(o["posts"] and o["age_s"] > stale_after_s)
+        return out
+
+    def debug_state(self) -> Dict[str, object]:
+        """Protocol words of every shard / worker, read on a private stream (safe while kernels spin): for debugging a
+        stalled run before a bounded device wait traps."""
+        dev = self.devices[0]
+        C = self.C
+        out: Dict[str, object] = {"bounds": self.bounds, "multicast": self.multicast}
+        st = torch.cuda.Stream(device=dev)
+        with torch.cuda.device(dev), torch.cuda.stream(st):
+            for r in range(self.n):
+                flags = _view(self.seg_ptr(r, self.o_flags), self.n * C.MB_WORDS * 4, torch.int32, dev).to("cpu", non_blocking=False).view(self.n, C.MB_WORDS)
+                out[f"shard{r}.posted"] = flags[:, 0].tolist()
+                out[f"shard{r}.applied"] = flags[:, C.MB_APPLIED].tolist()
+                out[f"shard{r}.sync"] = _view(self.seg_ptr(r, self.o_sync), 64, torch.int32, dev).cpu().tolist()
+                out[f"shard{r}.ctrl"] = self.view("ctrl", r, dev)[:8].cpu().tolist()
+                out[f"worker{r}.acks"] = self.view("ack", r, dev).cpu().view(-1, ACK_STRIDE)[: self.n, 0].tolist()
+                stamps = self.view("stamps", r, dev).cpu().view(-1, VER_STRIDE)
+                out[f"replica{r}.stamps(begin,end)"] = [(int(stamps[q, 0]), int(stamps[q, 16])) for q in range(self.n)]
+            st.synchronize()
+        out["appliers_alive"] = {s: a.alive() for s, a in self.appliers.items()}
+        out["applier_launches"] = {s: a.launches() for s, a in self.appliers.items()}
+        return out
 
     def view(self, which: str, shard: int, device: Optional[torch.device] = None) -> torch.Tensor:
         lay, dev = self.layout, device or self.dev_of(shard)
@@ -262,7 +308,10 @@ class ShardedMaster:
                             grad=0, applier=1, segs=native.ptr(segs_dev), tile_map=native.ptr(tile_map), num_tiles=self.n_tiles,
                             seg_rows=lay.seg_rows(), optimizer=self.spec.opt_id, lock_mode=0, drop=0, scope_sys=1 if scope_sys else 0,
                             grad_scale=1.0, hyper=self.spec.native_hyper(), mb_zero=1 if self.mb_zero else 0)
-                shard = dict(tile_begin=self.bounds[s], tile_end=self.bounds[s + 1], ack=[self.ack_ptr(w, s) for w in range(self.n)])
+                if s not in self._stats:
+                    self._stats[s] = torch.zeros(8, dtype=torch.int64, device=dev)
+                shard = dict(tile_begin=self.bounds[s], tile_end=self.bounds[s + 1], ack=[self.ack_ptr(w, s) for w in range(self.n)],
+                             stats=native.ptr(self._stats[s]))
                 if self.lock_mode:
                     shard.update(ver_begin=[p + s * VER_STRIDE * 4 for p in stamps], ver_end=[p + (s * VER_STRIDE + 16) * 4 for p in stamps],
                                  ver_mc=1 if self.multicast else 0)
@@ -271,6 +320,19 @@ class ShardedMaster:
                 self.appliers[s] = C.Applier(push, self.seg_ptr(s, self.o_mail), self.mb_stride, self.seg_ptr(s, self.o_flags), self.n,
                                              self.seg_ptr(s, self.o_sync), poll_window_s, g, depth,
                                              max_batch or int(os.environ.get("SPARKFLOW_APPLIER_BATCH", "8")), 0, 0, shard)
+
+    def applier_latency(self) -> Dict[str, float]:
+        """Device-measured averages of the owned shards' appliers: decision -> all tiles applied + published (`apply_us`),
+        decision -> every consumed push acknowledged (`ack_us`), pushes per pass."""
+        out = {"apply_us": 0.0, "ack_us": 0.0, "passes": 0, "pushes_per_pass": 0.0}
+        for s, t in self._stats.items():
+            v = t.cpu().numpy()
+            if v[2]:
+                out["apply_us"] = max(out["apply_us"], v[0] / v[2] / 1e3)
+                out["ack_us"] = max(out["ack_us"], v[1] / v[2] / 1e3)
+                out["passes"] = max(out["passes"], int(v[2]))
+                out["pushes_per_pass"] = max(out["pushes_per_pass"], float(v[3]) / float(v[2]))
+        return out
 
     @property
     def applier(self):

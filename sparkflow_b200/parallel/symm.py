@@ -118,13 +118,15 @@ class SymmetricHeap:
         self._maps: List[int] = []
         C = self.C
         dev0 = self.devices[0]
-        want_mc = bool(multicast) and os.environ.get("SPARKFLOW_MULTICAST", "1") != "0" and self.n > 1
+        uniq = sorted(set(self.devices))            # a device may host several segments (two shards on one GPU in tests)
+        self._uniq = uniq
+        want_mc = bool(multicast) and os.environ.get("SPARKFLOW_MULTICAST", "1") != "0" and self.n > 1 and (self.spmd or len(uniq) == self.n)
         if want_mc:
             ok = all(C.vmm_multicast_supported(d) for d in self.devices)
             if self.spmd:
                 ok = all(D.all_gather_object(self.ctx, ok))
             want_mc = ok
-        for d in self.devices:
+        for d in uniq:
             with torch.cuda.device(d):
                 torch.zeros(1, device=f"cuda:{d}")               # make sure the primary context exists
         gran = C.vmm_granularity(dev0, want_mc, self.n)
@@ -144,7 +146,7 @@ class SymmetricHeap:
         for i, d in enumerate(self.devices):
             h = C.vmm_create(d, self.nbytes)
             self._handles.append(h)
-            self.base[i] = C.vmm_map(h, self.nbytes, self.devices)
+            self.base[i] = C.vmm_map(h, self.nbytes, self._uniq)
             self._maps.append(self.base[i])
             with torch.cuda.device(d):
                 C.memset_d8(self.base[i], 0, self.nbytes)
@@ -156,7 +158,7 @@ class SymmetricHeap:
                     C.mc_add_device(mc, d)
                 for h in self._handles:
                     C.mc_bind(mc, 0, h, 0, self.nbytes)
-                self.mc_base = C.vmm_map(mc, self.nbytes, self.devices)
+                self.mc_base = C.vmm_map(mc, self.nbytes, self._uniq)
                 self._maps.append(self.mc_base)
             except RuntimeError as exc:
                 self._mc_error = str(exc)

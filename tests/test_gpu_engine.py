@@ -293,3 +293,78 @@ def test_megakernel_chain_matches_per_gemm_launches(name, monkeypatch):
     assert abs(l_a - l_b) < 1e-3 * max(1.0, abs(l_a))
     for a, b, v in zip(w_a, w_b, ir.trainable):
         np.testing.assert_allclose(a, b, rtol=2e-3, atol=2e-5, err_msg=v.name)
+
+
+def test_fused_dropout_mask_statistics_and_gradients():
+    """K13: tf.nn.dropout after a dense layer runs inside the compiled plan (Philox mask in the GEMM epilogue).  The mask
+    is recovered from the stored activation; forward statistics and every gradient are checked against PyTorch given
+    that observed mask (reference semantics: keep with prob p, scale by 1/p - tf.nn.dropout; ml_util.py:70-71)."""
+    from sparkflow_b200.graph import tfcompat as tf
+    from sparkflow_b200.graph_utils import build_graph
+
+    def model():
+        x = tf.placeholder(tf.float32, shape=[None, 784], name="x")
+        y = tf.placeholder(tf.float32, shape=[None, 10], name="y")
+        kp = tf.placeholder_with_default(0.5, shape=[], name="keep_prob")
+        h1 = tf.nn.dropout(tf.layers.dense(x, 256, activation=tf.nn.relu), keep_prob=kp)
+        h2 = tf.layers.dense(h1, 128, activation=tf.nn.tanh)
+        h2 = tf.layers.dropout(h2, rate=0.25, training=True)
+        logits = tf.layers.dense(h2, 10)
+        tf.argmax(logits, 1, name="out")
+        return tf.losses.softmax_cross_entropy(y, logits)
+
+    spec = OptimizerSpec.from_tf_kwargs("gradient_descent", dict(learning_rate=0.0))
+    ir = GraphIR.from_metagraph(build_graph(model))
+    lp = compile_graph(ir, "x:0", "y:0")
+    assert [round(l.dropout_keep, 2) for l in lp.layers] == [0.5, 0.75, 0.0]
+    need_w, need_wt = plan_publish_needs(lp)
+    lay = ParamLayout.build(ir.param_shapes(), need_w, need_wt)
+    dev = torch.device("cuda:0")
+    master = MasterState(lay, spec, dev)
+    w0 = GraphProgram(ir).init_weights(seed=2)
+    w0 = [w if w.ndim > 1 else (0.1 * np.random.default_rng(1).standard_normal(w.shape)).astype(np.float32) for w in w0]
+    master.load_weights(w0)
+    worker = DeviceWorker(ir, "x:0", "y:0", spec, master, shared=False, use_graphs=False)
+    B = 256
+    X, Y = _data(B, 784, 10, "onehot", seed=5)
+    plan, bufs = worker.build_plan(B, 0, with_pull=True, with_push=False)
+    with torch.cuda.stream(worker.stream):
+        bufs.x_stage.copy_(torch.from_numpy(X))
+        bufs.y_stage.copy_(torch.from_numpy(Y))
+        plan.run(worker.stream.cuda_stream)
+    worker.stream.synchronize()
+    dbg = worker.last_debug
+    dense = [i for i, l in enumerate(lp.layers) if l.kind == "dense"]
+    a1 = dbg[dense[1]]["a_in"].float()[:, :256].cpu()          # dropout(relu(x W0 + b0), keep 0.5) as consumed by layer 1
+    a2 = dbg[dense[2]]["a_in"].float()[:, :128].cpu()          # dropout(tanh(.), keep 0.75)
+    xb = torch.from_numpy(X).to(torch.bfloat16).float()
+    W = [torch.from_numpy(w).to(torch.bfloat16).float() if w.ndim > 1 else torch.from_numpy(w) for w in w0]
+    h1 = torch.relu(xb @ W[0] + W[1])
+    m1 = (a1 != 0).float()
+    pos = h1 > 1e-3
+    kept = (m1[pos]).mean().item()
+    assert 0.47 < kept < 0.53, kept                              # keep probability 0.5
+    assert torch.allclose(a1[pos & (m1 > 0)], 2.0 * h1[pos & (m1 > 0)], rtol=3e-2, atol=3e-2)   # survivors scaled by 1/keep
+    h2 = torch.tanh(a1 @ W[2] + W[3])
+    m2 = (a2 != 0).float()
+    big = h2.abs() > 1e-2
+    assert 0.72 < m2[big].mean().item() < 0.78
+    assert torch.allclose(a2[big & (m2 > 0)], h2[big & (m2 > 0)] / 0.75, rtol=3e-2, atol=3e-2)
+    # the two layers' masks are different streams, rows differ, columns differ
+    assert (m1[0] != m1[1]).any() and (m1[:, 0] != m1[:, 1]).any()
+    # ---- gradients given the observed masks (autograd on the same computation) ----
+    Wt = [w.clone().requires_grad_(True) for w in W]
+    xh = xb
+    z1 = torch.relu(xh @ Wt[0] + Wt[1]) * m1 * 2.0
+    z2 = torch.tanh(z1.to(torch.bfloat16).float() @ Wt[2] + Wt[3]) * m2 / 0.75
+    logits = z2.to(torch.bfloat16).float() @ Wt[4] + Wt[5]
+    loss = -(torch.from_numpy(Y) * torch.log_softmax(logits, 1)).sum(1).mean()
+    loss.backward()
+    got = lay.unflatten(worker.grads.cpu().numpy())
+    for g, w, v in zip(got, Wt, ir.trainable):
+        ref = w.grad.numpy()
+        scale = max(np.abs(ref).max(), 1e-6)
+        assert np.abs(g - ref).max() < 6e-2 * scale, (v.name, np.abs(g - ref).max(), scale)
+    assert abs(float(worker.loss_acc.cpu()[0]) - float(loss)) < 2e-2 * max(1.0, float(loss))
+    # a second step draws a different mask only when the step counter moves: without a push the counter is unchanged
+    master.close()

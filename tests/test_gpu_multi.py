@@ -22,7 +22,7 @@ WORKER = textwrap.dedent("""
     from sparkflow_b200.parallel import dist as D
     from sparkflow_b200.parallel.session import TrainingSession
     lock = sys.argv[1].startswith("lock")
-    push_mode = "direct" if sys.argv[1].endswith("direct") else "served"
+    push_mode = "direct" if sys.argv[1].endswith("direct") else ("sharded" if sys.argv[1].endswith("sharded") else "served")
     ctx = D.get_context()
     rng = np.random.default_rng(11)
     centers = rng.normal(0, 1, (10, 784)).astype(np.float32)
@@ -45,7 +45,7 @@ WORKER = textwrap.dedent("""
     X = np.concatenate([p[0] for p in parts]); L = np.concatenate([p[2] for p in parts])
     acc = float((prog.forward("out:0", {{"x:0": X}}, w).numpy() == L).mean())
     with open(os.path.join(sys.argv[2], "rank%d.json" % ctx.rank), "w") as fh:
-        json.dump({{"rank": ctx.rank, "acc": acc, "counters": c, "w0": float(np.abs(w[0]).sum())}}, fh)
+        json.dump({{"rank": ctx.rank, "acc": acc, "counters": c, "w0": float(np.abs(w[0]).sum()), "master": sess.master_desc()}}, fh)
     sess.close()
 """)
 
@@ -61,11 +61,14 @@ def _run(n, mode, tmp_path, port):
     return [json.load(open(tmp_path / f)) for f in sorted(os.listdir(tmp_path)) if f.startswith("rank")]
 
 
+MODES = ["hogwild", "lock", "hogwild-direct", "lock-direct", "hogwild-sharded", "lock-sharded"]
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("mode", ["hogwild", "lock", "hogwild-direct", "lock-direct"])
+@pytest.mark.parametrize("mode", MODES)
 def test_two_gpu_async_parameter_server(mode, tmp_path):
     n = min(torch.cuda.device_count(), 8)
-    res = _run(n, mode, tmp_path, 29541 + ["hogwild", "lock", "hogwild-direct", "lock-direct"].index(mode))
+    res = _run(n, mode, tmp_path, 29541 + MODES.index(mode))
     assert len(res) == n
     total = n * 6 * 5                       # ranks x iters x batches
     for r in res:

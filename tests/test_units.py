@@ -148,7 +148,7 @@ def test_compiler_covers_every_reference_model():
     assert lp.layers[3].in_shape == (12, 12, 32) and lp.layers[3].out_shape == (10, 10, 64) and lp.layers[-1].in_shape == (1600,)
 
 
-def test_compiler_reports_unsupported_graphs():
+def test_compiler_fuses_dense_dropout_and_reports_unsupported_graphs():
     def with_dropout():
         x = tf.placeholder(tf.float32, [None, 8], name="x")
         y = tf.placeholder(tf.float32, [None, 1], name="y")
@@ -156,13 +156,37 @@ def test_compiler_reports_unsupported_graphs():
         h = tf.nn.dropout(tf.layers.dense(x, 4, activation=tf.nn.relu), keep)
         return tf.losses.mean_squared_error(y, tf.layers.dense(h, 1))
 
+    # K13: dropout after a dense layer is part of the compiled plan (fused Philox mask in the GEMM epilogue)
     ir = GraphIR.from_metagraph(build_graph(with_dropout))
-    with pytest.raises(UnsupportedGraph):
-        compile_graph(ir, "x:0", "y:0")
-    # ... but the generic interpreter trains it
+    lp = compile_graph(ir, "x:0", "y:0")
+    assert [l.dropout_keep for l in lp.layers] == [0.5, 0.0]
+    # ... and the generic interpreter trains the same graph
     prog = GraphProgram(ir)
     loss, grads = prog.loss_and_grads({"x:0": np.random.rand(6, 8), "y:0": np.random.rand(6, 1)}, prog.init_weights(0))
     assert np.isfinite(loss) and len(grads) == 4
+
+    def dropout_on_input():
+        x = tf.placeholder(tf.float32, [None, 8], name="x")
+        y = tf.placeholder(tf.float32, [None, 1], name="y")
+        return tf.losses.mean_squared_error(y, tf.layers.dense(tf.nn.dropout(x, 0.5), 1))
+
+    def keep_prob_never_fed():
+        x = tf.placeholder(tf.float32, [None, 8], name="x")
+        y = tf.placeholder(tf.float32, [None, 1], name="y")
+        keep = tf.placeholder(tf.float32, [], name="keep")            # no default: the reference never feeds it while training
+        return tf.losses.mean_squared_error(y, tf.layers.dense(tf.nn.dropout(tf.layers.dense(x, 4), keep), 1))
+
+    def custom_loss():
+        x = tf.placeholder(tf.float32, [None, 8], name="x")
+        y = tf.placeholder(tf.float32, [None, 1], name="y")
+        out = tf.layers.dense(x, 1)
+        loss = tf.reduce_mean(tf.abs(out - y))
+        tf.losses.add_loss(loss)
+        return loss
+
+    for fn in (dropout_on_input, keep_prob_never_fed, custom_loss):
+        with pytest.raises(UnsupportedGraph):
+            compile_graph(GraphIR.from_metagraph(build_graph(fn)), "x:0", "y:0")
 
 
 # ---------------------------------------------------------------------------------------------
