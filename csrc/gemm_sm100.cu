@@ -281,6 +281,26 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      if (ep.ryw != nullptr) {
+        // pull fused into this GEMM: read-your-writes wait before the first weight tile is fetched (local spin)
+        const SfRyw& w = *ep.ryw;
+        const uint32_t posted = *w.my_posted;
+        const unsigned long long t0 = sf_globaltimer();
+        for (int r = 0; r < w.n_shards; ++r) {
+          const uint32_t want = posted * static_cast<uint32_t>(w.ack_grid[r] ? w.ack_grid[r] : 1);
+          while (static_cast<int32_t>(ld_relaxed_sys(w.applied + r * 16) - want) < 0) {
+            if (sf_globaltimer() - t0 > 20000000000ull) sf_fail(0x405);
+          }
+        }
+        if (w.stats != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+          const unsigned long long t1 = sf_globaltimer(), t_post = w.stats[0];
+          if (t_post != 0 && t0 > t_post) {
+            w.stats[8] += t0 - t_post;
+            w.stats[9] += t1 - t0;
+            w.stats[11] += 1ull;
+          }
+        }
+      }
       // weights (B) are re-read by every M tile: keep them in L2; activations stream through.
       const uint64_t hintA = ep.a_evict_first ? kEvictFirst : kEvictNormal;
       const uint64_t hintB = kEvictLast;

@@ -245,7 +245,8 @@ __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc
 template <int OPT, bool ZERO>
 __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* grads, int n_grads, int tile,
                                           const uint32_t* s_t_ptr, bool sync_for_t, __nv_bfloat16 (*s_tr)[kTileR + 8],
-                                          __nv_bfloat16* pub0, float* vec0) {
+                                          __nv_bfloat16* pub0, float* vec0, unsigned long long* tp = nullptr,
+                                          long long off_bf16 = 0, long long off_f32 = 0) {
   constexpr int NS = Slots<OPT>::n;
   const int tid = threadIdx.x;
   const bool mc = a.shadow_is_mc != 0;
@@ -289,11 +290,12 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
       const int r = r0 + ty + 16 * half;
       nv[half] = (r < sg.rows && c < sg.cols) ? ((sg.cols - c) >= 4 ? 4 : (sg.cols - c)) : 0;
       e[half] = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
-      load_grad(grads[0], e[half], nv[half], g[half]);
+      if (!(a.dbg_skip & 4)) load_grad(grads[0], e[half], nv[half], g[half]);
+      else g[half][0] = g[half][1] = g[half][2] = g[half][3] = 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!a.drop && j < nv[half]) v = ld_weak_f4(reinterpret_cast<const float*>(a.state + e[half] + j));
+        if (!a.drop && j < nv[half] && !(a.dbg_skip & 4)) v = ld_weak_f4(reinterpret_cast<const float*>(a.state + e[half] + j));
         u[half][j] = Upd{v.x, v.y, v.z, v.w};
       }
       if (ZERO && nv[half] > 0) {
@@ -302,6 +304,7 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
         else for (int j = 0; j < nv[half]; ++j) grads[0][e[half] + j] = 0.f;
       }
     }
+    if (tp != nullptr) tp[0] = gtime_ns();      // loads issued
     // ---- step number: under the lock it was granted above; Hogwild read it at kernel entry ----
     if (sync_for_t) __syncthreads();     // the step count was written to shared memory by thread 0
     const float t0 = static_cast<float>(*s_t_ptr);
@@ -341,6 +344,7 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
           else for (int j = 0; j < nv[half]; ++j) grads[k][e[half] + j] = 0.f;
         }
     }
+    if (tp != nullptr) tp[1] = gtime_ns() + static_cast<unsigned long long>(u[0][0].p == 12345.678f);      // optimizer math done (loads consumed)
     // ---- phase 3: stores ----
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -354,11 +358,11 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
             const Upd& q = u[half][j];
             w[j] = q.p;
             float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
-            st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
+            if (!(a.dbg_skip & 2)) st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
             if (a.n_vec_dst > 0) {                                      // sharded master: every replica's fp32 tail
               if (e[half] + j >= a.vec_offset) {
                 const long long vi = e[half] + j - a.vec_offset;
-                for (int d = 0; d < a.n_vec_dst; ++d) st_vec_f32(a.vec_dst[d] + vi, q.p, mc);
+                for (int d = 0; d < a.n_vec_dst; ++d) st_vec_f32(a.vec_dst[d] + off_f32 + vi, q.p, mc);
               }
             } else if (a.n_vec_pub > 0 && e[half] + j >= a.vec_offset) {       // 1-D variables: fp32 publish copy / copies
               const long long vi = e[half] + j - a.vec_offset;
@@ -368,10 +372,10 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
           }
         }
         // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
-        if (sg.w_off >= 0) {
+        if (sg.w_off >= 0 && !(a.dbg_skip & 1)) {
           const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
           const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
-          for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8((d == 0 ? pub0 : a.shadow_dst[d]) + wo, q, mc && d == 0);
+          for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8((d == 0 ? pub0 : a.shadow_dst[d] + off_bf16) + wo, q, mc && d == 0);
         }
       }
       if (sg.wt_off >= 0 && !a.drop) {
@@ -379,15 +383,16 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
         for (int j = 0; j < 4; ++j) s_tr[tx * 4 + j][rl] = __float2bfloat16(w[j]);
       }
     }
+    if (tp != nullptr) tp[2] = gtime_ns();      // state + row-major publish stores issued
     if (sg.wt_off >= 0 && !a.drop) {
       __syncthreads();
       // transposed bf16 publish: [cols, wt_ld]; each thread owns 8 consecutive rows of one column
       const int cl = tid >> 2, part = tid & 3;
       const int cc = c0 + cl, rr = r0 + part * 8;
-      if (cc < sg.cols && rr < sg.rows) {
+      if (cc < sg.cols && rr < sg.rows && !(a.dbg_skip & 1)) {
         const int64_t to = sg.wt_off + static_cast<int64_t>(cc) * sg.wt_ld + rr;
         const uint4 q = *reinterpret_cast<const uint4*>(&s_tr[cl][part * 8]);
-        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16((d == 0 ? pub0 : a.shadow_dst[d]) + to, q, mc && d == 0);
+        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16((d == 0 ? pub0 : a.shadow_dst[d] + off_bf16) + to, q, mc && d == 0);
       }
       __syncthreads();
     }
@@ -644,9 +649,11 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
   const int tid = threadIdx.x;
   const bool leader = blockIdx.x == 0;
   const bool locked = a.push.lock_mode == SF_LOCK_RW;
-  constexpr int kMaxBatches = 8;            // one launch keeps draining while mailboxes are posted
+  // One launch serves up to kMaxBatches passes.  With `linger` it keeps listening between passes: the same resident CTAs
+  // (instruction cache, TLB warm) serve the next push - measured on B200, a cold pass spends ~5 us just fetching code.
+  constexpr int kMaxBatches = 256;
   for (int k = 0; k < kMaxBatches; ++k) {
-    const uint32_t epoch = seq * 16u + static_cast<uint32_t>(k);
+    const uint32_t epoch = seq * 256u + static_cast<uint32_t>(k);
     uint32_t posted = 0;                    // leader warp: lane w holds worker w's POSTED word
     if (leader) {
       if (tid < 32) {
@@ -662,7 +669,7 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
           m_ready = __ballot_sync(0xffffffffu, ready);
           if (m_ready) break;
           // the first decision listens for a whole window; follow-ups only take what is already there
-          const bool over = (k > 0) || (gtime_ns() - t0 > a.idle_timeout_ns);
+          const bool over = (k > 0 && !a.linger) || (gtime_ns() - t0 > a.idle_timeout_ns);
           if (__ballot_sync(0xffffffffu, over) & 1u) break;      // lane 0 decides for the whole warp
           __nanosleep(40);
         }
@@ -701,9 +708,10 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
             t = ld_relaxed_sys(a.push.ctrl + SF_CTRL_STEP) + 1;
             if (a.n_ver > 0) {
               // seqlock: stamp `begin` in every replica before the first publish store of this pass can land
-              const uint32_t ver = a.sync[6] + 1;
+              const uint32_t ver = (a.ver_local != nullptr ? ld_relaxed_sys(a.ver_local) : a.sync[6]) + 1;
               for (int d = 0; d < a.n_ver; ++d) st_u32_pub(a.ver_begin[d], ver, a.ver_mc != 0);
               asm volatile("fence.acq_rel.sys;" ::: "memory");
+              if (a.slot_off_bf16 != 0) buf = ver & 1u;          // two publish slots: this pass lands in slot ver & 1
             }
           }
           if (a.stats != nullptr) a.sync[8] = static_cast<uint32_t>(gtime_ns()), a.sync[9] = static_cast<uint32_t>(gtime_ns() >> 32);
@@ -729,6 +737,8 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
     __syncthreads();
     const uint32_t mask = s_mask;
     if (mask == 0) return;                              // nothing (more) is posted: this launch is done
+    const bool probe = a.stats != nullptr && blockIdx.x == gridDim.x - 1 && tid == 0;      // phase timing of one follower CTA
+    const unsigned long long tp0 = probe ? gtime_ns() : 0ull;
     if (tid == 0) {
       // application order: round-robin from the cursor, so no worker's push is always last in a batch
       const int rr = static_cast<int>(a.sync[4]) % a.n_workers;
@@ -741,16 +751,52 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
     }
     __syncthreads();
     const int n = s_n;
-    __nv_bfloat16* const pub0 = (a.dbuf && s_buf) ? a.shadow_alt : a.push.shadow_dst[0];
+    const long long off_bf16 = (a.slot_off_bf16 != 0 && s_buf) ? a.slot_off_bf16 : 0;
+    const long long off_f32 = (a.slot_off_bf16 != 0 && s_buf) ? a.slot_off_f32 : 0;
+    __nv_bfloat16* const pub0 = ((a.dbuf && s_buf) ? a.shadow_alt : a.push.shadow_dst[0]) + off_bf16;
     float* const vec0 = (a.dbuf && s_buf) ? a.vec_pub_alt : a.push.vec_pub[0];
     const int tile_lo = a.tile_end > a.tile_begin ? a.tile_begin : 0;
     const int tile_hi = a.tile_end > a.tile_begin ? a.tile_end : a.push.num_tiles;
+    unsigned long long tpt[3] = {0ull, 0ull, 0ull};
+    const unsigned long long tpa = probe ? gtime_ns() : 0ull;          // s_grads built, barrier passed
     for (int tile = tile_lo + blockIdx.x; tile < tile_hi; tile += gridDim.x)
-      push_tile<OPT, false>(a.push, s_grads, n, tile, &s_t, false, s_tr, pub0, vec0);
+      push_tile<OPT, false>(a.push, s_grads, n, tile, &s_t, false, s_tr, pub0, vec0, probe ? tpt : nullptr, off_bf16, off_f32);
     __syncthreads();
+    const unsigned long long tp1 = probe ? gtime_ns() : 0ull;
+    if (probe && tpt[0] != 0ull) {
+      a.stats[8] += tpa - tp0;             // build the mailbox list + barrier
+      a.stats[9] += tpt[0] - tpa;          // tile header + loads issued
+      a.stats[10] += tpt[1] - tpt[0];      // loads returned + optimizer math
+      a.stats[11] += tpt[2] - tpt[1];      // state / W stores issued
+      a.stats[12] += tp1 - tpt[2];         // transpose through smem + W^T stores + barriers
+      const unsigned long long q0 = gtime_ns(), q1 = gtime_ns();
+      a.stats[13] += q1 - q0;              // cost of one %globaltimer read
+    }
+    if (a.ack_counting) {
+      // distributed acknowledgement: this CTA is done with the consumed mailboxes and its share of the publish is on its
+      // way.  ONE system fence per CTA (thread 0; bar.sync makes it cumulative over the CTA's stores), then relaxed
+      // counts: every CTA pays its NVLink flush in parallel instead of the leader paying it after all of them.
+      if (tid == 0) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      __syncthreads();
+      if (tid < 8 && (mask >> tid & 1u) && a.ack[tid] != nullptr)
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(a.ack[tid]), "r"(1u) : "memory");
+      // seqlock `end`: count this CTA's completion in every replica (after the fence: its publish stores are performed)
+      if (a.n_ver > 0 && tid >= 8 && tid < 8 + a.n_ver) {
+        if (a.ver_mc) asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(a.ver_end[tid - 8]), "r"(1u) : "memory");
+        else asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(a.ver_end[tid - 8]), "r"(1u) : "memory");
+      }
+    }
     if (tid == 0) {
-      if (a.n_ver > 0) asm volatile("fence.acq_rel.sys;" ::: "memory");     // this CTA's publish stores are performed everywhere
-      lk_red_release<false>(a.sync + 3, 1u);
+      if (a.n_ver > 0 && !a.ack_counting) asm volatile("fence.acq_rel.sys;" ::: "memory");     // this CTA's publish stores are performed everywhere
+      if (a.ack_counting) lk_red_relaxed<false>(a.sync + 3, 1u);       // ordered after the fence above
+      else lk_red_release<false>(a.sync + 3, 1u);
+      if (probe) {
+        const unsigned long long tp2 = gtime_ns();
+        const unsigned long long t_dec = static_cast<unsigned long long>(a.sync[8]) | (static_cast<unsigned long long>(a.sync[9]) << 32);
+        a.stats[4] += tp0 - t_dec;          // decision -> this CTA saw it
+        a.stats[5] += tp1 - tp0;            // tiles: loads, optimizer, stores issued
+        a.stats[6] += tp2 - tp1;            // acknowledgement red + arrive (the NVLink flush)
+      }
     }
     if (leader && tid < 32) {
       if (tid == 0) {
@@ -764,7 +810,7 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         // the freshly written buffer becomes the current one (release: after every CTA's publish stores, which the
         // acquire of the done counter above made visible to this thread)
         if (a.dbuf) (void)atom_xor_release_sys(a.push.ctrl + SF_CTRL_PUB, 0x80000000u);
-        if (a.n_ver > 0) {
+        if (a.n_ver > 0 && !a.ack_counting) {
           // every CTA fenced its publish stores before arriving: the pass is complete in every replica -> stamp `end`
           const uint32_t ver = a.sync[6] + 1;
           asm volatile("fence.acq_rel.sys;" ::: "memory");
@@ -790,7 +836,7 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
         st_release_sys(a.flags + tid * SF_MB_WORDS + SF_MB_APPLIED, posted);
         // sharded master: the acknowledgement lands in the worker's OWN memory (its next step spins locally)
-        if (a.ack[tid] != nullptr) {
+        if (a.ack[tid] != nullptr && !a.ack_counting) {
           asm volatile("fence.acq_rel.sys;" ::: "memory");
           st_release_sys(a.ack[tid], posted);
         }
@@ -821,8 +867,11 @@ __device__ __forceinline__ uint4 ld_local_u4(const uint4* p) {
 // copy the publish slices (W block, W^T block, fp32 tail elements) of up to kCopyBatch push tiles: inbox -> working
 // replica.  All loads of the batch are issued before the first store (the copy is latency-, not bandwidth-bound).
 constexpr int kCopyBatch = 4;
-__device__ __forceinline__ void copy_tiles_publish(const SfSyncPullArgs& a, int tile0, int tile_end, int stride) {
+__device__ __forceinline__ void copy_tiles_publish(const SfSyncPullArgs& a, int tile0, int tile_end, int stride, long long soff_bf16,
+                                                   long long soff_f32) {
   const int tid = threadIdx.x;
+  const __nv_bfloat16* const src = a.src + soff_bf16;
+  const float* const src_vec = a.src_vec != nullptr ? a.src_vec + soff_f32 : nullptr;
   uint4 vw[kCopyBatch], vt[kCopyBatch];
   float vv[kCopyBatch];
   int64_t ow[kCopyBatch], ot[kCopyBatch];
@@ -839,19 +888,19 @@ __device__ __forceinline__ void copy_tiles_publish(const SfSyncPullArgs& a, int 
       const int row = r0 + (tid >> 3), col = c0 + (tid & 7) * 8;
       if (row < sg.rows && col < sg.w_ld) {
         ow[b] = sg.w_off + static_cast<int64_t>(row) * sg.w_ld + col;
-        vw[b] = ld_local_u4(reinterpret_cast<const uint4*>(a.src + ow[b]));
+        vw[b] = ld_local_u4(reinterpret_cast<const uint4*>(src + ow[b]));
       }
     }
     if (sg.wt_off >= 0) {
       const int trow = c0 + (tid >> 2), el = r0 + (tid & 3) * 8;
       if (trow < sg.cols && el < sg.wt_ld) {
         ot[b] = sg.wt_off + static_cast<int64_t>(trow) * sg.wt_ld + el;
-        vt[b] = ld_local_u4(reinterpret_cast<const uint4*>(a.src + ot[b]));
+        vt[b] = ld_local_u4(reinterpret_cast<const uint4*>(src + ot[b]));
       }
     }
     if (sg.rows == 1 && a.dst_vec != nullptr && tid < kTileC && c0 + tid < sg.cols) {
       ov[b] = sg.offset + c0 + tid - a.vec_offset;
-      vv[b] = ld_relaxed_sys_f32(a.src_vec + ov[b]);
+      vv[b] = ld_relaxed_sys_f32(src_vec + ov[b]);
     }
   }
 #pragma unroll
@@ -876,10 +925,13 @@ sync_pull_kernel(const SfSyncPullArgs a) {
   // ---- read-your-writes: this shard's applier has consumed my last post (it acknowledges into MY memory) ----
   unsigned long long t_seen = 0;
   if (tid == 0) {
-    const uint32_t want = *a.my_posted;
+    const uint32_t grid_r = static_cast<uint32_t>(a.ack_grid[shard]);
+    const uint32_t want = *a.my_posted * (grid_r ? grid_r : 1u);
     const unsigned long long t0 = gtime_ns();
-    while (static_cast<int32_t>(ld_acquire_sys(a.applied + shard * 16) - want) < 0) {
-      __nanosleep(32);
+    // relaxed polling (the word lives in local memory, remote appliers write it); the data the acknowledgement covers is
+    // consumed by LATER kernels (kernel boundary) or validated by the seqlock below
+    while (static_cast<int32_t>(ld_relaxed_sys(a.applied + shard * 16) - want) < 0) {
+      __nanosleep(20);
       if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x405);
     }
     if (a.stats != nullptr && part == 0) {
@@ -902,21 +954,38 @@ sync_pull_kernel(const SfSyncPullArgs a) {
   const unsigned long long t0 = gtime_ns();
   while (true) {
     if (tid == 0) {
-      uint32_t e;
-      while ((e = ld_acquire_sys(a.ver_end + shard * a.ver_stride)) != ld_acquire_sys(a.ver_begin + shard * a.ver_stride)) {
-        __nanosleep(32);                       // an update of this shard is landing right now
-        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40A);
+      // seqlock reader without fences: the stamp loads are relaxed.sys (served by L2, the coherence point of local
+      // memory); the copy's loads cannot issue before the version is known (bar.sync below) and the re-check of `begin`
+      // is issued after the copy's values were consumed by its stores (bar.sync), i.e. in program order.
+      // `begin` = passes started, `end` = CTA completions (grid_r per pass).
+      const uint32_t grid_r = static_cast<uint32_t>(a.ack_grid[shard]);
+      uint32_t b;
+      if (a.slot_off_bf16 != 0) {
+        // two slots: never wait.  Quiescent -> the newest pass is complete; a pass in flight -> the one before it is
+        // (the leader starts a pass only after every CTA of the previous one fenced its publish stores)
+        b = ld_relaxed_sys(a.ver_begin + shard * a.ver_stride);
+        if (ld_relaxed_sys(a.ver_end + shard * a.ver_stride) != b * (grid_r ? grid_r : 1u)) b -= 1u;
+      } else {
+        while (ld_relaxed_sys(a.ver_end + shard * a.ver_stride) != (b = ld_relaxed_sys(a.ver_begin + shard * a.ver_stride)) * (grid_r ? grid_r : 1u)) {
+          __nanosleep(20);                       // an update of this shard is landing right now
+          if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40A);
+        }
       }
-      s_e = e;
+      s_e = b;
     }
     __syncthreads();
-    for (int tile = a.bounds[shard] + part; tile < a.bounds[shard + 1]; tile += cps * kCopyBatch)
-      copy_tiles_publish(a, tile, a.bounds[shard + 1], cps);
+    {
+      const uint32_t ver = s_e;
+      const long long so_b = (a.slot_off_bf16 != 0 && (ver & 1u)) ? a.slot_off_bf16 : 0, so_f = (a.slot_off_bf16 != 0 && (ver & 1u)) ? a.slot_off_f32 : 0;
+      for (int tile = a.bounds[shard] + part; tile < a.bounds[shard + 1]; tile += cps * kCopyBatch)
+        copy_tiles_publish(a, tile, a.bounds[shard + 1], cps, so_b, so_f);
+    }
     __syncthreads();
     if (tid == 0) {
-      asm volatile("fence.acq_rel.sys;" ::: "memory");
       const uint32_t e = s_e;
-      const bool clean = ld_acquire_sys(a.ver_begin + shard * a.ver_stride) == e;
+      // single slot: nothing may have started; two slots: slot e & 1 is rewritten by pass e + 2
+      const uint32_t b2 = ld_relaxed_sys(a.ver_begin + shard * a.ver_stride);
+      const bool clean = a.slot_off_bf16 != 0 ? (static_cast<int32_t>(b2 - e) <= 1) : (b2 == e);
       uint32_t ok;
       if (cps == 1) {
         ok = clean ? 1u : 0u;
@@ -957,7 +1026,7 @@ post_flags_kernel(const SfPostFlagsArgs a) {
   trace.mark();
   const int tid = threadIdx.x;
   // ---- 1-D tail (bias gradients were accumulated locally by atomics): forward each 64-element tile to its owner ----
-  for (int i = tid >> 6; i < a.n_vec_tiles; i += blockDim.x >> 6) {
+  for (int i = tid >> 6; i < (a.phase == 2 ? 0 : a.n_vec_tiles); i += blockDim.x >> 6) {
     const long long tile = a.vec_tiles[i * 3 + 0], off = a.vec_tiles[i * 3 + 1], cnt = a.vec_tiles[i * 3 + 2];
     int owner = 0;
     for (int r = 1; r < a.n_shards; ++r) owner += tile >= a.bounds[r] ? 1 : 0;
@@ -975,6 +1044,10 @@ post_flags_kernel(const SfPostFlagsArgs a) {
         st_weak_f4(a.mailbox[r] + i * 4, 0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
+  if (a.phase == 1) {                  // forwarding only: the post comes from a later launch
+    trace.end(KID_PUSH);
+    return;
+  }
   if (tid == 0) {
     if (a.loss_acc != nullptr) {
       *a.loss_out = *a.loss_acc;
@@ -982,7 +1055,13 @@ post_flags_kernel(const SfPostFlagsArgs a) {
     }
     signal_done(a.loss_out, a.done_dev);
   }
-  if (!a.drop && tid < a.n_shards) {
+  if (!a.drop && a.phase == 2 && tid < a.n_shards) {
+    // every gradient store (wgrad epilogues, tail forwarding) belongs to a kernel that COMPLETED before this one started
+    // (griddepcontrol.wait / graph edges): completed kernels' writes are performed system-wide, no fence needed here
+    const uint32_t seq = *a.my_posted + 1;
+    asm volatile("st.global.relaxed.sys.u32 [%0], %1;" ::"l"(a.posted[tid]), "r"(seq) : "memory");
+  }
+  if (!a.drop && a.phase != 2 && tid < a.n_shards) {
     // the matrix gradients were stored by the wgrad kernels this kernel depends on (kernel boundary = performed);
     // the release below orders them, and the tail stores above (bar.sync), before the post becomes visible
     const uint32_t seq = *a.my_posted + 1;

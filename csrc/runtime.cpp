@@ -94,6 +94,7 @@ struct Gemm {
     g.ep.drop_stream = getd<unsigned int>(d, "drop_stream", 0u);
     g.ep.drop_ctr = P<const unsigned int>(getd<uintptr_t>(d, "drop_ctr", 0));
     g.ep.aux_keep = getd<float>(d, "aux_keep", 0.0f);
+    g.ep.ryw = P<const SfRyw>(getd<uintptr_t>(d, "ryw", 0));
     g.ep.route = P<const SfRoute>(getd<uintptr_t>(d, "route", 0));
     g.ep.route_tile0 = getd<int>(d, "route_tile0", 0);
     g.ep.route_tiles_c = getd<int>(d, "route_tiles_c", 1);
@@ -209,6 +210,7 @@ SfPushArgs parse_push(const py::dict& d) {
   a.n_vec_dst = static_cast<int>(vds.size());
   for (size_t i = 0; i < vds.size(); ++i) a.vec_dst[i] = P<float>(vds[i]);
   a.mb_zero = getd<int>(d, "mb_zero", 0);
+  a.dbg_skip = getd<int>(d, "dbg_skip", 0);
   a.grad = P<float>(getd<uintptr_t>(d, "grad", 0));
   a.loss_acc = P<float>(getd<uintptr_t>(d, "loss_acc", 0));
   a.loss_out = P<float>(getd<uintptr_t>(d, "loss_out", 0));
@@ -299,6 +301,8 @@ SfSyncPullArgs parse_sync_pull(const py::dict& d) {
   a.ver_begin = P<const uint32_t>(getd<uintptr_t>(d, "ver_begin", 0));
   a.ver_end = P<const uint32_t>(getd<uintptr_t>(d, "ver_end", 0));
   a.ver_stride = getd<int>(d, "ver_stride", 16);
+  a.slot_off_bf16 = getd<long long>(d, "slot_off_bf16", 0);
+  a.slot_off_f32 = getd<long long>(d, "slot_off_f32", 0);
   a.src = P<const __nv_bfloat16>(getd<uintptr_t>(d, "src", 0));
   a.dst = P<__nv_bfloat16>(getd<uintptr_t>(d, "dst", 0));
   a.src_vec = P<const float>(getd<uintptr_t>(d, "src_vec", 0));
@@ -309,6 +313,10 @@ SfSyncPullArgs parse_sync_pull(const py::dict& d) {
   a.ctas_per_shard = getd<int>(d, "ctas_per_shard", 1);
   a.sync = P<uint32_t>(getd<uintptr_t>(d, "sync", 0));
   a.stats = P<unsigned long long>(getd<uintptr_t>(d, "stats", 0));
+  {
+    auto ag = getd<std::vector<int>>(d, "ack_grid", {});
+    for (size_t i = 0; i < ag.size() && i < SF_MAX_SHARDS; ++i) a.ack_grid[i] = ag[i];
+  }
   if (!a.applied || !a.my_posted) throw std::runtime_error("sync_pull: applied / my_posted are required");
   if (a.copy && (!a.ver_begin || !a.ver_end || !a.src || !a.dst || !a.segs || !a.tile_map || !a.sync))
     throw std::runtime_error("sync_pull: copy needs ver_begin/ver_end/src/dst/segs/tile_map/sync");
@@ -336,10 +344,23 @@ SfPostFlagsArgs parse_post_flags(const py::dict& d) {
   a.drop = getd<int>(d, "drop", 0);
   a.total = getd<long long>(d, "total", 0);
   a.mb_zero = getd<int>(d, "mb_zero", 0);
+  a.phase = getd<int>(d, "phase", 0);
   a.heartbeat = P<unsigned long long>(getd<uintptr_t>(d, "heartbeat", 0));
   a.stats = P<unsigned long long>(getd<uintptr_t>(d, "stats", 0));
   if (!a.grad || !a.my_posted || (a.n_vec_tiles > 0 && !a.vec_tiles)) throw std::runtime_error("post_flags: grad / my_posted / vec_tiles are required");
   return a;
+}
+
+py::bytes pack_ryw(int n_shards, const std::vector<int>& ack_grid, uintptr_t applied, uintptr_t my_posted, uintptr_t stats) {
+  SfRyw r;
+  std::memset(&r, 0, sizeof(r));
+  if (n_shards < 1 || n_shards > SF_MAX_SHARDS || static_cast<int>(ack_grid.size()) != n_shards) throw std::runtime_error("pack_ryw: n_shards in [1, 8], one grid size per shard");
+  r.n_shards = n_shards;
+  for (int i = 0; i < n_shards; ++i) r.ack_grid[i] = ack_grid[i];
+  r.applied = P<const uint32_t>(applied);
+  r.my_posted = P<const uint32_t>(my_posted);
+  r.stats = P<unsigned long long>(stats);
+  return py::bytes(reinterpret_cast<const char*>(&r), sizeof(r));
 }
 
 // device-resident routing table of one worker (kept alive by the Python side)
@@ -842,6 +863,11 @@ class Applier {
       for (size_t i = 0; i < vb.size(); ++i) { args_.ver_begin[i] = P<uint32_t>(vb[i]); args_.ver_end[i] = P<uint32_t>(ve[i]); }
       args_.ver_mc = getd<int>(shard, "ver_mc", 0);
       args_.stats = P<unsigned long long>(getd<uintptr_t>(shard, "stats", 0));
+      args_.ack_counting = getd<int>(shard, "ack_counting", 0);
+      args_.linger = getd<int>(shard, "linger", 0);
+      args_.ver_local = P<const uint32_t>(getd<uintptr_t>(shard, "ver_local", 0));
+      args_.slot_off_bf16 = getd<long long>(shard, "slot_off_bf16", 0);
+      args_.slot_off_f32 = getd<long long>(shard, "slot_off_f32", 0);
     }
     ck(cudaGetDevice(&device_), "cudaGetDevice");
     int lo = 0, hi = 0;
@@ -1194,6 +1220,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("pack_segs", &pack_segs);
 
   m.def("pack_route", &pack_route);
+  m.def("pack_ryw", &pack_ryw);
   m.attr("MAX_SHARDS") = static_cast<int>(SF_MAX_SHARDS);
   m.def("sync_pull", [](const py::dict& d, uintptr_t stream) {
     const SfSyncPullArgs a = parse_sync_pull(d);

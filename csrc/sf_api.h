@@ -35,6 +35,18 @@ struct SfRoute {
   float* mailbox[SF_MAX_SHARDS];  // this worker's mailbox on every shard owner (flat gradient layout)
 };
 
+// Pull fused into the first GEMM of a step (sharded master, Hogwild): the TMA producer of every CTA waits until every
+// shard's applier has acknowledged this worker's last push (read-your-writes; the words live in LOCAL memory, the
+// appliers write them over NVLink) before it fetches the first weight tile - from the inbox replica the appliers
+// publish into with multimem.st.  The wait overlaps everything the step does before its first GEMM.
+struct SfRyw {
+  int n_shards;
+  int ack_grid[SF_MAX_SHARDS];    // acknowledgements per push of shard r (CTAs of its applier)
+  const uint32_t* applied;        // local: word r * 16
+  const uint32_t* my_posted;      // local: sequence number of my last post
+  unsigned long long* stats;      // optional latency accounting, same layout as SfSyncPullArgs.stats
+};
+
 struct SfGemmEpilogue {
   float* out_f32;                 // [M, ld_f32] optional
   __nv_bfloat16* out_bf16;        // [M, ld_bf16] optional (ld multiple of 8, pad columns get 0)
@@ -70,6 +82,7 @@ struct SfGemmEpilogue {
   unsigned int drop_seed, drop_stream;
   const unsigned int* drop_ctr;   // device word that changes every step (nullptr: 0)
   float aux_keep;                 // dgrad: keep probability of the dropout that produced aux (0 = none)
+  const SfRyw* ryw;               // device memory; nullptr = no wait
 };
 
 enum SfLossMode { SF_LOSS_NONE = 0, SF_LOSS_SOFTMAX_XENT = 1, SF_LOSS_MSE = 2 };
@@ -219,6 +232,7 @@ struct SfPushArgs {
   float* vec_dst[8];              // sharded master: fp32 publish of the 1-D variables into every replica (one multicast
   int n_vec_dst;                  // alias when shadow_is_mc); indexed from vec_offset.  0 = use vec_pub
   int mb_zero;                    // applier: zero the consumed mailbox elements (accumulating wgrad epilogues add into them)
+  int dbg_skip;                   // profiling only: bit 0 = no publish stores, bit 1 = no state stores, bit 2 = no state / gradient loads
   float* grad;                    // local flat gradient (consumed, then zeroed for the next step)
   float* loss_acc;                // local: loss accumulated by the loss kernel (consumed + zeroed)
   float* loss_out;                // last step's loss for the host to read (device or pinned host memory)
@@ -304,15 +318,20 @@ struct SfApplierArgs {
   uint32_t* flags;                // [n_workers][SF_MB_WORDS]
   int n_workers;
   uint32_t* sync;                 // 8 words of master-local memory for the in-grid protocol
-  unsigned long long idle_timeout_ns;   // listening window of one launch
+  unsigned long long idle_timeout_ns;   // listening window: a launch exits after this long without any posted mailbox
+  int linger;                           // 1: keep listening after a pass (warm instruction cache / TLB for the next one: the
+                                        // pass is latency bound); 0: a launch exits as soon as nothing more is posted
   int dbuf;                       // double-buffered publish: passes alternate between (push.shadow_dst[0], push.vec_pub[0])
   __nv_bfloat16* shadow_alt;      // and (shadow_alt, vec_pub_alt); SF_CTRL_PUB bit 31 names the complete one
   float* vec_pub_alt;
   int max_batch;                  // pushes fused into one pass over the state (1..8; 0 = 8)
   // ---- sharded master: this applier owns push tiles [tile_begin, tile_end) (0, 0 = all) ----
   int tile_begin, tile_end;
-  uint32_t* ack[8];               // per worker: APPLIED word of THIS shard inside the worker's own memory (peer mapped);
-                                  // nullptr = acknowledge through flags[w][SF_MB_APPLIED] only
+  uint32_t* ack[8];               // per worker: acknowledgement word of THIS shard inside the worker's own memory (peer
+                                  // mapped); nullptr = acknowledge through flags[w][SF_MB_APPLIED] only
+  int ack_counting;               // 1: every CTA adds 1 to the word of each consumed worker right after its own tiles
+                                  // (red.release.sys: one NVLink flush per CTA, all in parallel) - the worker waits for
+                                  // posts * gridDim acknowledgements; 0: the leader stores the sequence number after the pass
   // seqlock stamps of this shard in every replica's publish segment: begin is bumped before the first publish store of a
   // pass, end after the last one; a reader's snapshot of the shard is consistent iff it read end == e before and
   // begin == e after copying.  n_ver = 1 + ver_mc: one multimem.st reaches every replica; else one store per peer.
@@ -320,6 +339,14 @@ struct SfApplierArgs {
   uint32_t* ver_end[8];
   int n_ver;
   int ver_mc;
+  // ack_counting mode: `begin` counts the passes STARTED (stamped by the leader before the first publish store), `end`
+  // counts CTA completions (every CTA adds 1 after its own fence): the shard is quiescent iff end == begin * gridDim.
+  // No leader-side end stamp, no serialised fences after the pass.  ver_local: this shard's begin stamp in the OWN
+  // replica (unicast address; survives applier restarts).
+  const uint32_t* ver_local;
+  // two publish slots per replica (lock mode): pass v writes slot v & 1 = every publish destination advanced by these
+  // element offsets, so a reader can always copy the newest COMPLETE pass while the next one is landing in the other slot
+  long long slot_off_bf16, slot_off_f32;
   unsigned long long* stats;      // optional: [0] sum(ns decide -> tiles done), [1] sum(ns decide -> acknowledged), [2] passes, [3] pushes
 };
 int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaStream_t st);
@@ -336,12 +363,14 @@ int sf_applier_launch(const SfApplierArgs* a, unsigned int seq, int grid, cudaSt
 struct SfSyncPullArgs {
   int n_shards;
   int bounds[SF_MAX_SHARDS + 1];
-  const uint32_t* applied;        // local: word r * 16 = APPLIED sequence of shard r for this worker
+  const uint32_t* applied;        // local: word r * 16 = acknowledgement word of shard r for this worker
   const uint32_t* my_posted;      // local: sequence number of my last post
+  int ack_grid[SF_MAX_SHARDS];    // CTAs of shard r's applier: the word counts CTA acknowledgements (0: it holds the sequence number)
   int copy;                       // 1: snapshot inbox -> working replica
   const uint32_t* ver_begin;      // local inbox stamps: word r * ver_stride
   const uint32_t* ver_end;
   int ver_stride;
+  long long slot_off_bf16, slot_off_f32;   // second publish slot (0: single slot, the reader waits for quiescence instead)
   const __nv_bfloat16* src;       // inbox publish buffer (local copy fed by the appliers' multicast stores)
   __nv_bfloat16* dst;             // working replica
   const float* src_vec;           // inbox fp32 copy of the 1-D tail (indexed from vec_offset)
@@ -373,6 +402,8 @@ struct SfPostFlagsArgs {
   int mb_zero;
   unsigned long long* heartbeat;     // optional: 2 words in this worker's symmetric segment (time of last post, posts)
   unsigned long long* stats;         // optional: [0] = %globaltimer of this post (see SfSyncPullArgs.stats)
+  int phase;                         // 0: everything; 1: only forward the 1-D tail (runs beside the last wgrad); 2: only post
+                                     // (every gradient store belongs to a COMPLETED kernel: no fence on the critical path)
 };
 int sf_post_flags_launch(const SfPostFlagsArgs* a, cudaStream_t st);
 int sf_preload_kernels();

@@ -308,6 +308,11 @@ class DeviceWorker:
             self.ack_words = m.view("ack", worker_index, dev)
             self.my_posted = torch.zeros(4, dtype=torch.int32, device=dev)
             self.shard_stats = torch.zeros(64, dtype=torch.int64, device=dev)      # device-side latency accounting (SfSyncPullArgs.stats)
+            ryw = self.C.pack_ryw(m.n, [m.applier_grid(r) for r in range(m.n)], native.ptr(self.ack_words), native.ptr(self.my_posted),
+                                  native.ptr(self.shard_stats))
+            self.ryw_dev = torch.frombuffer(bytearray(ryw), dtype=torch.uint8).to(dev)
+            # Hogwild: the read-your-writes wait is fused into the step's first GEMM (no pull kernel at all)
+            self.fuse_ryw = (not self.lock_mode) and os.environ.get("SPARKFLOW_NO_FUSED_PULL") != "1"
             route = self.C.pack_route(m.n, m.bounds, [m.mailbox_ptr(r, worker_index) for r in range(m.n)])
             self.route_dev = torch.frombuffer(bytearray(route), dtype=torch.uint8).to(dev)
             vt = []
@@ -376,17 +381,19 @@ class DeviceWorker:
 
         stamps = m.pub_ptr(self.worker_index, m.o_stamps)
         d = dict(n_shards=m.n, bounds=m.bounds, applied=native.ptr(self.ack_words), my_posted=native.ptr(self.my_posted),
-                 copy=1 if (copy and self.lock_mode) else 0, stats=native.ptr(self.shard_stats))
+                 copy=1 if (copy and self.lock_mode) else 0, stats=native.ptr(self.shard_stats),
+                 ack_grid=[m.applier_grid(r) for r in range(m.n)])
         if d["copy"]:
-            d.update(ver_begin=stamps, ver_end=stamps + 16 * 4, ver_stride=VER_STRIDE, src=native.ptr(self.inbox_shadow), dst=native.ptr(self.replica),
+            d.update(ver_begin=stamps, ver_end=stamps + 16 * 4, ver_stride=VER_STRIDE, slot_off_bf16=m.slot_off_bf16, slot_off_f32=m.slot_off_f32,
+                     src=native.ptr(self.inbox_shadow), dst=native.ptr(self.replica),
                      src_vec=native.ptr(self.inbox_vec) if lay.vec_count else 0, dst_vec=native.ptr(self.vec_local) if lay.vec_count else 0,
                      vec_offset=lay.vec_offset, segs=native.ptr(self.segs_dev), tile_map=native.ptr(self.tile_map),
                      ctas_per_shard=self.sync_cps, sync=native.ptr(self.sync_sp))
         return d
 
-    def _post_flags_args(self, loss_out: torch.Tensor, drop: int = 0) -> dict:
+    def _post_flags_args(self, loss_out: torch.Tensor, drop: int = 0, phase: int = 0) -> dict:
         m = self.master
-        return dict(n_shards=m.n, bounds=m.bounds, posted=[m.posted_ptr(r, self.worker_index) for r in range(m.n)],
+        return dict(phase=phase, n_shards=m.n, bounds=m.bounds, posted=[m.posted_ptr(r, self.worker_index) for r in range(m.n)],
                     mailbox=[m.mailbox_ptr(r, self.worker_index) for r in range(m.n)], grad=native.ptr(self.grads),
                     vec_tiles=native.ptr(self.vec_tiles), n_vec_tiles=self.n_vec_tiles, loss_acc=native.ptr(self.loss_acc),
                     loss_out=native.ptr(loss_out), my_posted=native.ptr(self.my_posted), drop=drop, total=self.layout.total,
@@ -578,7 +585,8 @@ class DeviceWorker:
             t0 = time.time()
             while True:
                 acks = self.ack_words.view(-1, 16)[: self.master.n, 0].cpu()
-                if all(((int(a) - posted) & 0xFFFFFFFF) < 0x80000000 for a in acks):
+                # every CTA of a shard's applier acknowledges a consumed push: posts x grid acknowledgements per shard
+                if all(((int(a) - posted * self.master.applier_grid(r)) & 0xFFFFFFFF) < 0x80000000 for r, a in enumerate(acks)):
                     return
                 if time.time() - t0 > timeout_s:
                     raise TimeoutError(f"shard appliers did not consume post {posted} of worker {self.worker_index} (acks={acks.tolist()})")

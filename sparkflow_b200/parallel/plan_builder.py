@@ -159,10 +159,23 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     branches = worker.use_branches and train
     sharded = bool(getattr(worker, "sharded", False))
     do_pull = with_pull and (worker.pull_mode != "direct" or lay.vec_count > 0)
+    fuse_ryw = False
     if sharded:
         # the step always starts with the read-your-writes wait (it also protects the mailboxes the wgrad epilogues
-        # are about to overwrite); the seqlock snapshot is only taken when this step really pulls (lock mode)
+        # are about to overwrite); the seqlock snapshot is only taken when this step really pulls (lock mode).
+        # Hogwild training steps fuse the wait into their first GEMM instead (no pull kernel at all).
         do_pull = bool(train or with_pull)
+        fuse_ryw = bool(train and getattr(worker, "fuse_ryw", False))
+        if fuse_ryw:
+            do_pull = False
+    ryw_pending = [fuse_ryw]
+
+    def ryw_args() -> Dict[str, Any]:
+        """dict entries for the first weight-reading GEMM of the step (consumed once)"""
+        if ryw_pending[0]:
+            ryw_pending[0] = False
+            return dict(ryw=P(worker.ryw_dev))
+        return {}
 
     def add_pull_op():
         if sharded:
@@ -262,7 +275,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             act_out = zeros(M, cout)
             g = C.Gemm(dict(a=P(patches), lda=ldK, b=P(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld, M=M, N=cout, K=K,
                             bias=worker._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act], out_bf16=P(act_out), ld_bf16=cout,
-                            a_evict_first=1))
+                            a_evict_first=1, **ryw_args()))
             gemms.append(g)
             plan.add_gemm(g, f"conv{i}")
             rec[i] = dict(patches=patches, patchesT=patchesT, act_out=act_out, in_shape=(h, w, cin), M=M, K=K, ldM=ldM, ldK=ldK)
@@ -283,7 +296,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
         last = i == stop_layer
         d = dict(a=P(cur["buf"]), lda=cur["ld"], b=P(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld, M=B, N=ks.cols, K=ks.rows,
-                 bias=worker._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act])
+                 bias=worker._bias_ptr(bs) if bs else 0, act=ACT_IDS[l.act], **ryw_args())
         if l.dropout_keep:
             # fused Philox dropout: the mask is a function of (row, column, step counter of this plan, layer)
             seed = (int(os.environ.get("SPARKFLOW_DROPOUT_SEED", "20260921")) ^ (0x9E3779B9 * (worker.worker_index + 1))
@@ -427,6 +440,10 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             g_img = zeros(B, h * w * cin)
             plan.add_col2im(P(dpatch), r["ldK"], B, h, w, cin, l.ksize[0], l.ksize[1], P(g_img))
             continue
+    if sharded and with_push:
+        # forward the 1-D tail (bias gradients, all complete by now on the main branch) beside the last wgrad, so the post
+        # after the join is a bare flag store: no store of its own to order, no system fence on the critical path
+        plan.add_post_flags(worker._post_flags_args(loss_out, phase=1))
     if use_mega:
         _emit_mega(plan, C, mega_items, keep)
     elif branches:
@@ -436,7 +453,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     if with_push:
         extra = dict(done_dev=P(done_dev)) if done_dev is not None else {}
         if sharded:
-            plan.add_post_flags(dict(worker._post_flags_args(loss_out), **extra))
+            plan.add_post_flags(dict(worker._post_flags_args(loss_out, phase=2), **extra))
         elif worker.served:
             plan.add_post(dict(worker._post_args(loss_out), **extra), P(worker.sync_push), 0)
         else:

@@ -83,6 +83,12 @@ class ShardedMaster:
         self.o_stamps = take(self.C.MAX_SHARDS * VER_STRIDE * 4)
         self.o_shadow = take(lay.shadow_total * 2)
         self.o_vec = take(max(lay.vec_count, 4) * 4)
+        # second publish slot (lock mode: pass v lands in slot v & 1, a pull copies the newest complete pass and never
+        # waits for one in flight); Hogwild uses slot 0 only
+        self.o_shadow1 = take(lay.shadow_total * 2)
+        self.o_vec1 = take(max(lay.vec_count, 4) * 4)
+        self.slot_off_bf16 = (self.o_shadow1 - self.o_shadow) // 2
+        self.slot_off_f32 = (self.o_vec1 - self.o_vec) // 4
         pub_bytes = off
         # ---- shard segment: ctrl | state | flags | applier sync | acks | mailboxes ----
         off = 0
@@ -180,6 +186,10 @@ class ShardedMaster:
             return _view(self.pub_ptr(shard, self.o_shadow), lay.shadow_total * 2, torch.bfloat16, dev)
         if which == "vec":
             return _view(self.pub_ptr(shard, self.o_vec), max(lay.vec_count, 4) * 4, torch.float32, dev)
+        if which == "shadow1":
+            return _view(self.pub_ptr(shard, self.o_shadow1), lay.shadow_total * 2, torch.bfloat16, dev)
+        if which == "vec1":
+            return _view(self.pub_ptr(shard, self.o_vec1), max(lay.vec_count, 4) * 4, torch.float32, dev)
         if which == "stamps":
             return _view(self.pub_ptr(shard, self.o_stamps), self.C.MAX_SHARDS * VER_STRIDE * 4, torch.int32, dev)
         raise KeyError(which)
@@ -195,8 +205,8 @@ class ShardedMaster:
             with torch.cuda.device(dev):
                 me = self.ctx.rank
                 self.view("state", me, dev).copy_(self.view("state", 0, dev))
-                self.view("shadow", me, dev).copy_(self.view("shadow", 0, dev))
-                self.view("vec", me, dev).copy_(self.view("vec", 0, dev))
+                for nm in ("shadow", "vec", "shadow1", "vec1"):
+                    self.view(nm, me, dev).copy_(self.view(nm, 0, dev))
                 _sync_current(dev)
             D.barrier(self.ctx)
             return
@@ -214,6 +224,8 @@ class ShardedMaster:
                 self.view("state", s).copy_(host)
                 self.view("shadow", s).copy_(pub)
                 self.view("vec", s).copy_(vec)
+                self.view("shadow1", s).copy_(pub)
+                self.view("vec1", s).copy_(vec)
                 self.view("ctrl", s).zero_()
                 self.view("stamps", s).zero_()
                 _sync_current(dev)
@@ -278,12 +290,14 @@ class ShardedMaster:
                 "errors": int(sum(c[4] for c in cs)), "dropped": int(cs[0][5]), "shards": self.n, "multicast": int(self.multicast)}
 
     # ---- appliers ---------------------------------------------------------------------------------------------
-    def start_applier(self, acquire_lock: bool, scope_sys: bool = True, grid: int = 0, poll_window_s: float = 30e-6, depth: int = 3,
+    def start_applier(self, acquire_lock: bool, scope_sys: bool = True, grid: int = 0, poll_window_s: float = 0.0, depth: int = 3,
                       max_batch: int = 0, dbuf: bool = False) -> None:
         """One applier per owned shard.  ``acquire_lock`` selects seqlock-stamped publishes (pulls snapshot a shard
         atomically); Hogwild publishes without stamps.  No RW lock anywhere: a shard has exactly one writer."""
         lay, C = self.layout, self.C
         self.lock_mode = bool(acquire_lock)
+        # a launch lingers between passes (warm code / TLB) and exits after this long without a post
+        poll_window_s = poll_window_s or float(os.environ.get("SPARKFLOW_APPLIER_IDLE_US", "300")) * 1e-6
         for s in self.my_shards:
             if s in self.appliers:
                 continue
@@ -307,19 +321,28 @@ class ShardedMaster:
                             shadow_is_mc=1 if self.multicast else 0, vec_dst=vec_dst if lay.vec_count else [], vec_offset=lay.vec_offset,
                             grad=0, applier=1, segs=native.ptr(segs_dev), tile_map=native.ptr(tile_map), num_tiles=self.n_tiles,
                             seg_rows=lay.seg_rows(), optimizer=self.spec.opt_id, lock_mode=0, drop=0, scope_sys=1 if scope_sys else 0,
-                            grad_scale=1.0, hyper=self.spec.native_hyper(), mb_zero=1 if self.mb_zero else 0)
+                            grad_scale=1.0, hyper=self.spec.native_hyper(), mb_zero=1 if self.mb_zero else 0,
+                            dbg_skip=int(os.environ.get("SPARKFLOW_DEBUG_SKIP", "0")))
                 if s not in self._stats:
-                    self._stats[s] = torch.zeros(8, dtype=torch.int64, device=dev)
+                    self._stats[s] = torch.zeros(16, dtype=torch.int64, device=dev)
                 shard = dict(tile_begin=self.bounds[s], tile_end=self.bounds[s + 1], ack=[self.ack_ptr(w, s) for w in range(self.n)],
-                             stats=native.ptr(self._stats[s]))
+                             stats=native.ptr(self._stats[s]), ack_counting=1,
+                             linger=int(os.environ.get("SPARKFLOW_APPLIER_LINGER", "1")))
                 if self.lock_mode:
                     shard.update(ver_begin=[p + s * VER_STRIDE * 4 for p in stamps], ver_end=[p + (s * VER_STRIDE + 16) * 4 for p in stamps],
-                                 ver_mc=1 if self.multicast else 0)
-                n_own = max(1, self.bounds[s + 1] - self.bounds[s])
-                g = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "0")) or min(112, n_own)
+                                 ver_mc=1 if self.multicast else 0, ver_local=self.pub_ptr(s, self.o_stamps) + s * VER_STRIDE * 4,
+                                 slot_off_bf16=self.slot_off_bf16, slot_off_f32=self.slot_off_f32)
+                if grid and grid != self.applier_grid(s):
+                    raise ValueError("the applier grid of a sharded master is fixed by applier_grid(): workers count its acknowledgements")
+                g = self.applier_grid(s)
                 self.appliers[s] = C.Applier(push, self.seg_ptr(s, self.o_mail), self.mb_stride, self.seg_ptr(s, self.o_flags), self.n,
                                              self.seg_ptr(s, self.o_sync), poll_window_s, g, depth,
                                              max_batch or int(os.environ.get("SPARKFLOW_APPLIER_BATCH", "8")), 0, 0, shard)
+
+    def applier_grid(self, shard: int) -> int:
+        """CTAs of shard ``shard``'s applier (the same number on every rank: workers wait for posts x grid acknowledgements)."""
+        n_own = max(1, self.bounds[shard + 1] - self.bounds[shard])
+        return int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "0")) or min(112, n_own)
 
     def applier_latency(self) -> Dict[str, float]:
         """Device-measured averages of the owned shards' appliers: decision -> all tiles applied + published (`apply_us`),
@@ -331,6 +354,11 @@ class ShardedMaster:
                 out["apply_us"] = max(out["apply_us"], v[0] / v[2] / 1e3)
                 out["ack_us"] = max(out["ack_us"], v[1] / v[2] / 1e3)
                 out["passes"] = max(out["passes"], int(v[2]))
+                out["cta_saw_decision_us"] = v[4] / v[2] / 1e3
+                out["cta_tiles_us"] = v[5] / v[2] / 1e3
+                out["cta_flush_us"] = v[6] / v[2] / 1e3
+                for i, nm in enumerate(["t_list", "t_issue", "t_loads_math", "t_stores", "t_transpose", "t_timer_read"]):
+                    out["cta_" + nm + "_us"] = v[8 + i] / v[2] / 1e3
                 out["pushes_per_pass"] = max(out["pushes_per_pass"], float(v[3]) / float(v[2]))
         return out
 
