@@ -133,13 +133,15 @@ def run_ours(args, ctx) -> dict:
 
     def timed(engine, n, start):
         """n steps, one event pair, max over ranks; returns (ms, wall_ms)."""
-        sess.quiesce()                   # barrier + device-wide synchronize (appliers paused around it)
+        sess.sync_all()                  # drain + barrier + device-wide torch.cuda.synchronize() + barrier
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(st)
         steps(engine, n, start)
         e1.record(st)
         engine.finish()                  # stream sync + wait until the master has applied this rank's last push
+        torch.cuda.synchronize(dev)
+        D.barrier(ctx)
         wall = time.perf_counter() - t0
         return _max_over_ranks(ctx, e0.elapsed_time(e1)), _max_over_ranks(ctx, wall * 1e3)
 
@@ -165,7 +167,7 @@ def run_ours(args, ctx) -> dict:
     Ks = _sustained_steps(K, dev_ms / K)
     sus_ms, _ = timed(eng_r, Ks, W + K)
     last_loss = eng_r.last_loss()
-    sess.quiesce()
+    sess.sync_all()
     # exposed push / pull per step, measured on the device (%globaltimer) inside the pull / applier kernels
     exposed = None
     if getattr(eng.w, "sharded", False):

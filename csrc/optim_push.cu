@@ -953,7 +953,16 @@ sync_pull_kernel(const SfSyncPullArgs a) {
   uint32_t* sy = a.sync + shard * 8;          // 0 arrivals, 1 min version, 2 max version / dirty, 3 result (round << 1 | ok), 4 round
   const unsigned long long t0 = gtime_ns();
   while (true) {
-    if (tid == 0) {
+    uint32_t round = 0;
+    if (tid == 0 && cps > 1) round = ld_acquire_gpu(sy + 4);
+    if (tid == 0 && cps > 1 && part != 0) {
+      // the shard's first CTA picks the version for all of them (independent picks disagree whenever a pass completes
+      // between two CTAs' reads - which is exactly when the acknowledgements they just waited for arrive)
+      while (ld_acquire_gpu(sy + 6) != round + 1) {
+        if (gtime_ns() - t0 > kLockTimeoutNs) sf_fail(0x40D);
+      }
+      s_e = sy[5];
+    } else if (tid == 0) {
       // seqlock reader without fences: the stamp loads are relaxed.sys (served by L2, the coherence point of local
       // memory); the copy's loads cannot issue before the version is known (bar.sync below) and the re-check of `begin`
       // is issued after the copy's values were consumed by its stores (bar.sync), i.e. in program order.
@@ -972,6 +981,10 @@ sync_pull_kernel(const SfSyncPullArgs a) {
         }
       }
       s_e = b;
+      if (cps > 1) {
+        sy[5] = b;
+        st_release_gpu(sy + 6, round + 1);
+      }
     }
     __syncthreads();
     {
@@ -991,7 +1004,6 @@ sync_pull_kernel(const SfSyncPullArgs a) {
         ok = clean ? 1u : 0u;
       } else {
         // agreement round: min / max over the CTAs' versions (a dirty CTA poisons max), last arriver publishes the verdict
-        const uint32_t round = ld_acquire_gpu(sy + 4);
         atomicMin(sy + 1, e);
         atomicMax(sy + 2, clean ? e : 0xFFFFFFFFu);
         if (lk_add_release<false>(sy + 0, 1u) == static_cast<uint32_t>(cps) - 1u) {

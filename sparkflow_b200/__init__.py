@@ -17,10 +17,12 @@ __version__ = "0.2.0"
 
 import os as _os
 
-# One hardware launch queue per stream (the default is 8): device-side waits (a worker's pull spinning until the shard
-# appliers acknowledge its push) must never share a queue with the applier kernels they wait for.  Only effective when
-# set before the CUDA context is created, which importing this package normally precedes.
-_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Single-process multi-worker runs (several worker threads + shard appliers on the same GPU, e.g. the test-suite) create
+# more streams than the default 8 hardware launch queues; streams that share a queue can delay each other's launches.
+# Opt in with SPARKFLOW_MAX_CONNECTIONS=32 (must be set before the CUDA context exists); one-process-per-GPU runs use 7
+# streams and keep the driver default.
+if _os.environ.get("SPARKFLOW_MAX_CONNECTIONS"):
+    _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", _os.environ["SPARKFLOW_MAX_CONNECTIONS"])
 
 from .graph_utils import (build_adadelta_config, build_adagrad_config, build_adam_config, build_gradient_descent,  # noqa: F401
                           build_graph, build_momentum_config, build_rmsprop_config)

@@ -181,6 +181,20 @@ class TrainingSession:
             return f"master sharded over {n} gpus, one applier per shard, multicast publish"
         return "master on gpu0" + (", mailbox + applier" if self.push_mode == "served" else ", worker-applied push")
 
+    def sync_all(self) -> None:
+        """Collective: drain every worker (its last push is applied everywhere), barrier, device-wide
+        ``torch.cuda.synchronize()``, barrier - WITHOUT stopping the appliers (they are finite, re-queued kernels: a
+        device-wide synchronise only waits for the launches already enqueued).  Benchmarks bracket timed regions with it."""
+        ctx = self.ctx
+        for w in self._workers:
+            if hasattr(w, "drain"):
+                w.drain()
+        D.barrier(ctx)
+        if self.use_cuda:
+            for d in self.local_devices():
+                torch.cuda.synchronize(d)
+        D.barrier(ctx)
+
     def quiesce(self) -> None:
         """Collective: drain every worker, stop the applier, do a genuine device-wide ``torch.cuda.synchronize()``
         and bring the applier back.  Benchmarks bracket their timed regions with this (a device-wide synchronise

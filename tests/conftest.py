@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# several workers + appliers share one GPU in the tests: one hardware launch queue per stream (see sparkflow_b200/__init__.py)
+os.environ.setdefault("SPARKFLOW_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
