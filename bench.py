@@ -300,7 +300,13 @@ def main() -> int:
         if ctx.rank == 0:
             print(json.dumps({"metric": METRIC, "error": f"--gpus {args.gpus} but WORLD_SIZE is {ctx.world}; launch with torchrun"}))
         return 1
-    res = run_ours(args, ctx) if args.impl == "ours" else run_nccl(args, ctx)
+    try:
+        res = run_ours(args, ctx) if args.impl == "ours" else run_nccl(args, ctx)
+    except Exception:
+        from sparkflow_b200.ops import native
+
+        sys.stderr.write(f"[rank {ctx.rank}] device error channel: {native.describe_device_error()}\n")
+        raise
     if args.impl == "ours" and not args.no_baseline:
         try:
             base = run_nccl(args, ctx)

@@ -249,7 +249,10 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   float* s_bias = reinterpret_cast<float*>(smem + S::kStages * S::kStageBytes + S::kBarBytes);
 
   TraceScope trace;
-  pdl_launch_dependents();
+  // A GEMM that carries the fused read-your-writes wait may spin for a while: do NOT let its successors pre-launch behind
+  // it (they would sit resident on SMs - one CTA per SM at this shared-memory size - that the shard applier whose
+  // acknowledgement this kernel waits for needs for its own CTAs).
+  if (ep.ryw == nullptr) pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN;

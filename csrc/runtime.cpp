@@ -865,6 +865,7 @@ class Applier {
       args_.stats = P<unsigned long long>(getd<uintptr_t>(shard, "stats", 0));
       args_.ack_counting = getd<int>(shard, "ack_counting", 0);
       args_.linger = getd<int>(shard, "linger", 0);
+      args_.warm_polls = getd<int>(shard, "warm_polls", 0);
       args_.ver_local = P<const uint32_t>(getd<uintptr_t>(shard, "ver_local", 0));
       args_.slot_off_bf16 = getd<long long>(shard, "slot_off_bf16", 0);
       args_.slot_off_f32 = getd<long long>(shard, "slot_off_f32", 0);

@@ -319,6 +319,10 @@ struct SfApplierArgs {
   int n_workers;
   uint32_t* sync;                 // 8 words of master-local memory for the in-grid protocol
   unsigned long long idle_timeout_ns;   // listening window: a launch exits after this long without any posted mailbox
+  int warm_polls;                       // > 0: follower CTAs re-execute the tile code as a dry run (no memory traffic)
+                                        // after every `warm_polls` unsuccessful polls, and CTA 0 only coordinates (owns no
+                                        // tile): the pass is bound by instruction fetch when the code was evicted by the
+                                        // training kernels sharing the SM (measured: 7 us cold vs the memory-bound ~2 us)
   int linger;                           // 1: keep listening after a pass (warm instruction cache / TLB for the next one: the
                                         // pass is latency bound); 0: a launch exits as soon as nothing more is posted
   int dbuf;                       // double-buffered publish: passes alternate between (push.shadow_dst[0], push.vec_pub[0])

@@ -163,7 +163,8 @@ class MasterState:
                         segs=native.ptr(self._segs_dev), tile_map=native.ptr(self._tile_map), num_tiles=int(self._tile_map.shape[0]),
                         seg_rows=lay.seg_rows(), optimizer=self.spec.opt_id, lock_mode=1 if acquire_lock else 0, drop=0,
                         scope_sys=1 if scope_sys else 0, grad_scale=1.0, hyper=self.spec.native_hyper())
-            grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "112"))
+            # every CTA (512 threads, one per SM) must be resident at once, beside the training kernels of this GPU
+            grid = grid or int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "64"))
             self.applier = self.C.Applier(push, self.base + self.ml.mailboxes, self.ml.mailbox_stride, self.base + self.ml.flags,
                                           self.ml.n_mailboxes, self.base + self.ml.applier_sync, poll_window_s, grid, depth,
                                           max_batch or int(os.environ.get("SPARKFLOW_APPLIER_BATCH", "8")),
@@ -325,7 +326,7 @@ class DeviceWorker:
             # snapshot pull: the copy is latency bound, so give every shard as many CTAs as it has tiles (all CTAs of the
             # kernel must be co-resident for the per-shard version agreement: at most one CTA per SM in total)
             tiles_per_shard = max(1, -(-m.n_tiles // m.n))
-            self.sync_cps = max(1, min(tiles_per_shard, 148 // m.n, int(os.environ.get("SPARKFLOW_PULL_CTAS_PER_SHARD", "64"))))
+            self.sync_cps = max(1, min(tiles_per_shard, 148 // m.n, int(os.environ.get("SPARKFLOW_PULL_CTAS_PER_SHARD", "16"))))
             init = torch.zeros(8, 8, dtype=torch.int64)
             init[:, 1] = 0xFFFFFFFF
             self.sync_sp = torch.from_numpy(init.numpy().astype("uint32").view("int32").copy()).to(dev)
@@ -340,12 +341,14 @@ class DeviceWorker:
         self.segs_dev = torch.frombuffer(bytearray(self.C.pack_segs(lay.seg_rows())), dtype=torch.uint8).to(dev)
         self.tile_map = torch.from_numpy(lay.tile_map()).to(dev)
         self._plans: Dict[Tuple[int, int], object] = {}
+        self._ordered: set = set()
         self._fetch = None
         self._input_sets: Dict[Tuple[int, int], Dict[str, Any]] = {}
         self._bufs: Dict[Tuple[int, int], StepBuffers] = {}
         self._keep: List[object] = []
         self.drop_next = 0
         self.launches_per_step = 0
+        self._order_after_build()          # the tables uploaded above (torch current stream) precede any plan kernel
 
     @classmethod
     def for_inference(cls, ir: GraphIR, plan: LayerPlan, spec: OptimizerSpec, master: MasterState) -> "DeviceWorker":
@@ -492,7 +495,15 @@ class DeviceWorker:
             plan = self.C.Plan()
             plan_builder.add_fetch_ops(plan, dict(args=self.fetch_args(B, slot), target=self.input_set(B, slot)), B, self.plan.input_dim)
             self._plans[key] = plan
+            self._order_after_build()
         return self._plans[key]
+
+    def _order_after_build(self) -> None:
+        """Plan building allocates (zero-fills) and uploads through torch's CURRENT stream; the worker's streams are
+        non-blocking ones, so nothing orders those fills before the plan's first kernels unless we say so."""
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
+        self.copy_stream.wait_stream(cur)
 
     def build_plan(self, B: int, slot: int = 0, with_pull: bool = True, with_push: bool = True, fetch_slots: int = 0,
                    resident: Optional[Tuple[torch.Tensor, Optional[torch.Tensor]]] = None):
@@ -526,6 +537,9 @@ class DeviceWorker:
             self._keep.append(built.keep)
             self.launches_per_step = len(built.plan)
             self._last_names = list(built.plan.names())
+        if key not in self._ordered:
+            self._ordered.add(key)
+            self._order_after_build()
         return self._plans[key], self._bufs[key]
 
     def build_forward_plan(self, B: int, upto: Optional[int] = None, post: Optional[str] = None, with_loss: bool = False,
@@ -540,6 +554,7 @@ class DeviceWorker:
             self._plans[key] = built.plan
             self._bufs[key] = StepBuffers(built.x_stage, built.y_stage, built.loss_out, built.result)
             self._keep.append(built.keep)
+            self._order_after_build()
         return self._plans[key], self._bufs[key]
 
     EVAL_CHUNK = 4096

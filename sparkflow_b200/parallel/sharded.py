@@ -105,6 +105,8 @@ class ShardedMaster:
         self.pub = SymmetricHeap(pub_bytes, ctx if self.spmd else None, idx, multicast=True, tag="pub")
         self.seg = SymmetricHeap(seg_bytes, ctx if self.spmd else None, idx, multicast=False, tag="seg")
         self.multicast = self.pub.multicast
+        # follower CTAs of an applier keep their tile code warm with dry runs between polls; CTA 0 then owns no tile
+        self.warm_polls = int(os.environ.get("SPARKFLOW_APPLIER_WARM_POLLS", "0"))
         self.appliers: Dict[int, object] = {}
         self._stats: Dict[int, torch.Tensor] = {}
         self._keep: List[object] = []
@@ -327,7 +329,7 @@ class ShardedMaster:
                     self._stats[s] = torch.zeros(16, dtype=torch.int64, device=dev)
                 shard = dict(tile_begin=self.bounds[s], tile_end=self.bounds[s + 1], ack=[self.ack_ptr(w, s) for w in range(self.n)],
                              stats=native.ptr(self._stats[s]), ack_counting=1,
-                             linger=int(os.environ.get("SPARKFLOW_APPLIER_LINGER", "1")))
+                             linger=int(os.environ.get("SPARKFLOW_APPLIER_LINGER", "1")), warm_polls=self.warm_polls)
                 if self.lock_mode:
                     shard.update(ver_begin=[p + s * VER_STRIDE * 4 for p in stamps], ver_end=[p + (s * VER_STRIDE + 16) * 4 for p in stamps],
                                  ver_mc=1 if self.multicast else 0, ver_local=self.pub_ptr(s, self.o_stamps) + s * VER_STRIDE * 4,
@@ -342,7 +344,11 @@ class ShardedMaster:
     def applier_grid(self, shard: int) -> int:
         """CTAs of shard ``shard``'s applier (the same number on every rank: workers wait for posts x grid acknowledgements)."""
         n_own = max(1, self.bounds[shard + 1] - self.bounds[shard])
-        return int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "0")) or min(112, n_own)
+        # An applier CTA (512 threads x ~96 registers) owns its SM while the launch lingers, and every CTA of the grid
+        # must be resident at once: small shards get one CTA per tile (lowest pass latency), larger ones are capped so
+        # the training kernels of the same GPU keep most of the SMs (big models: up to half of them).
+        cap = 40 if n_own <= 160 else 74
+        return int(os.environ.get("SPARKFLOW_APPLIER_CTAS", "0")) or (min(cap, n_own) + (1 if self.warm_polls > 0 else 0))
 
     def applier_latency(self) -> Dict[str, float]:
         """Device-measured averages of the owned shards' appliers: decision -> all tiles applied + published (`apply_us`),

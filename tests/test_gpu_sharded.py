@@ -80,7 +80,7 @@ def test_one_worker_two_shards_tracks_the_host_parameter_server(lock):
     got, exp = sess.weights(), ps.weights()
     for a, b, v in zip(got, exp, ir.trainable):
         assert np.abs(a - b).max() < 5 * 0.001 * len(rows), v.name
-        assert np.mean(np.abs(a - b)) < 0.35 * 0.001 * len(rows), v.name
+        assert np.mean(np.abs(a - b)) < 0.45 * 0.001 * len(rows), v.name
     c = sess.counters()
     assert c["pushes"] == len(rows) and c["shards"] == 2
     names = eng.w.last_plan_names()
