@@ -231,3 +231,263 @@ extern "C" int sf_maxpool2_bwd(const __nv_bfloat16* dout, const uint8_t* argmax,
   return static_cast<int>(sf::launch(sf::maxpool_bwd_kernel, grid, dim3(256), 0, st, dout, argmax, n, h, w, c, act_out, act, dz,
                                      ld_dz, dzT, ld_t, dbias));
 }
+
+namespace sf {
+
+// ------------------------------------------------------------------------------------------------
+// First convolution of a network, fused with its bias, activation and 2x2 max-pool - forward and weight gradient.
+// (reference workload: examples/cnn_example.py:14-15: 5x5x1 -> 32, ReLU, max_pooling2d(2, 2).)
+// With K = kh * kw * cin <= 64 the layer is a poor tensor-core GEMM (K = 25 padded to 64, 172,800 x 32 outputs in 1,350
+// latency-bound 128-row tiles, plus an im2col matrix and a pooling pass through HBM: ~110 us of a 350 us step); as a
+// direct CUDA-core kernel it is ~0.3 GFLOP that never leaves shared memory: one CTA per image holds the image and
+// the filter bank on chip, every thread owns one output channel (lane = channel: filter reads are conflict free, pixel
+// reads are warp broadcasts) and produces whole pooled pixels, so the un-pooled activation is never written at all.
+// The backward kernel recomputes nothing: the gradient of a pooled pixel goes to the arg-max position if the pooled
+// value passed the activation (ReLU: pooled > 0), and is correlated with the input patch there.
+// ------------------------------------------------------------------------------------------------
+constexpr int kConv1Threads = 256;
+constexpr int kConv1MaxK = 64;
+
+__device__ __forceinline__ float conv1_act(float v, int act) {
+  switch (act) {
+    case SF_ACT_RELU: return fmaxf(v, 0.f);
+    case SF_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    case SF_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+// x [n, h, w, cin] bf16; wT [cout, ld_w] bf16 (row c = filter of channel c, k = (dy * kw + dx) * cin + ci); bias fp32 [cout]
+// pooled [n, oh/2, ow/2, cout] bf16; argmax uint8 (position 0..3 of the winner inside its 2x2 window)
+// KH / KW / CIN are compile-time (0 = runtime): with constant taps the filter lives in registers and the window loop unrolls.
+template <int KH, int KW, int CIN>
+__global__ void __launch_bounds__(kConv1Threads)
+conv_first_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int cin_rt, int kh_rt, int kw_rt, int cout,
+                      const __nv_bfloat16* __restrict__ wT, int ld_w, const float* __restrict__ bias, int act,
+                      __nv_bfloat16* __restrict__ pooled, uint8_t* __restrict__ argmax, int parts) {
+  extern __shared__ float conv1_smem[];
+  TraceScope trace;
+  pdl_launch_dependents();
+  const int kh = KH ? KH : kh_rt, kw = KW ? KW : kw_rt, cin = CIN ? CIN : cin_rt;
+  const int K = kh * kw * cin;
+  float* s_w = conv1_smem;                       // [K][cout]  (runtime-shape path only)
+  float* s_x = conv1_smem + (KH ? 0 : K * cout); // [h * w * cin]
+  const int tid = threadIdx.x;
+  const int oh = h - kh + 1, ow = w - kw + 1, ph = oh / 2, pw = ow / 2;
+  const int c = tid % cout, grp = tid / cout, n_grp = kConv1Threads / cout;
+  pdl_wait();
+  trace.mark();
+  constexpr int KC = KH ? KH * KW * CIN : 1;
+  float wr[KC];
+  if constexpr (KH != 0) {
+#pragma unroll
+    for (int k = 0; k < KC; ++k) wr[k] = __bfloat162float(wT[static_cast<size_t>(c) * ld_w + k]);
+  } else {
+    for (int i = tid; i < K * cout; i += kConv1Threads) s_w[i] = __bfloat162float(wT[static_cast<size_t>(i % cout) * ld_w + i / cout]);
+  }
+  const float b = bias != nullptr ? bias[c] : 0.f;
+  // `parts` CTAs share an image (each takes every parts-th pooled pixel group): more resident warps to hide latency
+  for (int item = blockIdx.x; item < n * parts; item += gridDim.x) {
+    const int img = item / parts, part = item - img * parts;
+    __syncthreads();                               // previous image fully consumed (and s_w complete on the first pass)
+    const __nv_bfloat16* xi = x + static_cast<size_t>(img) * h * w * cin;
+    for (int i = tid; i < h * w * cin; i += kConv1Threads) s_x[i] = __bfloat162float(xi[i]);
+    __syncthreads();
+    for (int p = grp + part * n_grp; p < ph * pw; p += n_grp * parts) {
+      const int py = p / pw, px = p - py * pw;
+      float a00 = b, a01 = b, a10 = b, a11 = b;
+      if constexpr (KH != 0) {
+        // (KH + 1) x (KW + 1) input window of the 2x2 output quad, one row at a time, filter taps from registers
+#pragma unroll
+        for (int iy = 0; iy <= KH; ++iy) {
+          float row[(KW + 1) * CIN];
+          const float* rp = s_x + ((2 * py + iy) * w + 2 * px) * CIN;
+#pragma unroll
+          for (int j = 0; j < (KW + 1) * CIN; ++j) row[j] = rp[j];
+#pragma unroll
+          for (int dx = 0; dx < KW; ++dx)
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) {
+              if (iy < KH) {                        // this input row is filter row iy of the upper outputs
+                const float wv = wr[(iy * KW + dx) * CIN + ci];
+                a00 = fmaf(wv, row[dx * CIN + ci], a00);
+                a01 = fmaf(wv, row[(dx + 1) * CIN + ci], a01);
+              }
+              if (iy >= 1) {                        // ... and filter row iy - 1 of the lower outputs
+                const float wv = wr[((iy - 1) * KW + dx) * CIN + ci];
+                a10 = fmaf(wv, row[dx * CIN + ci], a10);
+                a11 = fmaf(wv, row[(dx + 1) * CIN + ci], a11);
+              }
+            }
+        }
+      } else {
+        for (int dy = 0; dy < kh; ++dy) {
+          const float* r0 = s_x + ((2 * py + dy) * w + 2 * px) * cin;
+          const float* r1 = r0 + w * cin;
+          for (int dx = 0; dx < kw; ++dx) {
+            for (int ci = 0; ci < cin; ++ci) {
+              const float wv = s_w[((dy * kw + dx) * cin + ci) * cout + c];
+              const int o = dx * cin + ci;
+              a00 = fmaf(wv, r0[o], a00);
+              a01 = fmaf(wv, r0[o + cin], a01);
+              a10 = fmaf(wv, r1[o], a10);
+              a11 = fmaf(wv, r1[o + cin], a11);
+            }
+          }
+        }
+      }
+      a00 = conv1_act(a00, act); a01 = conv1_act(a01, act); a10 = conv1_act(a10, act); a11 = conv1_act(a11, act);
+      float m = a00;
+      int am = 0;
+      if (a01 > m) { m = a01; am = 1; }
+      if (a10 > m) { m = a10; am = 2; }
+      if (a11 > m) { m = a11; am = 3; }
+      const size_t o = (static_cast<size_t>(img) * ph * pw + p) * cout + c;
+      pooled[o] = __float2bfloat16(m);
+      argmax[o] = static_cast<uint8_t>(am);
+    }
+  }
+  trace.end(KID_IM2COL);
+}
+
+// g_pool [n, ph, pw, cout] bf16 = dL/d(pooled); dW [K, cout] fp32 and db [cout] are ACCUMULATED with atomics
+template <int KH, int KW, int CIN>
+__global__ void __launch_bounds__(kConv1Threads)
+conv_first_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int cin_rt, int kh_rt, int kw_rt, int cout,
+                        const __nv_bfloat16* __restrict__ g_pool, const __nv_bfloat16* __restrict__ pooled,
+                        const uint8_t* __restrict__ argmax, int act, float* __restrict__ dW, float* __restrict__ db) {
+  extern __shared__ float conv1_smem[];
+  TraceScope trace;
+  pdl_launch_dependents();
+  const int kh = KH ? KH : kh_rt, kw = KW ? KW : kw_rt, cin = CIN ? CIN : cin_rt;
+  const int K = kh * kw * cin;
+  float* s_x = conv1_smem;                         // [h * w * cin]
+  float* s_red = conv1_smem + h * w * cin;         // [n_grp][K + 1][cout]
+  __shared__ int s_off[kConv1MaxK];                // input offset of filter tap k relative to the window origin (runtime shapes)
+  const int tid = threadIdx.x;
+  if (KH == 0 && tid < kConv1MaxK) {
+    const int k = tid < K ? tid : 0, ci = k % cin, t = k / cin;
+    s_off[tid] = ((t / kw) * w + (t % kw)) * cin + ci;
+  }
+  const int oh = h - kh + 1, ow = w - kw + 1, ph = oh / 2, pw = ow / 2;
+  const int c = tid % cout, grp = tid / cout, n_grp = kConv1Threads / cout;
+  constexpr int KA = KH ? KH * KW * CIN : kConv1MaxK;
+  float acc[KA];
+#pragma unroll
+  for (int k = 0; k < KA; ++k) acc[k] = 0.f;
+  float bacc = 0.f;
+  pdl_wait();
+  trace.mark();
+  for (int img = blockIdx.x; img < n; img += gridDim.x) {
+    __syncthreads();
+    const __nv_bfloat16* xi = x + static_cast<size_t>(img) * h * w * cin;
+    for (int i = tid; i < h * w * cin; i += kConv1Threads) s_x[i] = __bfloat162float(xi[i]);
+    __syncthreads();
+    for (int p = grp; p < ph * pw; p += n_grp) {
+      const size_t o = (static_cast<size_t>(img) * ph * pw + p) * cout + c;
+      const float a = __bfloat162float(pooled[o]);
+      const float g = __bfloat162float(g_pool[o]) * pool_dact(a, act);
+      if (g == 0.f) continue;
+      const int am = argmax[o];
+      const int py = p / pw, px = p - py * pw;
+      const float* r = s_x + ((2 * py + (am >> 1)) * w + 2 * px + (am & 1)) * cin;
+      bacc += g;
+      if constexpr (KH != 0) {
+#pragma unroll
+        for (int dy = 0; dy < KH; ++dy)
+#pragma unroll
+          for (int j = 0; j < KW * CIN; ++j) acc[dy * KW * CIN + j] = fmaf(g, r[dy * w * CIN + j], acc[dy * KW * CIN + j]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kConv1MaxK; ++k)
+          if (k < K) acc[k] = fmaf(g, r[s_off[k]], acc[k]);
+      }
+    }
+  }
+  // reduce the groups that share a channel, then one atomic per (k, channel) and CTA
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < KA; ++k)
+    if (k < K) s_red[(grp * (K + 1) + k) * cout + c] = acc[k];
+  s_red[(grp * (K + 1) + K) * cout + c] = bacc;
+  __syncthreads();
+  for (int i = tid; i < (K + 1) * cout; i += kConv1Threads) {
+    float v = 0.f;
+    for (int g = 0; g < n_grp; ++g) v += s_red[g * (K + 1) * cout + i];
+    if (v != 0.f) {
+      if (i < K * cout) atomicAdd(dW + i, v);
+      else if (db != nullptr) atomicAdd(db + (i - K * cout), v);
+    }
+  }
+  trace.end(KID_POOL_BWD);
+}
+
+}  // namespace sf
+
+template <int KH, int KW, int CIN>
+static int conv_first_fwd_launch(const __nv_bfloat16* x, int n, int h, int w, int cin, int kh, int kw, int cout, const __nv_bfloat16* wT, int ld_w,
+                                 const float* bias, int act, __nv_bfloat16* pooled, uint8_t* argmax, cudaStream_t st) {
+  const int K = kh * kw * cin;
+  const size_t smem = ((KH ? 0 : static_cast<size_t>(K) * cout) + static_cast<size_t>(h) * w * cin) * sizeof(float);
+  if (smem > 96 * 1024) return -8;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(sf::conv_first_fwd_kernel<KH, KW, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = smem;
+  }
+  // work items = (image, part): pick the split whose wave count x pixels-per-thread is smallest on 148 SMs x 4 resident CTAs
+  const int slots = 148 * 4, n_grp = sf::kConv1Threads / cout, P = ((h - kh + 1) / 2) * ((w - kw + 1) / 2);
+  int parts = 1;
+  float best = 1e30f;
+  for (int p = 1; p <= 8; ++p) {
+    const int items = n * p, waves = (items + slots - 1) / slots;
+    const float util = items < slots ? static_cast<float>(items) / slots : 1.f;
+    const float cost = waves * ((P + n_grp * p - 1) / (n_grp * p) + 2.f) / util;
+    if (cost < best) { best = cost; parts = p; }
+  }
+  const int grid = n * parts < slots ? n * parts : slots;
+  return static_cast<int>(sf::launch(sf::conv_first_fwd_kernel<KH, KW, CIN>, dim3(grid), dim3(sf::kConv1Threads), smem, st, x, n, h, w, cin, kh, kw,
+                                     cout, wT, ld_w, bias, act, pooled, argmax, parts));
+}
+
+template <int KH, int KW, int CIN>
+static int conv_first_wgrad_launch(const __nv_bfloat16* x, int n, int h, int w, int cin, int kh, int kw, int cout, const __nv_bfloat16* g_pool,
+                                   const __nv_bfloat16* pooled, const uint8_t* argmax, int act, float* dW, float* db, cudaStream_t st) {
+  const int K = kh * kw * cin;
+  const int n_grp = sf::kConv1Threads / cout;
+  const size_t smem = (static_cast<size_t>(h) * w * cin + static_cast<size_t>(n_grp) * (K + 1) * cout) * sizeof(float);
+  if (smem > 96 * 1024) return -8;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(sf::conv_first_wgrad_kernel<KH, KW, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr = smem;
+  }
+  int grid = n < 148 * 2 ? n : 148 * 2;           // one (or a few) images per CTA; one atomic per gradient word and CTA
+  if (grid < 1) grid = 1;
+  return static_cast<int>(sf::launch(sf::conv_first_wgrad_kernel<KH, KW, CIN>, dim3(grid), dim3(sf::kConv1Threads), smem, st, x, n, h, w, cin, kh, kw,
+                                     cout, g_pool, pooled, argmax, act, dW, db));
+}
+
+#define SF_CONV1_DISPATCH(FN, ...)                                             \
+  do {                                                                         \
+    if (kh == 5 && kw == 5 && cin == 1) return FN<5, 5, 1>(__VA_ARGS__);       \
+    if (kh == 3 && kw == 3 && cin == 1) return FN<3, 3, 1>(__VA_ARGS__);       \
+    if (kh == 3 && kw == 3 && cin == 3) return FN<3, 3, 3>(__VA_ARGS__);       \
+    return FN<0, 0, 0>(__VA_ARGS__);                                           \
+  } while (0)
+
+extern "C" int sf_conv_first_fwd(const __nv_bfloat16* x, int n, int h, int w, int cin, int kh, int kw, int cout, const __nv_bfloat16* wT,
+                                 int ld_w, const float* bias, int act, __nv_bfloat16* pooled, uint8_t* argmax, cudaStream_t st) {
+  const int K = kh * kw * cin;
+  if (K > sf::kConv1MaxK || cout < 8 || cout > 64 || (sf::kConv1Threads % cout) != 0) return -8;
+  SF_CONV1_DISPATCH(conv_first_fwd_launch, x, n, h, w, cin, kh, kw, cout, wT, ld_w, bias, act, pooled, argmax, st);
+}
+
+extern "C" int sf_conv_first_wgrad(const __nv_bfloat16* x, int n, int h, int w, int cin, int kh, int kw, int cout, const __nv_bfloat16* g_pool,
+                                   const __nv_bfloat16* pooled, const uint8_t* argmax, int act, float* dW, float* db, cudaStream_t st) {
+  const int K = kh * kw * cin;
+  if (K > sf::kConv1MaxK || cout < 8 || cout > 64 || (sf::kConv1Threads % cout) != 0) return -8;
+  SF_CONV1_DISPATCH(conv_first_wgrad_launch, x, n, h, w, cin, kh, kw, cout, g_pool, pooled, argmax, act, dW, db, st);
+}

@@ -233,10 +233,13 @@ struct GemmSmem {
   static constexpr int kBytes = kStages * kStageBytes + kBarBytes + BN * 4 + 1024;
 };
 
-template <int BN>
+// MN: both operands MN-major (D = a^T . b with a [K, M], b [K, N] row-major): the stage buffers have the same size, but a
+// stage is filled with {64 MN elements, 64 K rows} boxes and described to the tensor core as MN-major.
+template <int BN, bool MN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const SfGemmEpilogue ep, int M, int N, int K, int kblocks_per_split) {
+  static_assert(!MN || BN % 64 == 0, "MN-major B needs whole 64-element swizzle atoms");
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stage bases
@@ -315,14 +318,21 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint8_t* b_dst = a_dst + S::kABytes;
         mbar_expect_tx(&full_bar[s], S::kStageBytes);
         const int kc = (kb_begin + i) * kBK;
-        tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0, hintA);
-        tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0, hintB);
+        if constexpr (MN) {
+#pragma unroll
+          for (int h = 0; h < kBM / 64; ++h) tma_load_2d(a_dst + h * 8192, &tmA, &full_bar[s], m0 + h * 64, kc, hintA);
+#pragma unroll
+          for (int h = 0; h < BN / 64; ++h) tma_load_2d(b_dst + h * 8192, &tmB, &full_bar[s], n0 + h * 64, kc, hintB);
+        } else {
+          tma_load_2d(a_dst, &tmA, &full_bar[s], kc, m0, hintA);
+          tma_load_2d(b_dst, &tmB, &full_bar[s], kc, n0, hintB);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kBM, BN);
+      constexpr uint32_t idesc = umma_idesc(1 /*bf16*/, kBM, BN, MN);
       const bool tr = g_trace_buf != nullptr;
       unsigned long long tm0 = tr ? trace_now() : 0, tm1 = 0;
       for (int i = 0; i < num_kb; ++i) {
@@ -333,12 +343,21 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after_sync();
         const uint32_t a_addr = smem_u32(stage_base + s * S::kStageBytes);
         const uint32_t b_addr = a_addr + S::kABytes;
-        const uint64_t a_desc = umma_desc_k_sw128(a_addr);
-        const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+        if constexpr (MN) {
+          // 64 K rows of 128 B per 64-element MN atom (8 KB); one MMA consumes 16 rows = 2 KB = +128 in 16-byte units
+          const uint64_t a_desc = umma_desc_mn_sw128(a_addr, 8192);
+          const uint64_t b_desc = umma_desc_mn_sw128(b_addr, 8192);
 #pragma unroll
-        for (int k = 0; k < kBK / kUmmaK; ++k) {
-          // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
-          umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_f16(tmem_base, a_desc + 128 * k, b_desc + 128 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        } else {
+          const uint64_t a_desc = umma_desc_k_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_k_sw128(b_addr);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advance 16 elements (32 B) along K inside the swizzle atom: +2 in 16-byte units
+            umma_f16(tmem_base, a_desc + 2 * k, b_desc + 2 * k, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty_bar[s]);      // smem slot reusable once these MMAs retire
       }
@@ -466,13 +485,25 @@ extern "C" int sf_gemm_prepare(SfGemm* g) {
     int want = g->pair;
     if (env != nullptr && want < 0) want = atoi(env);
     if (want < 0) want = (g->bn == 256 && pair_tiles >= 74 && g->K >= 512) ? 1 : 0;
-    g->pair = (want > 0 && eligible) ? 1 : 0;
+    g->pair = (want > 0 && eligible && !g->mn_major) ? 1 : 0;
     if (g->pair) g->bn = 256;
   }
-  int rc = sf_make_tmap_bf16_kmajor(&g->tmA, g->a, g->M, g->K, g->lda, sf::kBM);
-  if (rc) return rc;
-  rc = sf_make_tmap_bf16_kmajor(&g->tmB, g->b, g->N, g->K, g->ldb, g->pair ? 128 : g->bn);
-  if (rc) return rc;
+  int rc;
+  if (g->mn_major) {
+    // a is [K, lda] (M contiguous), b is [K, ldb] (N contiguous): boxes of {64 MN elements, 64 K rows}
+    if (g->pair || g->ep.loss_mode != SF_LOSS_NONE) return -7;
+    if (g->bn < 64) g->bn = 64;
+    if (g->bn > 128) g->bn = 128;
+    rc = sf_make_tmap_bf16_kmajor(&g->tmA, g->a, g->K, g->M, g->lda, 64);
+    if (rc) return rc;
+    rc = sf_make_tmap_bf16_kmajor(&g->tmB, g->b, g->K, g->N, g->ldb, 64);
+    if (rc) return rc;
+  } else {
+    rc = sf_make_tmap_bf16_kmajor(&g->tmA, g->a, g->M, g->K, g->lda, sf::kBM);
+    if (rc) return rc;
+    rc = sf_make_tmap_bf16_kmajor(&g->tmB, g->b, g->N, g->K, g->ldb, g->pair ? 128 : g->bn);
+    if (rc) return rc;
+  }
   const int total_kb = (g->K + sf::kBK - 1) / sf::kBK;
   if (g->split_k > total_kb) g->split_k = total_kb;
   g->kblocks_per_split = (total_kb + g->split_k - 1) / g->split_k;
@@ -490,24 +521,32 @@ extern "C" int sf_gemm_prepare(SfGemm* g) {
   return 0;
 }
 
-template <int BN>
+template <int BN, bool MN = false>
 static cudaError_t launch_bn(const SfGemm* g, cudaStream_t st) {
   using S = sf::GemmSmem<BN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sf::sf_gemm_kernel<BN>,
+    cudaError_t e = cudaFuncSetAttribute(sf::sf_gemm_kernel<BN, MN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   dim3 grid((g->N + BN - 1) / BN, (g->M + sf::kBM - 1) / sf::kBM, g->split_k);
-  return sf::launch(sf::sf_gemm_kernel<BN>, grid, dim3(sf::kGemmThreads), S::kBytes, st, g->tmA, g->tmB, g->ep,
+  return sf::launch(sf::sf_gemm_kernel<BN, MN>, grid, dim3(sf::kGemmThreads), S::kBytes, st, g->tmA, g->tmB, g->ep,
                     g->M, g->N, g->K, g->kblocks_per_split);
 }
 
 extern "C" int sf_gemm_launch(const SfGemm* g, cudaStream_t st) {
   if (g->pair) return sf_gemm_pair_launch(g, st);
   cudaError_t e;
+  if (g->mn_major) {
+    switch (g->bn) {
+      case 64: e = launch_bn<64, true>(g, st); break;
+      case 128: e = launch_bn<128, true>(g, st); break;
+      default: return -3;
+    }
+    return static_cast<int>(e);
+  }
   switch (g->bn) {
     case 32: e = launch_bn<32>(g, st); break;
     case 64: e = launch_bn<64>(g, st); break;

@@ -30,11 +30,17 @@ extern "C" int sf_preload_kernels() {
   // opt-in shared memory sizes are set here too, so a plan can be CAPTURED without ever having run eagerly
   SF_SMEM_ATTR(sf::sf_gemm_kernel<32>, sf::GemmSmem<32>::kBytes); SF_SMEM_ATTR(sf::sf_gemm_kernel<64>, sf::GemmSmem<64>::kBytes);
   SF_SMEM_ATTR(sf::sf_gemm_kernel<128>, sf::GemmSmem<128>::kBytes); SF_SMEM_ATTR(sf::sf_gemm_kernel<256>, sf::GemmSmem<256>::kBytes);
+  SF_SMEM_ATTR((sf::sf_gemm_kernel<64, true>), sf::GemmSmem<64>::kBytes); SF_SMEM_ATTR((sf::sf_gemm_kernel<128, true>), sf::GemmSmem<128>::kBytes);
+  SF_PRELOAD((sf::sf_gemm_kernel<64, true>)); SF_PRELOAD((sf::sf_gemm_kernel<128, true>));
   SF_SMEM_ATTR(sf::sf_mega_kernel, sf::GemmSmem<32>::kBytes); SF_SMEM_ATTR(sf::sf_gemm_pair_kernel<6>, sf::pair_smem_bytes<6>()); SF_SMEM_ATTR(sf::sf_gemm_pair_kernel<7>, sf::pair_smem_bytes<7>());
   SF_PRELOAD(sf::sf_gemm_kernel<32>); SF_PRELOAD(sf::sf_gemm_kernel<64>); SF_PRELOAD(sf::sf_gemm_kernel<128>); SF_PRELOAD(sf::sf_gemm_kernel<256>); SF_PRELOAD(sf::sf_mega_kernel); SF_PRELOAD(sf::sf_gemm_pair_kernel<6>); SF_PRELOAD(sf::sf_gemm_pair_kernel<7>);
   SF_PRELOAD(sf::hostcopy_kernel); SF_PRELOAD(sf::gather_rows_f32_kernel); SF_PRELOAD(sf::fetch_kernel); SF_PRELOAD(sf::cast_transpose_kernel<false>); SF_PRELOAD(sf::cast_transpose_kernel<true>);
   SF_PRELOAD(sf::softmax_xent_kernel); SF_PRELOAD(sf::mse_kernel); SF_PRELOAD(sf::argmax_rows_kernel);
   SF_PRELOAD(sf::im2col_kernel); SF_PRELOAD(sf::col2im_kernel); SF_PRELOAD(sf::maxpool_fwd_kernel); SF_PRELOAD(sf::maxpool_bwd_kernel);
+  SF_PRELOAD((sf::conv_first_fwd_kernel<5, 5, 1>)); SF_PRELOAD((sf::conv_first_wgrad_kernel<5, 5, 1>));
+  SF_PRELOAD((sf::conv_first_fwd_kernel<3, 3, 1>)); SF_PRELOAD((sf::conv_first_wgrad_kernel<3, 3, 1>));
+  SF_PRELOAD((sf::conv_first_fwd_kernel<3, 3, 3>)); SF_PRELOAD((sf::conv_first_wgrad_kernel<3, 3, 3>));
+  SF_PRELOAD((sf::conv_first_fwd_kernel<0, 0, 0>)); SF_PRELOAD((sf::conv_first_wgrad_kernel<0, 0, 0>));
   SF_PRELOAD(sf::pull_kernel<true>); SF_PRELOAD(sf::pull_kernel<false>); SF_PRELOAD(sf::post_kernel); SF_PRELOAD(sf::lock_test_kernel);
   SF_PRELOAD(sf::sync_pull_kernel); SF_PRELOAD(sf::post_flags_kernel);
   SF_PRELOAD_OPT(push_kernel, true); SF_PRELOAD_OPT(push_kernel, false);

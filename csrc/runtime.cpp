@@ -69,6 +69,7 @@ struct Gemm {
     g.bn = getd<int>(d, "bn", 0);
     g.split_k = getd<int>(d, "split_k", 1);
     g.pair = getd<int>(d, "pair", -1);
+    g.mn_major = getd<int>(d, "mn_major", 0);
     g.pair_ctas = getd<int>(d, "pair_ctas", 0);
     g.ep.out_f32 = P<float>(getd<uintptr_t>(d, "out_f32", 0));
     g.ep.ld_f32 = getd<int>(d, "ld_f32", g.N);
@@ -111,6 +112,7 @@ struct Gemm {
   py::tuple grid() const {
     return py::make_tuple((g.N + g.bn - 1) / g.bn, (g.M + 127) / 128, g.split_k);
   }
+  int mn_major() const { return g.mn_major; }
 };
 
 // ---------------------------------------------------------------------------
@@ -1006,6 +1008,7 @@ PYBIND11_MODULE(_C, m) {
       .def_property_readonly("bn", &Gemm::bn)
       .def_property_readonly("split_k", &Gemm::split_k)
       .def_property_readonly("pair", &Gemm::pair)
+      .def("mn_major", &Gemm::mn_major)
       .def_property_readonly("grid", &Gemm::grid);
 
   py::class_<Plan>(m, "Plan")
@@ -1091,6 +1094,22 @@ PYBIND11_MODULE(_C, m) {
                return sf_maxpool2_bwd(P<const __nv_bfloat16>(dout), P<const uint8_t>(argmax), n, h, w, c,
                                       P<const __nv_bfloat16>(act_out), act, P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT),
                                       ld_t, P<float>(dbias), st);
+             });
+           })
+      .def("add_conv_first_fwd",
+           [](Plan& p, uintptr_t x, int n, int h, int w, int cin, int kh, int kw, int cout, uintptr_t wT, int ld_w, uintptr_t bias, int act,
+              uintptr_t pooled, uintptr_t argmax) {
+             p.add("conv_first_fwd", [=](cudaStream_t st) {
+               return sf_conv_first_fwd(P<const __nv_bfloat16>(x), n, h, w, cin, kh, kw, cout, P<const __nv_bfloat16>(wT), ld_w, P<const float>(bias),
+                                        act, P<__nv_bfloat16>(pooled), P<uint8_t>(argmax), st);
+             });
+           })
+      .def("add_conv_first_wgrad",
+           [](Plan& p, uintptr_t x, int n, int h, int w, int cin, int kh, int kw, int cout, uintptr_t g_pool, uintptr_t pooled, uintptr_t argmax,
+              int act, uintptr_t dW, uintptr_t db) {
+             p.add("conv_first_wgrad", [=](cudaStream_t st) {
+               return sf_conv_first_wgrad(P<const __nv_bfloat16>(x), n, h, w, cin, kh, kw, cout, P<const __nv_bfloat16>(g_pool),
+                                          P<const __nv_bfloat16>(pooled), P<const uint8_t>(argmax), act, P<float>(dW), P<float>(db), st);
              });
            })
       .def("add_push",
@@ -1206,6 +1225,16 @@ PYBIND11_MODULE(_C, m) {
                           uintptr_t dzT, int ld_t, uintptr_t dbias, uintptr_t stream) {
     ck_rc(sf_maxpool2_bwd(P<const __nv_bfloat16>(dout), P<const uint8_t>(argmax), n, h, w, c, P<const __nv_bfloat16>(act_out), act,
                           P<__nv_bfloat16>(dz), ld_dz, P<__nv_bfloat16>(dzT), ld_t, P<float>(dbias), S(stream)), "maxpool_bwd");
+  });
+  m.def("conv_first_fwd", [](uintptr_t x, int n, int h, int w, int cin, int kh, int kw, int cout, uintptr_t wT, int ld_w, uintptr_t bias, int act,
+                             uintptr_t pooled, uintptr_t argmax, uintptr_t stream) {
+    ck_rc(sf_conv_first_fwd(P<const __nv_bfloat16>(x), n, h, w, cin, kh, kw, cout, P<const __nv_bfloat16>(wT), ld_w, P<const float>(bias), act,
+                            P<__nv_bfloat16>(pooled), P<uint8_t>(argmax), S(stream)), "conv_first_fwd");
+  });
+  m.def("conv_first_wgrad", [](uintptr_t x, int n, int h, int w, int cin, int kh, int kw, int cout, uintptr_t g_pool, uintptr_t pooled,
+                               uintptr_t argmax, int act, uintptr_t dW, uintptr_t db, uintptr_t stream) {
+    ck_rc(sf_conv_first_wgrad(P<const __nv_bfloat16>(x), n, h, w, cin, kh, kw, cout, P<const __nv_bfloat16>(g_pool), P<const __nv_bfloat16>(pooled),
+                              P<const uint8_t>(argmax), act, P<float>(dW), P<float>(db), S(stream)), "conv_first_wgrad");
   });
   m.def("gemm_pick_bn", &sf_gemm_pick_bn);
   m.def("set_pdl", &sf_set_pdl);

@@ -97,6 +97,9 @@ struct SfGemm {
   int bn;                         // 0 = auto
   int split_k;                    // 0/1 = none
   int kblocks_per_split;          // filled
+  int mn_major;                   // 1: BOTH operands are MN-major: a is [K, lda] with M contiguous, b is [K, ldb] with N contiguous
+                                  // (D = a^T . b, the weight-gradient form: activations / dz are consumed as they are
+                                  // stored, no transposed copies); 0: both K-major (a [M, lda], b [N, ldb])
   int pair;                       // in: -1 = auto, 0 = one-CTA kernel, 1 = force the 2-CTA persistent kernel; out: 0 / 1
   int pair_ctas;                  // CTAs of the persistent 2-CTA kernel (0 = 148)
   SfGemmEpilogue ep;
@@ -194,6 +197,13 @@ int sf_maxpool2_fwd(const __nv_bfloat16* in, int n, int h, int w, int c, __nv_bf
 int sf_maxpool2_bwd(const __nv_bfloat16* dout, const uint8_t* argmax, int n, int h, int w, int c,
                     const __nv_bfloat16* act_out, int act, __nv_bfloat16* dz, int ld_dz,
                     __nv_bfloat16* dzT, int ld_t, float* dbias, cudaStream_t st);
+
+// first convolution of a network (K = kh * kw * cin <= 64, cout in {8, 16, 32, 64}) fused with bias, activation and the
+// 2x2 max-pool that follows it: direct CUDA-core kernels, one CTA per image, nothing but the pooled tensor is written
+int sf_conv_first_fwd(const __nv_bfloat16* x, int n, int h, int w, int cin, int kh, int kw, int cout, const __nv_bfloat16* wT,
+                      int ld_w, const float* bias, int act, __nv_bfloat16* pooled, uint8_t* argmax, cudaStream_t st);
+int sf_conv_first_wgrad(const __nv_bfloat16* x, int n, int h, int w, int cin, int kh, int kw, int cout, const __nv_bfloat16* g_pool,
+                        const __nv_bfloat16* pooled, const uint8_t* argmax, int act, float* dW, float* db, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // Fused push: optimizer step on the (possibly remote) master shard + bf16 publish (optim_push.cu)

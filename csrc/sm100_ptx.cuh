@@ -230,10 +230,26 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Shared-memory matrix descriptor, MN-major operand, 128-byte swizzle: the tile is stored as K rows of 128 bytes (64
+// consecutive M / N elements of one k), i.e. exactly what a TMA box {64 elements, K rows} of a row-major [K, MN] tensor
+// produces.  Canonical form ((8, n), (8, k)) : ((1, LBO), (8, SBO)) in 16-byte units: 8 rows of one k-group are 128 B
+// apart, k-groups of 8 rows are SBO = 1024 B apart, the next 64 MN elements are LBO bytes away.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulation, both operands K-major.
 // fmt: 0 = f16, 1 = bf16, 2 = tf32
-__host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N) {
-  return (1u << 4)            // D format = f32
+// mn_major: bits 15 / 16 select MN-major A / B (allowed for f16 / bf16 / tf32 sources)
+__host__ __device__ constexpr uint32_t umma_idesc(uint32_t fmt, uint32_t M, uint32_t N, bool mn_major = false) {
+  return (mn_major ? (3u << 15) : 0u)
+         | (1u << 4)          // D format = f32
          | (fmt << 7)         // A format
          | (fmt << 10)        // B format
          | ((N >> 3) << 17)   // N / 8

@@ -19,6 +19,7 @@ from .ml_util import handle_features
 from .ops.optimizers import OptimizerSpec
 from .parallel import dist as D
 from .parallel.session import TrainingSession
+from .spark.backend import collect_partitions
 
 # live sessions by master url, so the module-level helper functions of the reference keep working
 _SERVERS: Dict[str, "HogwildSparkModel"] = {}
@@ -139,7 +140,7 @@ class HogwildSparkModel(object):
             supervised = self.tfLabel is not None
             ctx = self._session.ctx
             for rnd in range(self.partition_shuffles):
-                parts = [handle_features(iter(p), supervised) for p in rdd.partitions()]
+                parts = [handle_features(iter(p), supervised) for p in collect_partitions(rdd)]
                 parts = [(f, l) for f, l in parts if f.shape[0] > 0]
                 self._session.train_partitions(parts)
                 if self.partition_shuffles - rnd > 1:

@@ -45,7 +45,7 @@ def install(force: bool = False) -> dict:
         from .spark import context, sql
         from .spark.ml import base, evaluation, feature, linalg, param
 
-        pyspark = _ns("pyspark", SparkContext=context.SparkContext, SparkConf=context.SparkConf, keyword_only=context.keyword_only,
+        pyspark = _ns("pyspark", __sparkflow_shim__=True, SparkContext=context.SparkContext, SparkConf=context.SparkConf, keyword_only=context.keyword_only,
                       __version__=spark.__version__, __path__=[])
         sql_mod = _ns("pyspark.sql", SparkSession=sql.SparkSession, DataFrame=sql.DataFrame, Row=sql.Row, __path__=[])
         fn_mod = _ns("pyspark.sql.functions", rand=sql.rand, col=sql.col)

@@ -140,8 +140,7 @@ def run_inference(graph_json: str, weights: Sequence[np.ndarray], features: np.n
 def predict_func(rows, graph_json, prediction, graph_weights, inp, activation, tf_input, tf_dropout=None, to_keep_dropout=False):
     """Per-partition prediction: adds ``prediction`` to every row (float for scalar outputs, a
     ``DenseVector`` otherwise) – reference: ml_util.py:54-83."""
-    from .spark.ml.linalg import Vectors
-    from .spark.sql import Row
+    from .spark.backend import Row, Vectors          # genuine pyspark classes when PySpark is installed
 
     rows = [r.asDict() for r in rows]
     if not rows:

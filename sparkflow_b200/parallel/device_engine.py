@@ -321,6 +321,17 @@ class DeviceWorker:
                 if sgm.rows == 1:
                     for tc in range((sgm.cols + 63) // 64):
                         vt.append((m.tile_prefix[i] + tc, sgm.offset + tc * 64, min(64, sgm.cols - tc * 64)))
+            # the fused first-conv weight gradient is accumulated locally too (direct CUDA-core kernel): forward its rows
+            from .plan_builder import fused_first_conv
+
+            fc = fused_first_conv(self.plan)
+            if fc is not None:
+                sgm = lay.by_name(self.plan.layers[fc].kernel)
+                tiles_c = (sgm.cols + 63) // 64
+                for r_ in range(sgm.rows):
+                    for tc in range(tiles_c):
+                        vt.append((m.tile_prefix[sgm.index] + (r_ // 32) * tiles_c + tc, sgm.offset + r_ * sgm.cols + tc * 64,
+                                   min(64, sgm.cols - tc * 64)))
             self.vec_tiles = torch.tensor(vt if vt else [(0, 0, 0)], dtype=torch.int64, device=dev)
             self.n_vec_tiles = len(vt)
             # snapshot pull: the copy is latency bound, so give every shard as many CTAs as it has tiles (all CTAs of the

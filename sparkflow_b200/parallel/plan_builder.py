@@ -70,6 +70,28 @@ def check_grammar(lp: LayerPlan) -> None:
         raise UnsupportedGraph("image inputs need a feature count that is a multiple of 8")
 
 
+def fused_first_conv(lp: LayerPlan) -> Optional[int]:
+    """Index of the network's first trainable layer when it is a small convolution directly followed by the 2x2 max-pool
+    (K = kh * kw * cin <= 64, 8..64 output channels): that pair runs as ONE direct CUDA-core kernel forward and ONE
+    backward (csrc/conv.cu: conv_first_fwd / conv_first_wgrad) instead of im2col + a K-padded GEMM + a pooling pass."""
+    if os.environ.get("SPARKFLOW_FUSED_CONV1", "1") == "0":
+        return None
+    layers = lp.layers
+    trainable = [i for i, l in enumerate(layers) if l.kind in ("dense", "conv")]
+    if not trainable:
+        return None
+    i = trainable[0]
+    l = layers[i]
+    if l.kind != "conv" or i + 1 >= len(layers) or layers[i + 1].kind != "pool":
+        return None
+    cin, cout = l.in_shape[2], l.out_shape[2]
+    if l.ksize[0] * l.ksize[1] * cin > 64 or cout not in (8, 16, 32, 64) or l.act not in (None, "Relu", "Sigmoid", "Tanh"):
+        return None
+    if l.in_shape[0] * l.in_shape[1] * cin * 4 > 64 * 1024:
+        return None
+    return i
+
+
 def _split_k(tiles: int, kblocks: int) -> int:
     if kblocks < 16:
         return 1
@@ -99,6 +121,15 @@ def _emit_mega(plan, C, items: List[List[Any]], keep: List[Any]) -> None:
     mega = C.Mega(gemms, deps, int(os.environ.get("SPARKFLOW_MEGA_CTAS", "0")))
     keep.append(mega)
     plan.add_mega(mega, "mega[" + ",".join(items[o][1] for o in order) + "]")
+
+
+def use_mn_possible(worker, layers, train: bool) -> bool:
+    """MN-major weight gradients (no transposed activation copies) are used unless switched off or the opt-in dense
+    megakernel (K-major tiles only) is active; forward-only plans never need transposes."""
+    if not train:
+        return True
+    return bool(os.environ.get("SPARKFLOW_WGRAD_MN", "1") == "1"
+                and not (getattr(worker, "use_mega", False) and all(l.kind == "dense" for l in layers)))
 
 
 def add_fetch_ops(plan, fetch: Dict[str, Any], B: int, D: int) -> None:
@@ -168,6 +199,11 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         fuse_ryw = bool(train and getattr(worker, "fuse_ryw", False))
         if fuse_ryw:
             do_pull = False
+    fused_conv = fused_first_conv(lp) if use_mn_possible(worker, lp.layers, train) else None
+    if fused_conv is not None:
+        fuse_ryw = False             # the first weight reader is the direct conv kernel: keep the stand-alone wait
+        if sharded:
+            do_pull = bool(train or with_pull)
     ryw_pending = [fuse_ryw]
 
     def ryw_args() -> Dict[str, Any]:
@@ -205,11 +241,14 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     elif do_pull:
         add_pull_op()
     first_is_dense = layers[first_trainable].kind == "dense"
+    # weight gradients read the row-major activation / dz buffers directly (MN-major tcgen05 operands): no transposed copy
+    # of any activation, gradient or im2col matrix is ever written.  (The opt-in megakernel only has K-major tiles.)
+    use_mn = bool(train and use_mn_possible(worker, layers, train))
     if inputs is not None:
         a0, a0T = inputs["a0"], inputs["a0T"]
     else:
         a0 = zeros(B, round_up(D, 8))
-        a0T = zeros(D, ldB) if (train and first_is_dense) else None
+        a0T = zeros(D, ldB) if (train and first_is_dense and not use_mn) else None
         if resident is not None:
             xr, yr = resident["x"], resident["y"]
             plan.add_cast_transpose(P(xr), xr.shape[1], P(idx_stage), P(a0), a0.shape[1], P(a0T), ldB if a0T is not None else 0, B, D)
@@ -262,6 +301,23 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
                 h, w, c = cur["shape"]
                 cur = dict(kind="flat", buf=cur["buf"], bufT=cur.get("flatT"), feat=h * w * c, ld=h * w * c)
             continue
+        if l.kind == "conv" and i == fused_conv:
+            # first conv + bias + activation + 2x2 max-pool as ONE direct kernel: only the pooled tensor is written
+            h, w, cin = cur["shape"]
+            kh, kw = l.ksize
+            oh, ow, cout = l.out_shape
+            ph, pw = oh // 2, ow // 2
+            ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
+            pooled = zeros(B, ph * pw * cout)
+            argmax = zeros(B, ph * pw * cout, dtype=torch.uint8)
+            plan.add_conv_first_fwd(P(cur["buf"]), B, h, w, cin, kh, kw, cout, P(wsrc) + ks.wt_off * 2, ks.wt_ld,
+                                    worker._bias_ptr(bs) if bs else 0, ACT_IDS[l.act], P(pooled), P(argmax))
+            rec[i] = dict(fused=True, x=cur["buf"], in_shape=(h, w, cin), pooled=pooled, argmax=argmax)
+            cur = dict(kind="img", buf=pooled, shape=(ph, pw, cout), flatT=None, fused_pool=i)
+            continue
+        if l.kind == "pool" and cur.get("fused_pool") is not None:
+            rec[i] = dict(fused=True, conv=cur.pop("fused_pool"))
+            continue
         if l.kind == "conv":
             h, w, cin = cur["shape"]
             kh, kw = l.ksize
@@ -269,8 +325,8 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             M, K = B * oh * ow, kh * kw * cin
             ldK, ldM = round_up(K, 8), round_up(M, 8)
             patches = zeros(M, ldK)
-            patchesT = zeros(K, ldM) if train else None
-            plan.add_im2col(P(cur["buf"]), B, h, w, cin, kh, kw, P(patches), ldK, P(patchesT), ldM if train else 0)
+            patchesT = zeros(K, ldM) if (train and not use_mn) else None
+            plan.add_im2col(P(cur["buf"]), B, h, w, cin, kh, kw, P(patches), ldK, P(patchesT), ldM if patchesT is not None else 0)
             ks, bs = lay.by_name(l.kernel), (lay.by_name(l.bias) if l.bias else None)
             act_out = zeros(M, cout)
             g = C.Gemm(dict(a=P(patches), lda=ldK, b=P(wsrc) + ks.wt_off * 2, ldb=ks.wt_ld, M=M, N=cout, K=K,
@@ -287,7 +343,7 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             pooled = zeros(B, oh * ow * c)
             argmax = zeros(B, oh * ow * c, dtype=torch.uint8)
             nxt_dense = (i + 2 < len(layers) and layers[i + 1].kind == "reshape" and layers[i + 2].kind == "dense")
-            flatT = zeros(oh * ow * c, ldB) if (train and nxt_dense) else None
+            flatT = zeros(oh * ow * c, ldB) if (train and nxt_dense and not use_mn) else None
             plan.add_maxpool_fwd(P(cur["buf"]), B, h, w, c, P(pooled), P(argmax), P(flatT), ldB if flatT is not None else 0)
             rec[i] = dict(argmax=argmax, in_shape=(h, w, c), conv=cur.get("conv"), pooled=pooled)
             cur = dict(kind="img", buf=pooled, shape=(oh, ow, c), flatT=flatT)
@@ -306,11 +362,11 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         if last:
             fuse_loss = train and worker.fuse_loss and (lp.loss == "mse" or ks.cols <= 32)
             if fuse_loss:
-                dz_last, dzT_last = zeros(B, round_up(ks.cols, 8)), zeros(ks.cols, ldB)
+                dz_last, dzT_last = zeros(B, round_up(ks.cols, 8)), (None if use_mn else zeros(ks.cols, ldB))
                 db = P(worker.grads) + bs.offset * 4 if bs else 0
                 d.update(loss_mode=1 if lp.loss == "softmax_xent" else 2, target=P(target), ld_target=target.shape[1],
-                         loss=P(worker.loss_acc), out_bf16=P(dz_last), ld_bf16=dz_last.shape[1], outT_bf16=P(dzT_last), ld_t=ldB,
-                         colsum=db)
+                         loss=P(worker.loss_acc), out_bf16=P(dz_last), ld_bf16=dz_last.shape[1], outT_bf16=P(dzT_last),
+                         ld_t=ldB if dzT_last is not None else 0, colsum=db)
             else:
                 out_f32 = zeros(B, ks.cols, dtype=f32)
                 d.update(out_f32=P(out_f32), ld_f32=ks.cols)
@@ -319,8 +375,8 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             rec[i]["N"] = ks.cols
             break
         nxt = zeros(B, round_up(ks.cols, 8))
-        nxtT = zeros(ks.cols, ldB) if train else None
-        d.update(out_bf16=P(nxt), ld_bf16=nxt.shape[1], outT_bf16=P(nxtT), ld_t=ldB if train else 0)
+        nxtT = zeros(ks.cols, ldB) if (train and not use_mn) else None
+        d.update(out_bf16=P(nxt), ld_bf16=nxt.shape[1], outT_bf16=P(nxtT), ld_t=ldB if nxtT is not None else 0)
         g = C.Gemm(d)
         emit(g, f"fwd{i}", d)
         cur = dict(kind="flat", buf=nxt, bufT=nxtT, feat=ks.cols, ld=nxt.shape[1])
@@ -345,14 +401,15 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
     # ---------------- loss (when not fused) ----------------
     bs_last = lay.by_name(last_l.bias) if last_l.bias else None
     if not fuse_loss:
-        dz_last, dzT_last = zeros(B, round_up(n_out, 8)), zeros(n_out, ldB)
+        dz_last, dzT_last = zeros(B, round_up(n_out, 8)), (None if use_mn else zeros(n_out, ldB))
         db = P(worker.grads) + bs_last.offset * 4 if bs_last else 0
+        ldt_last = ldB if dzT_last is not None else 0
         if lp.loss == "softmax_xent":
             plan.add_softmax_xent(P(out_f32), n_out, P(target), target.shape[1], P(worker.loss_acc), P(dz_last), dz_last.shape[1],
-                                  P(dzT_last), ldB, db, B, n_out)
+                                  P(dzT_last), ldt_last, db, B, n_out)
         else:
             plan.add_mse(P(out_f32), n_out, P(target), target.shape[1], ACT_IDS[last_l.act], P(worker.loss_acc), P(dz_last),
-                         dz_last.shape[1], P(dzT_last), ldB, db, B, n_out)
+                         dz_last.shape[1], P(dzT_last), ldt_last, db, B, n_out)
 
     # ---------------- backward ----------------
     def side(fn):
@@ -371,9 +428,13 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
         if l.kind == "dense":
             ks = lay.by_name(l.kernel)
             r = rec[i]
-            if r["a_inT"] is None:
-                raise UnsupportedGraph("dense layer input has no transposed copy")
-            wd = dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B)
+            if use_mn:
+                # dW = a_in^T . dz straight from the row-major buffers (both operands MN-major)
+                wd = dict(a=P(r["a_in"]), lda=r["a_in_ld"], b=P(g_dz), ldb=g_dz.shape[1], M=ks.rows, N=ks.cols, K=B, mn_major=1)
+            else:
+                if r["a_inT"] is None:
+                    raise UnsupportedGraph("dense layer input has no transposed copy")
+                wd = dict(a=P(r["a_inT"]), lda=ldB, b=P(g_dzT), ldb=ldB, M=ks.rows, N=ks.cols, K=B)
             if sharded:
                 wd.update(worker.route_args(ks))          # push fused into the epilogue: tiles go to the owners' mailboxes
             else:
@@ -385,10 +446,10 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             prev = layers[i - 1]
             if prev.kind == "dense":
                 pb = lay.by_name(prev.bias) if prev.bias else None
-                ndz, ndzT = zeros(B, r["a_in_ld"]), zeros(ks.rows, ldB)
+                ndz, ndzT = zeros(B, r["a_in_ld"]), (None if use_mn else zeros(ks.rows, ldB))
                 dd = dict(a=P(g_dz), lda=g_dz.shape[1], b=P(wsrc) + ks.w_off * 2, ldb=ks.w_ld, M=B, N=ks.rows, K=ks.cols,
                           aux=P(r["a_in"]), ld_aux=r["a_in_ld"], aux_act=ACT_IDS[prev.act], aux_keep=float(prev.dropout_keep or 0.0), out_bf16=P(ndz),
-                          ld_bf16=ndz.shape[1], outT_bf16=P(ndzT), ld_t=ldB,
+                          ld_bf16=ndz.shape[1], outT_bf16=P(ndzT), ld_t=ldB if ndzT is not None else 0,
                           colsum=P(worker.grads) + pb.offset * 4 if pb else 0)
                 dg = C.Gemm(dd)
                 emit(dg, f"dgrad{i}", dd)
@@ -402,17 +463,27 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             continue
         if l.kind == "reshape":
             continue
+        if l.kind == "pool" and rec[i].get("fused"):
+            ci = rec[i]["conv"]
+            conv_l, cr = layers[ci], rec[ci]
+            ks = lay.by_name(conv_l.kernel)
+            cb = lay.by_name(conv_l.bias) if conv_l.bias else None
+            h, w, cin = cr["in_shape"]
+            plan.add_conv_first_wgrad(P(cr["x"]), B, h, w, cin, conv_l.ksize[0], conv_l.ksize[1], ks.cols, P(g_img), P(cr["pooled"]),
+                                      P(cr["argmax"]), ACT_IDS[conv_l.act], P(worker.grads) + ks.offset * 4,
+                                      P(worker.grads) + cb.offset * 4 if cb else 0)
+            break                                  # it is the first trainable layer: nothing below needs a gradient
         if l.kind == "pool":
             r = rec[i]
             ci = r["conv"]
             conv_l, cr = layers[ci], rec[ci]
             h, w, c = r["in_shape"]
             cb = lay.by_name(conv_l.bias) if conv_l.bias else None
-            need_dz = ci != first_trainable            # conv dgrad needs the row-major dz
+            need_dz = ci != first_trainable or use_mn   # conv dgrad (and the MN-major wgrad) read the row-major dz
             dzc = zeros(cr["M"], c) if need_dz else None
-            dzcT = zeros(c, cr["ldM"])
+            dzcT = None if use_mn else zeros(c, cr["ldM"])
             plan.add_maxpool_bwd(P(g_img), P(r["argmax"]), B, h, w, c, P(cr["act_out"]), ACT_IDS[conv_l.act], P(dzc), c if need_dz else 0,
-                                 P(dzcT), cr["ldM"], P(worker.grads) + cb.offset * 4 if cb else 0)
+                                 P(dzcT), cr["ldM"] if dzcT is not None else 0, P(worker.grads) + cb.offset * 4 if cb else 0)
             rec[ci]["dz"], rec[ci]["dzT"] = dzc, dzcT
             continue
         if l.kind == "conv":
@@ -420,8 +491,13 @@ def build(worker, B: int, *, train: bool, with_pull: bool, with_push: bool = Tru
             r = rec[i]
             kblocks = (r["M"] + 63) // 64
             tiles = ((r["K"] + 127) // 128) * max(1, (ks.cols + 63) // 64)
-            cw = dict(a=P(r["patchesT"]), lda=r["ldM"], b=P(r["dzT"]), ldb=r["ldM"], M=r["K"], N=ks.cols, K=r["M"],
-                      split_k=_split_k(tiles, kblocks), accumulate=1)
+            if use_mn:
+                # dW = patches^T . dz from the row-major im2col matrix and dz (no patches^T / dz^T are ever written)
+                cw = dict(a=P(r["patches"]), lda=r["ldK"], b=P(r["dz"]), ldb=ks.cols, M=r["K"], N=ks.cols, K=r["M"], mn_major=1,
+                          split_k=_split_k(tiles, kblocks), accumulate=1)
+            else:
+                cw = dict(a=P(r["patchesT"]), lda=r["ldM"], b=P(r["dzT"]), ldb=r["ldM"], M=r["K"], N=ks.cols, K=r["M"],
+                          split_k=_split_k(tiles, kblocks), accumulate=1)
             if sharded:
                 cw.update(worker.route_args(ks))          # red.add into the owners' mailboxes (appliers hand them back zeroed)
             else:

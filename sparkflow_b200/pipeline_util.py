@@ -13,8 +13,7 @@ from typing import List
 
 import dill
 
-from .spark.ml.base import MLReader, MLWriter, Pipeline, PipelineModel
-from .spark.ml.feature import StopWordsRemover
+from .spark.backend import REAL_PYSPARK, JavaMLReader, JavaMLWriter, MLReader, MLWriter, Pipeline, PipelineModel, StopWordsRemover
 
 
 class PysparkObjId(object):
@@ -82,9 +81,13 @@ class _CarrierWriter(MLWriter):
 
 
 class PysparkReaderWriter(object):
-    """Mixin: ``write()/save()`` persist the stage as a carrier; ``read()/load()`` restore it."""
+    """Mixin: ``write()/save()`` persist the stage as a carrier; ``read()/load()`` restore it.  With a genuine PySpark the
+    carrier is a JVM ``StopWordsRemover`` written by ``JavaMLWriter`` (what the reference does); without one the
+    stand-in writes the same directory layout itself."""
 
     def write(self):
+        if REAL_PYSPARK:
+            return JavaMLWriter(self)
         return _CarrierWriter(self)
 
     def save(self, path: str) -> None:
@@ -92,6 +95,8 @@ class PysparkReaderWriter(object):
 
     @classmethod
     def read(cls):
+        if REAL_PYSPARK:
+            return JavaMLReader(PysparkObjId._getCarrierClass())
         return MLReader(PysparkObjId._getCarrierClass())
 
     @classmethod
@@ -100,9 +105,22 @@ class PysparkReaderWriter(object):
 
     @classmethod
     def _from_java(cls, java_obj):
-        return load_byte_array(java_obj.getStopWords()[:-1])
+        return load_byte_array(list(java_obj.getStopWords())[:-1])
 
     def _to_java(self):
+        if REAL_PYSPARK:
+            # a JVM StopWordsRemover carrying this object's uid, its stop words = [payload, GUID]
+            from pyspark import SparkContext
+            from pyspark.ml.wrapper import JavaParams
+
+            words = dump_byte_array(self) + [PysparkObjId._getPyObjId()]
+            gateway = SparkContext._active_spark_context._gateway
+            jwords = gateway.new_array(gateway.jvm.java.lang.String, len(words))
+            for i, w in enumerate(words):
+                jwords[i] = w
+            jcarrier = JavaParams._new_java_obj(PysparkObjId._getCarrierClass(javaName=True), self.uid)
+            jcarrier.setStopWords(jwords)
+            return jcarrier
         carrier = StopWordsRemover()
         carrier._resetUid(self.uid)
         carrier.setStopWords(dump_byte_array(self) + [PysparkObjId._getPyObjId()])

@@ -20,9 +20,9 @@ from .HogwildSparkModel import HogwildSparkModel
 from .ml_util import convert_weights_to_json, predict_func
 from .ops.optimizers import OptimizerSpec
 from .pipeline_util import PysparkReaderWriter
-from .spark.context import SparkContext, keyword_only
-from .spark.ml.base import Estimator, MLReadable, MLWritable, Model
-from .spark.ml.param import HasInputCol, HasLabelCol, HasPredictionCol, Identifiable, Param, Params, TypeConverters
+# genuine pyspark classes when PySpark is importable, the dependency-free stand-ins otherwise (spark/backend.py)
+from .spark.backend import (Estimator, HasInputCol, HasLabelCol, HasPredictionCol, Identifiable, MLReadable, MLWritable, Model, Param, Params,
+                            SparkContext, TypeConverters, keyword_only)
 
 AVAILABLE_OPTIMIZERS = ("adam", "rmsprop", "momentum", "adadelta", "adagrad", "gradient_descent", "adagrad_da", "ftrl",
                         "proximal_adagrad", "proximal_gradient_descent")

@@ -117,6 +117,32 @@ def test_gemm_large(C):
     _run_gemm(C, 2048, 2048, 2048, want_t=False)
 
 
+@pytest.mark.parametrize("M,N,K,bn,split_k", [(784, 256, 300, 0, 1), (256, 256, 300, 64, 1), (256, 10, 300, 0, 1), (1600, 10, 300, 0, 1),
+                                              (288, 64, 30000, 0, 8), (25, 32, 4000, 64, 1), (4096, 4096, 300, 128, 1), (130, 70, 17, 0, 1)])
+def test_gemm_mn_major_operands(C, M, N, K, bn, split_k):
+    """D = a^T . b with a [K, M] and b [K, N] row-major (both operands MN-major for the tensor core): the weight-gradient
+    form dW = activations^T . dz consumed straight from the row-major activation / dz buffers, no transposed copies."""
+    g = torch.Generator(device="cuda").manual_seed(7)
+    lda, ldb = round_up(M, 8), round_up(N, 8)
+    a = torch.zeros(K, lda, dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros(K, ldb, dtype=torch.bfloat16, device="cuda")
+    a[:, :M] = (torch.randn(K, M, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    b[:, :N] = (torch.randn(K, N, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    ref = a[:, :M].float().t() @ b[:, :N].float()
+    out = torch.zeros(M, N, device="cuda") if split_k > 1 else torch.full((M, N), float("nan"), device="cuda")
+    cs = torch.zeros(N, device="cuda")
+    gm = C.Gemm(dict(a=native.ptr(a), lda=lda, b=native.ptr(b), ldb=ldb, M=M, N=N, K=K, mn_major=1, bn=bn, split_k=split_k,
+                     out_f32=native.ptr(out), ld_f32=N, colsum=native.ptr(cs) if split_k == 1 else 0, accumulate=1 if split_k > 1 else 0))
+    assert gm.mn_major() == 1 and gm.bn in (64, 128)
+    gm.launch(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < 2e-2 * scale * (K / 300) ** 0.5 + 1e-3
+    if split_k == 1:
+        assert torch.allclose(cs, ref.sum(0), rtol=2e-2, atol=2e-2 * scale)
+
+
 @pytest.mark.parametrize("M,N,K,ctas", [(512, 512, 256, 0), (1000, 520, 1000, 0), (256, 256, 64, 0), (2048, 2048, 512, 8),
                                           (1536, 1280, 320, 6), (4096, 4096, 1024, 0)])
 def test_gemm_pair_kernel(C, M, N, K, ctas):
@@ -497,3 +523,49 @@ def test_fetch_kernel_zero_copy_minibatch(C, rows, cols, ycols, B, start, ldpad)
     assert int(counter.item()) == 2 and int(sync.item()) == 0
     assert torch.equal(x_out.cpu(), Xfull[start:start + B, :cols])
     assert torch.equal(y_out.cpu(), Yfull[start:start + B, :ycols])
+
+
+@pytest.mark.parametrize("n,h,w,cin,kh,kw,cout,act", [(5, 28, 28, 1, 5, 5, 32, "relu"), (3, 12, 12, 2, 3, 3, 16, "tanh"), (2, 9, 9, 3, 2, 2, 64, None)])
+def test_conv_first_fused_fwd_and_wgrad(C, n, h, w, cin, kh, kw, cout, act):
+    """First conv + bias + activation + 2x2 max-pool as one direct kernel, and its fused weight / bias gradient, against
+    torch (conv2d -> act -> max_pool2d and autograd through them)."""
+    import torch.nn.functional as F
+
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).to(torch.bfloat16)
+    K = kh * kw * cin
+    wmat = (torch.randn(K, cout, device="cuda", generator=g) * 0.3).to(torch.bfloat16)      # [K = (dy, dx, ci), cout] (HWIO flattened)
+    ld_w = round_up(K, 8)
+    wT = torch.zeros(cout, ld_w, dtype=torch.bfloat16, device="cuda")
+    wT[:, :K] = wmat.t()
+    bias = torch.randn(cout, device="cuda", generator=g) * 0.1
+    oh, ow = h - kh + 1, w - kw + 1
+    ph, pw = oh // 2, ow // 2
+    pooled = torch.zeros(n, ph, pw, cout, dtype=torch.bfloat16, device="cuda")
+    argmax = torch.zeros(n, ph, pw, cout, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    C.conv_first_fwd(x.data_ptr(), n, h, w, cin, kh, kw, cout, wT.data_ptr(), ld_w, bias.data_ptr(), ACT[act], pooled.data_ptr(), argmax.data_ptr(), st)
+    torch.cuda.synchronize()
+    xt = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wt = wmat.float().reshape(kh, kw, cin, cout).permute(3, 2, 0, 1).clone().requires_grad_(True)
+    bt = bias.clone().requires_grad_(True)
+    conv = _act(F.conv2d(xt, wt, bt), act)
+    ref = F.max_pool2d(conv, 2)[:, :, :ph, :pw]
+    assert torch.allclose(pooled.float().permute(0, 3, 1, 2), ref, rtol=2e-2, atol=2e-2)
+    # gradient of sum(g_pool * pooled) through the SAME arg-max positions the kernel recorded
+    gp = torch.randn(n, ph, pw, cout, device="cuda", generator=g).to(torch.bfloat16)
+    dW = torch.zeros(K, cout, device="cuda")
+    db = torch.zeros(cout, device="cuda")
+    C.conv_first_wgrad(x.data_ptr(), n, h, w, cin, kh, kw, cout, gp.data_ptr(), pooled.data_ptr(), argmax.data_ptr(), ACT[act], dW.data_ptr(),
+                       db.data_ptr(), st)
+    torch.cuda.synchronize()
+    am = argmax.long().permute(0, 3, 1, 2)
+    ys = 2 * torch.arange(ph, device="cuda").view(1, 1, ph, 1) + am // 2
+    xs = 2 * torch.arange(pw, device="cuda").view(1, 1, 1, pw) + am % 2
+    picked = conv[torch.arange(n, device="cuda").view(n, 1, 1, 1), torch.arange(cout, device="cuda").view(1, cout, 1, 1), ys, xs]
+    # the kernel takes act'(.) from the bf16-rounded pooled value: use the same mask convention for ReLU ties
+    (picked * gp.float().permute(0, 3, 1, 2)).sum().backward()
+    ref_dW = wt.grad.permute(2, 3, 1, 0).reshape(K, cout)
+    scale = max(1.0, ref_dW.abs().max().item())
+    assert (dW - ref_dW).abs().max().item() < 3e-2 * scale
+    assert torch.allclose(db, bt.grad, rtol=3e-2, atol=3e-2 * max(1.0, bt.grad.abs().max().item()))

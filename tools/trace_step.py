@@ -12,8 +12,9 @@ from sparkflow_b200.parallel.session import TrainingSession
 from sparkflow_b200.utils.trace import DeviceTrace
 
 lock = "--lock" in sys.argv
+model = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--model=")), "simple_dnn")
 spec = OptimizerSpec.from_tf_kwargs("adam", dict(learning_rate=0.001))
-sess = TrainingSession(zoo.build("simple_dnn"), "x:0", "y:0", spec, acquire_lock=lock, engine="b200", seed=0, devices=[0]).open()
+sess = TrainingSession(zoo.build(model), "x:0", "y:0", spec, acquire_lock=lock, engine="b200", seed=0, devices=[0]).open()
 eng = sess.make_engine(torch.device("cuda", 0))
 w = eng.w
 plan, bufs = w.build_plan(300, 0)
@@ -46,7 +47,7 @@ for r in [x for x in rows if x["kid"] < 100]:
     cur["ctas"] += 1
     cur["ready"] = max(cur["ready"], r["t1"])
     cur["end"] = max(cur["end"], r["t2"])
-names = {1: "gemm", 2: "cast", 3: "softmax", 4: "mse", 5: "argmax", 6: "push", 7: "pull"}
+names = {1: "gemm", 2: "cast", 3: "softmax", 4: "mse", 5: "argmax", 6: "push", 7: "pull", 8: "im2col", 9: "col2im", 10: "pool_fwd", 11: "pool_bwd"}
 print("plan:", plan.names())
 print("%-8s %5s %9s %9s %9s %8s" % ("kernel", "ctas", "start_us", "ready_us", "end_us", "dur_us"))
 for s in summ:
@@ -55,5 +56,5 @@ print("--- gemm phases (block 0 of each gemm): 101 = MMA thread [role start, fir
 for r in rows:
     if r["kid"] >= 100 and r["block"] == 0:
         print(r)
-json.dump(dict(summary=summ, rows=rows), open("gpurun_out/trace_step%s.json" % ("_lock" if lock else ""), "w"))
+json.dump(dict(summary=summ, rows=rows), open("gpurun_out/trace_step_%s%s.json" % (model, "_lock" if lock else ""), "w"))
 sess.close()
