@@ -31,11 +31,18 @@ constexpr int kBK = 64;           // 64 bf16 = 128 B = one swizzle row
 constexpr int kUmmaK = 16;
 constexpr int kGemmThreads = 256;
 
+// Fast forms: the results are rounded to bf16 (or feed a loss) - a slow-path division per element would triple the
+// epilogue's code size, and the epilogue is instruction-fetch bound (it runs once per launch on a cold I-cache).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = __expf(-2.f * fabsf(x));
+  return copysignf(__fdividef(1.f - t, 1.f + t), x);
+}
 __device__ __forceinline__ float act_fwd(float x, int act) {
   switch (act) {
     case SF_ACT_RELU: return fmaxf(x, 0.f);
-    case SF_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
-    case SF_ACT_TANH: return tanhf(x);
+    case SF_ACT_SIGMOID: return sigmoid_fast(x);
+    case SF_ACT_TANH: return tanh_fast(x);
     default: return x;
   }
 }
@@ -48,23 +55,53 @@ __device__ __forceinline__ float act_bwd_from_out(float a, int act) {
     default: return 1.f;
   }
 }
+// whole-chunk forms: ONE (uniform) branch on the activation kind instead of one per element
+__device__ __forceinline__ void act_fwd32(float (&f)[32], int act) {
+  if (act == SF_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  } else if (act == SF_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = sigmoid_fast(f[j]);
+  } else if (act == SF_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
+  }
+}
+// f[j] *= act'(a[j]) (a = activation output); keep in (0, 1): a = act(z) * mask / keep (fused dropout), mask = a != 0
+__device__ __forceinline__ void act_bwd32(float (&f)[32], const float (&a)[32], int act, float keep) {
+  if (keep > 0.f && keep < 1.f) {
+    const float ik = __fdividef(1.f, keep);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= a[j] != 0.f ? act_bwd_from_out(a[j] * keep, act) * ik : 0.f;
+  } else if (act == SF_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = a[j] > 0.f ? f[j] : 0.f;
+  } else if (act == SF_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= a[j] * (1.f - a[j]);
+  } else if (act == SF_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= 1.f - a[j] * a[j];
+  }
+}
 
 // One 32-column chunk of a thread's output row: everything between the accumulator (v, already in registers) and
 // global memory.  `aux_pref` / `tgt_pref` are the act'(a) operand / label row of this chunk when the caller fetched
 // them before the accumulator wait (nullptr: read here).  kLoss compiles the fused softmax-CE / MSE heads in.
 template <bool kLoss>
 __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32_t (&v)[32], const float* s_bias32, int row, bool row_ok,
-                                          int col0, int M, int N, int lane, const uint4* aux_pref, const float* tgt_pref) {
+                                          int col0, int M, int N, int lane, const uint4* aux_pref, const float* tgt_pref,
+                                          unsigned long long* tq = nullptr) {
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * ep.alpha + s_bias32[j];
-    if (ep.act != SF_ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = act_fwd(f[j], ep.act);
-    }
+    if (tq != nullptr) tq[0] = trace_now();
+    act_fwd32(f, ep.act);
+    if (tq != nullptr) tq[1] = trace_now();
     if (ep.drop_keep > 0.f && ep.drop_keep < 1.f) {
       // fused dropout: keep with probability drop_keep, scale the survivors by 1 / drop_keep
-      const float inv_keep = 1.f / ep.drop_keep;
+      const float inv_keep = __fdividef(1.f, ep.drop_keep);
       const uint32_t thr = static_cast<uint32_t>(fminf(ep.drop_keep * 4294967296.f, 4294967040.f));
       const uint32_t stepc = ep.drop_ctr != nullptr ? *ep.drop_ctr : 0u;
 #pragma unroll
@@ -77,28 +114,30 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
         f[4 * g + 3] = rnd.w < thr ? f[4 * g + 3] * inv_keep : 0.f;
       }
     }
+    if (tq != nullptr) tq[2] = trace_now();
     if (kLoss && ep.loss_mode == SF_LOSS_SOFTMAX_XENT) {
       // whole row lives in this thread (host guarantees N <= 32): softmax + CE + gradient in registers
-      float ysum = 0.f, zy = 0.f, mx = -INFINITY;
       const float* yv = tgt_pref;                         // N <= 32: the single chunk was prefetched
+      const int nvalid = row_ok ? (N - col0 < 32 ? N - col0 : 32) : 0;
+      float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (row_ok && col0 + j < N) mx = fmaxf(mx, f[j]);
-      float se = 0.f;
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, j < nvalid ? f[j] : -INFINITY);
+      float se = 0.f, ysum = 0.f, zy = 0.f;
+      float ex[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        if (col0 + j < N && row_ok) {
-          se += __expf(f[j] - mx);
-          ysum += yv[j];
-          zy += yv[j] * f[j];
-        }
+        const bool ok = j < nvalid;
+        ex[j] = ok ? __expf(f[j] - mx) : 0.f;
+        const float y = ok ? yv[j] : 0.f;
+        se += ex[j];
+        ysum += y;
+        zy += ok ? y * f[j] : 0.f;
       }
-      const float inv_b = 1.f / static_cast<float>(M);
+      const float inv_b = __fdividef(1.f, static_cast<float>(M));
       float lrow = row_ok ? ((mx + __logf(se)) * ysum - zy) * inv_b : 0.f;
-      const float inv_se = row_ok ? 1.f / se : 0.f;
+      const float inv_se = row_ok ? __fdividef(1.f, se) : 0.f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        f[j] = (col0 + j < N && row_ok) ? (__expf(f[j] - mx) * inv_se * ysum - yv[j]) * inv_b : 0.f;
+      for (int j = 0; j < 32; ++j) f[j] = j < nvalid ? (ex[j] * inv_se * ysum - yv[j]) * inv_b : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
       if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow);
@@ -106,43 +145,42 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
       const float scale = 2.f / (static_cast<float>(M) * static_cast<float>(N));
       const float* tp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target + col0;
       float lrow = 0.f;
+      float a_out[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
+        a_out[j] = f[j];
         if (row_ok && col0 + j < N) {
           const float d = f[j] - (tgt_pref != nullptr ? tgt_pref[j] : tp[j]);
           lrow += d * d;
-          f[j] = d * scale * act_bwd_from_out(f[j], ep.act);
+          f[j] = d * scale;
         } else {
           f[j] = 0.f;
         }
       }
+      act_bwd32(f, a_out, ep.act, 0.f);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) lrow += __shfl_xor_sync(0xffffffffu, lrow, o);
       if (lane == 0 && lrow != 0.f) atomicAdd(ep.loss, lrow * 0.5f * scale);
     }
+    if (tq != nullptr) tq[3] = trace_now();
     if (ep.aux != nullptr && row_ok) {
       const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + col0;
+      float a32[32];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        if (col0 + g * 8 < ep.ld_aux) {
-          const uint4 q = (aux_pref != nullptr) ? aux_pref[g] : *reinterpret_cast<const uint4*>(ap + g * 8);
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (col0 + g * 8 < ep.ld_aux) q = (aux_pref != nullptr) ? aux_pref[g] : *reinterpret_cast<const uint4*>(ap + g * 8);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float2 a2 = __bfloat1622float2(h[t]);
-            if (ep.aux_keep > 0.f && ep.aux_keep < 1.f) {
-              // aux = act(z) * mask / keep: the dropout mask is (aux != 0), the activation output is aux * keep
-              const float ik = 1.f / ep.aux_keep;
-              f[g * 8 + 2 * t] *= a2.x != 0.f ? act_bwd_from_out(a2.x * ep.aux_keep, ep.aux_act) * ik : 0.f;
-              f[g * 8 + 2 * t + 1] *= a2.y != 0.f ? act_bwd_from_out(a2.y * ep.aux_keep, ep.aux_act) * ik : 0.f;
-            } else {
-              f[g * 8 + 2 * t] *= act_bwd_from_out(a2.x, ep.aux_act);
-              f[g * 8 + 2 * t + 1] *= act_bwd_from_out(a2.y, ep.aux_act);
-            }
-          }
+        for (int t = 0; t < 4; ++t) {
+          const float2 a2 = __bfloat1622float2(h[t]);
+          a32[g * 8 + 2 * t] = a2.x;
+          a32[g * 8 + 2 * t + 1] = a2.y;
         }
       }
+      act_bwd32(f, a32, ep.aux_act, ep.aux_keep);
     }
+    if (tq != nullptr) tq[4] = trace_now();
     // padded columns / rows contribute exact zeros everywhere below
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -168,6 +206,7 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
       if (col0 + lane < N) atomicAdd(ep.colsum + col0 + lane, r[0]);
     }
 
+    if (tq != nullptr) tq[5] = trace_now();          // tracer: math done, stores follow
     if ((ep.out_f32 != nullptr || ep.route != nullptr) && row_ok) {
       float* op;
       if (ep.route != nullptr) {
@@ -197,6 +236,7 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
           if (col0 + j < N) op[j] = f[j];
       }
     }
+    if (tq != nullptr) tq[6] = trace_now();
     if (ep.out_bf16 != nullptr && row_ok) {
       __nv_bfloat16* op = ep.out_bf16 + static_cast<size_t>(row) * ep.ld_bf16 + col0;
 #pragma unroll
@@ -211,6 +251,7 @@ __device__ __forceinline__ void epi_chunk(const SfGemmEpilogue& ep, const uint32
         }
       }
     }
+    if (tq != nullptr) tq[7] = trace_now();
     if (ep.outT_bf16 != nullptr && row_ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
@@ -382,34 +423,49 @@ sf_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         s_bias[j] = (ep.bias != nullptr && is_split0 && n0 + j < N) ? ep.bias[n0 + j] : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");           // epilogue warps only
     }
+    const SfGemmEpilogue& eps = ep;
     uint4 aux0[4] = {};
-    if (ep.aux != nullptr && row_ok) {
-      const __nv_bfloat16* ap = ep.aux + static_cast<size_t>(row) * ep.ld_aux + n0;
+    if (eps.aux != nullptr && row_ok) {
+      const __nv_bfloat16* ap = eps.aux + static_cast<size_t>(row) * eps.ld_aux + n0;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (n0 + g * 8 < ep.ld_aux) aux0[g] = *reinterpret_cast<const uint4*>(ap + g * 8);
+        if (n0 + g * 8 < eps.ld_aux) aux0[g] = *reinterpret_cast<const uint4*>(ap + g * 8);
     }
     float tgt0[32];
-    if (ep.loss_mode != SF_LOSS_NONE) {
-      const float* tp = ep.target + static_cast<size_t>(row_ok ? row : 0) * ep.ld_target + n0;
+    if (eps.loss_mode != SF_LOSS_NONE) {
+      const float* tp = eps.target + static_cast<size_t>(row_ok ? row : 0) * eps.ld_target + n0;
 #pragma unroll
       for (int j = 0; j < 32; ++j) tgt0[j] = (row_ok && n0 + j < N) ? tp[j] : 0.f;
     }
+    // touch every line of the epilogue descriptor now: the kernel-parameter bank is cold at every launch, and each first
+    // touch after the accumulator is ready would be a constant-cache miss on the critical path
+    asm volatile("" ::"l"(eps.out_f32), "l"(eps.colsum), "r"(eps.n_store_limit), "l"(eps.target), "l"(eps.loss), "l"(eps.route),
+                 "l"(eps.route_off), "l"(eps.drop_ctr), "f"(eps.aux_keep), "f"(eps.alpha), "r"(eps.accumulate));
     mbar_wait(tmem_full_bar, 0, 0x300);
     tc_fence_after_sync();
     const unsigned long long te1 = tr ? trace_now() : 0;
+    unsigned long long te2 = 0, tq8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(e * 32) << 16) + c * 32, v);
       tmem_ld_wait();
+      if (tr && c == 0) te2 = trace_now();
       const int col0 = n0 + c * 32;
-      if (col0 >= ep.n_store_limit) break;   // whole chunk outside every output pitch
-      epi_chunk<true>(ep, v, s_bias + c * 32, row, row_ok, col0, M, N, lane, c == 0 ? aux0 : nullptr, c == 0 ? tgt0 : nullptr);
+      if (col0 >= eps.n_store_limit) break;   // whole chunk outside every output pitch
+      epi_chunk<true>(eps, v, s_bias + c * 32, row, row_ok, col0, M, N, lane, c == 0 ? aux0 : nullptr, c == 0 ? tgt0 : nullptr,
+                      (tr && c == 0) ? tq8 : nullptr);
     }
-    if (tr) {                             // phase record: wait start / accumulator ready / epilogue done
-      const unsigned int i = atomicAdd(&g_trace_n, 1u);
-      if (i < g_trace_cap) g_trace_buf[i] = TraceRec{te0, te1, trace_now(), 102u, blockIdx.x + gridDim.x * blockIdx.y};
+    if (tr) {                             // phase records: wait start / accumulator ready / epilogue done;
+      const unsigned long long te4 = trace_now();                 // first chunk in registers / its math done / done
+      const unsigned int i = atomicAdd(&g_trace_n, 4u);
+      if (i + 3 < g_trace_cap) {
+        const unsigned int bid = blockIdx.x + gridDim.x * blockIdx.y;
+        g_trace_buf[i] = TraceRec{te0, te1, te4, 102u, bid};
+        g_trace_buf[i + 1] = TraceRec{te2, tq8[0], tq8[1], 103u, bid};        // chunk 0 in registers / alpha+bias / activation
+        g_trace_buf[i + 2] = TraceRec{tq8[2], tq8[3], tq8[4], 104u, bid};     // dropout / loss head / act'(aux)
+        g_trace_buf[i + 3] = TraceRec{tq8[5], tq8[6], tq8[7], 105u, bid};     // padding + colsum / fp32 out / bf16 out; then outT -> 102.t2
+      }
     }
     tc_fence_before_sync();
   }

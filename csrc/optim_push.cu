@@ -244,6 +244,179 @@ __device__ __forceinline__ void st_shadow16(__nv_bfloat16* dst, uint4 q, bool mc
 // `pub0` / `vec0`: publish targets standing in for a.shadow_dst[0] / a.vec_pub[0] (the applier alternates buffers).
 // HALVES: half-rows per thread (2: 256 threads per tile, 1: 512 threads per tile - the applier: a pass is bound by the
 // per-thread instruction chain, not by memory, so it spreads the tile over twice the warps)
+// Everything one thread holds for one tile between "loads issued" and "apply": the applier keeps TWO of these alive
+// (software pipeline: the next tile's tuples and first gradient are in flight while the current tile is applied).
+template <int HALVES>
+struct TileRegs {
+  SfTensorSeg sg;
+  int r0, c0, c;
+  bool vec;
+  int nv[HALVES];
+  int64_t e[HALVES];
+  float g[HALVES][4];
+  Upd u[HALVES][4];
+};
+
+__device__ __forceinline__ void tile_load_grad(const float* grad, int64_t e, int nv, bool vec, float (&g)[4]) {
+  g[0] = g[1] = g[2] = g[3] = 0.f;
+  if (nv == 0) return;
+  if (vec) {
+    const float4 gv = *reinterpret_cast<const float4*>(grad + e);
+    g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+  } else {
+    for (int j = 0; j < nv; ++j) g[j] = grad[e + j];
+  }
+}
+
+// phase 1 of a tile: geometry + every load of the thread's half-rows (tuples and the first gradient), nothing consumed yet
+template <bool ZERO, int HALVES>
+__device__ __forceinline__ void push_tile_load(const SfPushArgs& a, float* grad0, int tile, TileRegs<HALVES>& T, int skip, bool dry) {
+  const int tid = threadIdx.x;
+  if (a.n_inline_segs > 0) {                         // tables live in constant (parameter) space
+    int si = 0;
+    while (si + 1 < a.n_inline_segs && tile >= a.tile_prefix[si + 1]) ++si;
+    T.sg = a.inline_segs[si];
+    const int local = tile - a.tile_prefix[si];
+    const int tiles_c = (T.sg.cols + kTileC - 1) / kTileC;
+    T.r0 = (local / tiles_c) * kTileR;
+    T.c0 = (local % tiles_c) * kTileC;
+  } else {
+    const int seg_i = a.tile_map[tile * 3 + 0];
+    T.r0 = a.tile_map[tile * 3 + 1] * kTileR;
+    T.c0 = a.tile_map[tile * 3 + 2] * kTileC;
+    T.sg = a.segs[seg_i];
+  }
+  const SfTensorSeg& sg = T.sg;
+  T.vec = ((sg.cols & 3) == 0) && ((sg.offset & 3) == 0);
+  const int tx = tid & 15, ty = tid >> 4;
+  T.c = T.c0 + tx * 4;
+#pragma unroll
+  for (int half = 0; half < HALVES; ++half) {
+    const int r = T.r0 + ty + 16 * half;
+    T.nv[half] = (r < sg.rows && T.c < sg.cols) ? ((sg.cols - T.c) >= 4 ? 4 : (sg.cols - T.c)) : 0;
+    T.e[half] = sg.offset + static_cast<int64_t>(r) * sg.cols + T.c;
+    if (!(skip & 4)) tile_load_grad(grad0, T.e[half], T.nv[half], T.vec, T.g[half]);
+    else T.g[half][0] = T.g[half][1] = T.g[half][2] = T.g[half][3] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (!a.drop && j < T.nv[half] && !(skip & 4)) v = ld_weak_f4(reinterpret_cast<const float*>(a.state + T.e[half] + j));
+      T.u[half][j] = Upd{v.x, v.y, v.z, v.w};
+    }
+    if (ZERO && T.nv[half] > 0 && !dry) {
+      // the gradient is consumed: zero it for the next step's accumulating epilogues
+      if (T.vec) *reinterpret_cast<float4*>(grad0 + T.e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      else for (int j = 0; j < T.nv[half]; ++j) grad0[T.e[half] + j] = 0.f;
+    }
+  }
+}
+
+// phases 2 + 3 of a tile: n_grads optimizer steps in registers, then the tuple stores and the bf16 / fp32 publish
+template <int OPT, bool ZERO, int HALVES>
+__device__ __forceinline__ void push_tile_apply(const SfPushArgs& a, float* const* grads, int n_grads, TileRegs<HALVES>& T,
+                                                const uint32_t* s_t_ptr, bool sync_for_t, __nv_bfloat16 (*s_tr)[kTileR + 8],
+                                                __nv_bfloat16* pub0, float* vec0, unsigned long long* tp, long long off_bf16,
+                                                long long off_f32, int skip, bool dry) {
+  constexpr int NS = Slots<OPT>::n;
+  const int tid = threadIdx.x;
+  const bool mc = a.shadow_is_mc != 0;
+  const SfTensorSeg& sg = T.sg;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int r0 = T.r0, c0 = T.c0, c = T.c;
+  // ---- step number: under the lock it was granted above; Hogwild read it at kernel entry ----
+  if (sync_for_t) __syncthreads();     // the step count was written to shared memory by thread 0
+  const float t0 = static_cast<float>(*s_t_ptr);
+  // ---- phase 2: n_grads optimizer steps in registers (the next push's gradient is in flight meanwhile) ----
+  if (!a.drop) {
+    for (int k = 0; k < n_grads; ++k) {
+      float gn[HALVES][4];
+      if (k + 1 < n_grads && !(skip & 4)) {
+#pragma unroll
+        for (int half = 0; half < HALVES; ++half) tile_load_grad(grads[k + 1], T.e[half], T.nv[half], T.vec, gn[half]);
+      }
+      const float t = t0 + static_cast<float>(k);
+      float lr_t = a.h.lr;
+      if constexpr (OPT == SF_OPT_ADAM) {
+        lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
+      }
+#pragma unroll
+      for (int half = 0; half < HALVES; ++half)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < T.nv[half]) apply_rule<OPT>(T.u[half][j], T.g[half][j] * a.grad_scale, a.h, t, lr_t);
+      if (k + 1 < n_grads) {
+#pragma unroll
+        for (int half = 0; half < HALVES; ++half)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) T.g[half][j] = gn[half][j];
+      }
+    }
+  }
+  if (a.mb_zero && !dry) {
+    // accumulating wgrad epilogues (split-K conv) add into the mailbox: hand it back zeroed
+    for (int k = 0; k < n_grads; ++k)
+#pragma unroll
+      for (int half = 0; half < HALVES; ++half) {
+        if (T.nv[half] == 0) continue;
+        if (T.vec) *reinterpret_cast<float4*>(grads[k] + T.e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else for (int j = 0; j < T.nv[half]; ++j) grads[k][T.e[half] + j] = 0.f;
+      }
+  }
+  if (tp != nullptr) tp[1] = gtime_ns() + static_cast<unsigned long long>(T.u[0][0].p == 12345.678f);      // optimizer math done (loads consumed)
+  // ---- phase 3: stores ----
+#pragma unroll
+  for (int half = 0; half < HALVES; ++half) {
+    const int rl = ty + 16 * half;
+    const int r = r0 + rl;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    if (T.nv[half] > 0 && !a.drop) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (j < T.nv[half]) {
+          const Upd& q = T.u[half][j];
+          w[j] = q.p;
+          float* dst = reinterpret_cast<float*>(a.state + T.e[half] + j);
+          if (!(skip & 2)) st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
+          if (skip & 1) {
+          } else if (a.n_vec_dst > 0) {                               // sharded master: every replica's fp32 tail
+            if (T.e[half] + j >= a.vec_offset) {
+              const long long vi = T.e[half] + j - a.vec_offset;
+              for (int d = 0; d < a.n_vec_dst; ++d) st_vec_f32(a.vec_dst[d] + off_f32 + vi, q.p, mc);
+            }
+          } else if (a.n_vec_pub > 0 && T.e[half] + j >= a.vec_offset) {       // 1-D variables: fp32 publish copy / copies
+            const long long vi = T.e[half] + j - a.vec_offset;
+            vec0[vi] = q.p;
+            if (a.n_vec_pub > 1) a.vec_pub[1][vi] = q.p;
+          }
+        }
+      }
+      // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
+      if (sg.w_off >= 0 && !(skip & 1)) {
+        const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
+        const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
+        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8((d == 0 ? pub0 : a.shadow_dst[d] + off_bf16) + wo, q, mc && d == 0);
+      }
+    }
+    if (sg.wt_off >= 0 && !a.drop) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s_tr[tx * 4 + j][rl] = __float2bfloat16(w[j]);
+    }
+  }
+  if (tp != nullptr) tp[2] = gtime_ns();      // state + row-major publish stores issued
+  if (sg.wt_off >= 0 && !a.drop) {
+    __syncthreads();
+    // transposed bf16 publish: [cols, wt_ld]; each thread owns 8 consecutive rows of one column
+    const int cl = tid >> 2, part = tid & 3;
+    const int cc = c0 + cl, rr = r0 + part * 8;
+    if (cl < kTileC && cc < sg.cols && rr < sg.rows && !(skip & 1)) {
+      const int64_t to = sg.wt_off + static_cast<int64_t>(cc) * sg.wt_ld + rr;
+      const uint4 q = *reinterpret_cast<const uint4*>(&s_tr[cl][part * 8]);
+      for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16((d == 0 ? pub0 : a.shadow_dst[d] + off_bf16) + to, q, mc && d == 0);
+    }
+    __syncthreads();
+  }
+}
+
 template <int OPT, bool ZERO, int HALVES = 2>
 __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* grads, int n_grads, int tile,
                                           const uint32_t* s_t_ptr, bool sync_for_t, __nv_bfloat16 (*s_tr)[kTileR + 8],
@@ -251,156 +424,28 @@ __device__ __forceinline__ void push_tile(const SfPushArgs& a, float* const* gra
                                           long long off_bf16 = 0, long long off_f32 = 0, bool dry = false) {
   // dry: execute the whole instruction stream without touching memory (keeps the code resident in the SM's instruction cache)
   const int skip = dry ? 7 : a.dbg_skip;
-  constexpr int NS = Slots<OPT>::n;
-  const int tid = threadIdx.x;
-  const bool mc = a.shadow_is_mc != 0;
-  {
-    int r0, c0;
-    SfTensorSeg sg;
-    if (a.n_inline_segs > 0) {                         // tables live in constant (parameter) space
-      int si = 0;
-      while (si + 1 < a.n_inline_segs && tile >= a.tile_prefix[si + 1]) ++si;
-      sg = a.inline_segs[si];
-      const int local = tile - a.tile_prefix[si];
-      const int tiles_c = (sg.cols + kTileC - 1) / kTileC;
-      r0 = (local / tiles_c) * kTileR;
-      c0 = (local % tiles_c) * kTileC;
-    } else {
-      const int seg_i = a.tile_map[tile * 3 + 0];
-      r0 = a.tile_map[tile * 3 + 1] * kTileR;
-      c0 = a.tile_map[tile * 3 + 2] * kTileC;
-      sg = a.segs[seg_i];
-    }
-    const bool vec = ((sg.cols & 3) == 0) && ((sg.offset & 3) == 0);
-    const int tx = tid & 15, ty = tid >> 4;
-    const int c = c0 + tx * 4;
-    auto load_grad = [&](const float* grad, int64_t e, int nv, float (&g)[4]) {
-      g[0] = g[1] = g[2] = g[3] = 0.f;
-      if (nv == 0) return;
-      if (vec) {
-        const float4 gv = *reinterpret_cast<const float4*>(grad + e);
-        g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
-      } else {
-        for (int j = 0; j < nv; ++j) g[j] = grad[e + j];
-      }
-    };
-    // ---- phase 1: issue every load of both half-rows before anything depends on them ----
-    float g[HALVES][4];
-    Upd u[HALVES][4];
-    int nv[HALVES];
-    int64_t e[HALVES];
-#pragma unroll
-    for (int half = 0; half < HALVES; ++half) {
-      const int r = r0 + ty + 16 * half;
-      nv[half] = (r < sg.rows && c < sg.cols) ? ((sg.cols - c) >= 4 ? 4 : (sg.cols - c)) : 0;
-      e[half] = sg.offset + static_cast<int64_t>(r) * sg.cols + c;
-      if (!(skip & 4)) load_grad(grads[0], e[half], nv[half], g[half]);
-      else g[half][0] = g[half][1] = g[half][2] = g[half][3] = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!a.drop && j < nv[half] && !(skip & 4)) v = ld_weak_f4(reinterpret_cast<const float*>(a.state + e[half] + j));
-        u[half][j] = Upd{v.x, v.y, v.z, v.w};
-      }
-      if (ZERO && nv[half] > 0 && !dry) {
-        // the gradient is consumed: zero it for the next step's accumulating epilogues
-        if (vec) *reinterpret_cast<float4*>(grads[0] + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
-        else for (int j = 0; j < nv[half]; ++j) grads[0][e[half] + j] = 0.f;
-      }
-    }
-    if (tp != nullptr) tp[0] = gtime_ns();      // loads issued
-    // ---- step number: under the lock it was granted above; Hogwild read it at kernel entry ----
-    if (sync_for_t) __syncthreads();     // the step count was written to shared memory by thread 0
-    const float t0 = static_cast<float>(*s_t_ptr);
-    // ---- phase 2: n_grads optimizer steps in registers (the next push's gradient is in flight meanwhile) ----
-    if (!a.drop) {
-      for (int k = 0; k < n_grads; ++k) {
-        float gn[HALVES][4];
-        if (k + 1 < n_grads && !(skip & 4)) {
-#pragma unroll
-          for (int half = 0; half < HALVES; ++half) load_grad(grads[k + 1], e[half], nv[half], gn[half]);
-        }
-        const float t = t0 + static_cast<float>(k);
-        float lr_t = a.h.lr;
-        if constexpr (OPT == SF_OPT_ADAM) {
-          lr_t = a.h.lr * sqrtf(1.f - __powf(a.h.beta2, t)) / (1.f - __powf(a.h.beta1, t));
-        }
-#pragma unroll
-        for (int half = 0; half < HALVES; ++half)
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (j < nv[half]) apply_rule<OPT>(u[half][j], g[half][j] * a.grad_scale, a.h, t, lr_t);
-        if (k + 1 < n_grads) {
-#pragma unroll
-          for (int half = 0; half < HALVES; ++half)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) g[half][j] = gn[half][j];
-        }
-      }
-    }
-    if (a.mb_zero && !dry) {
-      // accumulating wgrad epilogues (split-K conv) add into the mailbox: hand it back zeroed
-      for (int k = 0; k < n_grads; ++k)
-#pragma unroll
-        for (int half = 0; half < HALVES; ++half) {
-          if (nv[half] == 0) continue;
-          if (vec) *reinterpret_cast<float4*>(grads[k] + e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
-          else for (int j = 0; j < nv[half]; ++j) grads[k][e[half] + j] = 0.f;
-        }
-    }
-    if (tp != nullptr) tp[1] = gtime_ns() + static_cast<unsigned long long>(u[0][0].p == 12345.678f);      // optimizer math done (loads consumed)
-    // ---- phase 3: stores ----
-#pragma unroll
-    for (int half = 0; half < HALVES; ++half) {
-      const int rl = ty + 16 * half;
-      const int r = r0 + rl;
-      float w[4] = {0.f, 0.f, 0.f, 0.f};
-      if (nv[half] > 0 && !a.drop) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (j < nv[half]) {
-            const Upd& q = u[half][j];
-            w[j] = q.p;
-            float* dst = reinterpret_cast<float*>(a.state + e[half] + j);
-            if (!(skip & 2)) st_weak_f4(dst, q.p, NS >= 1 ? q.s0 : 0.f, NS >= 2 ? q.s1 : 0.f, NS >= 3 ? q.s2 : 0.f);
-            if (skip & 1) {
-            } else if (a.n_vec_dst > 0) {                               // sharded master: every replica's fp32 tail
-              if (e[half] + j >= a.vec_offset) {
-                const long long vi = e[half] + j - a.vec_offset;
-                for (int d = 0; d < a.n_vec_dst; ++d) st_vec_f32(a.vec_dst[d] + off_f32 + vi, q.p, mc);
-              }
-            } else if (a.n_vec_pub > 0 && e[half] + j >= a.vec_offset) {       // 1-D variables: fp32 publish copy / copies
-              const long long vi = e[half] + j - a.vec_offset;
-              vec0[vi] = q.p;
-              if (a.n_vec_pub > 1) a.vec_pub[1][vi] = q.p;
-            }
-          }
-        }
-        // row-major bf16 publish: [rows, w_ld]; w_ld is a multiple of 8 and c of 4, pads carry zeros
-        if (sg.w_off >= 0 && !(skip & 1)) {
-          const int64_t wo = sg.w_off + static_cast<int64_t>(r) * sg.w_ld + c;
-          const uint2 q = make_uint2(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]));
-          for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow8((d == 0 ? pub0 : a.shadow_dst[d] + off_bf16) + wo, q, mc && d == 0);
-        }
-      }
-      if (sg.wt_off >= 0 && !a.drop) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) s_tr[tx * 4 + j][rl] = __float2bfloat16(w[j]);
-      }
-    }
-    if (tp != nullptr) tp[2] = gtime_ns();      // state + row-major publish stores issued
-    if (sg.wt_off >= 0 && !a.drop) {
-      __syncthreads();
-      // transposed bf16 publish: [cols, wt_ld]; each thread owns 8 consecutive rows of one column
-      const int cl = tid >> 2, part = tid & 3;
-      const int cc = c0 + cl, rr = r0 + part * 8;
-      if (cl < kTileC && cc < sg.cols && rr < sg.rows && !(skip & 1)) {
-        const int64_t to = sg.wt_off + static_cast<int64_t>(cc) * sg.wt_ld + rr;
-        const uint4 q = *reinterpret_cast<const uint4*>(&s_tr[cl][part * 8]);
-        for (int d = 0; d < a.n_shadow_dst; ++d) st_shadow16((d == 0 ? pub0 : a.shadow_dst[d] + off_bf16) + to, q, mc && d == 0);
-      }
-      __syncthreads();
-    }
+  TileRegs<HALVES> T;
+  push_tile_load<ZERO, HALVES>(a, grads[0], tile, T, skip, dry);
+  if (tp != nullptr) tp[0] = gtime_ns();      // loads issued
+  push_tile_apply<OPT, ZERO, HALVES>(a, grads, n_grads, T, s_t_ptr, sync_for_t, s_tr, pub0, vec0, tp, off_bf16, off_f32, skip, dry);
+}
+
+// A run of tiles on one CTA with the NEXT tile's loads in flight while the current one is applied (the applier of a big
+// shard: ~60 tiles per CTA; without this every tile pays a full HBM round trip with nothing else outstanding).
+template <int OPT, int HALVES>
+__device__ __forceinline__ void push_tiles_pipelined(const SfPushArgs& a, float* const* grads, int n_grads, int tile, int tile_hi, int stride,
+                                                     const uint32_t* s_t_ptr, __nv_bfloat16 (*s_tr)[kTileR + 8], __nv_bfloat16* pub0,
+                                                     float* vec0, unsigned long long* tp, long long off_bf16, long long off_f32) {
+  const int skip = a.dbg_skip;
+  TileRegs<HALVES> cur, nxt;
+  if (tile >= tile_hi) return;
+  push_tile_load<false, HALVES>(a, grads[0], tile, cur, skip, false);
+  for (; tile < tile_hi; tile += stride) {
+    const bool more = tile + stride < tile_hi;
+    if (more) push_tile_load<false, HALVES>(a, grads[0], tile + stride, nxt, skip, false);
+    if (tp != nullptr) tp[0] = gtime_ns();
+    push_tile_apply<OPT, false, HALVES>(a, grads, n_grads, cur, s_t_ptr, false, s_tr, pub0, vec0, tp, off_bf16, off_f32, skip, false);
+    if (more) cur = nxt;
   }
 }
 
@@ -411,6 +456,26 @@ __device__ __forceinline__ void signal_done(float* loss_out, unsigned int* done_
   *done_dev = v;
   asm volatile("fence.acq_rel.sys;" ::: "memory");
   st_release_sys(reinterpret_cast<uint32_t*>(loss_out) + 1, v);
+}
+
+// End-of-step hand-off to the host: the mean loss and the step count.  With a spinning host (done_dev) both travel in
+// ONE aligned 8-byte store to the pinned word pair {loss, count} - single-copy atomic, so no system fence (measured
+// ~5 us on B200, on the critical path of every step) is needed to order "loss before count".
+__device__ __forceinline__ void publish_loss(float* loss_out, float* loss_acc, unsigned int* done_dev) {
+  if (loss_acc != nullptr && done_dev != nullptr) {
+    const float l = *loss_acc;
+    *loss_acc = 0.f;
+    const unsigned int v = *done_dev + 1;
+    *done_dev = v;
+    const unsigned long long w = static_cast<unsigned long long>(__float_as_uint(l)) | (static_cast<unsigned long long>(v) << 32);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(loss_out), "l"(w) : "memory");
+    return;
+  }
+  if (loss_acc != nullptr) {
+    *loss_out = *loss_acc;
+    *loss_acc = 0.f;
+  }
+  signal_done(loss_out, done_dev);
 }
 
 template <int OPT, bool SYS>
@@ -466,11 +531,7 @@ push_kernel(const SfPushArgs a, uint32_t* local_sync) {
     if (prev == gridDim.x - 1) {                  // last CTA of this push
       if (locked) (void)ld_acquire_gpu(local_sync + 2);
       local_sync[2] = 0;
-      if (a.loss_acc != nullptr) {
-        *a.loss_out = *a.loss_acc;
-        *a.loss_acc = 0.f;
-      }
-      signal_done(a.loss_out, a.done_dev);
+      publish_loss(a.loss_out, a.loss_acc, a.done_dev);
       if (a.drop) {
         lk_red_relaxed<SYS>(a.ctrl + SF_CTRL_DROPPED, 1u);
       } else {
@@ -613,11 +674,7 @@ post_kernel(const SfPostArgs a, uint32_t* local_sync) {
     if (prev == gridDim.x - 1) {
       (void)ld_acquire_gpu(local_sync + 2);
       local_sync[2] = 0;
-      if (a.loss_acc != nullptr) {
-        *a.loss_out = *a.loss_acc;
-        *a.loss_acc = 0.f;
-      }
-      signal_done(a.loss_out, a.done_dev);
+      publish_loss(a.loss_out, a.loss_acc, a.done_dev);
       if (!a.drop) {
         st_release_gpu(local_sync + 4, s_seq + 1);
         st_release_sys(a.flags + SF_MB_POSTED, s_seq + 1);
@@ -793,9 +850,14 @@ applier_kernel(const SfApplierArgs a, const uint32_t seq) {
     // warm mode: CTA 0 only coordinates (its tile code would be cold: it spends its idle time scanning the flags)
     const int tile_ctas = a.warm_polls > 0 ? static_cast<int>(gridDim.x) - 1 : static_cast<int>(gridDim.x);
     const int tile_cta = a.warm_polls > 0 ? static_cast<int>(blockIdx.x) - 1 : static_cast<int>(blockIdx.x);
-    if (tile_cta >= 0)
-      for (int tile = tile_lo + tile_cta; tile < tile_hi; tile += tile_ctas)
-        push_tile<OPT, false, 1>(a.push, s_grads, n, tile, &s_t, false, s_tr, pub0, vec0, probe ? tpt : nullptr, off_bf16, off_f32);
+    if (tile_cta >= 0) {
+      if (tile_hi - tile_lo > tile_ctas)      // several tiles per CTA: keep the next tile's loads in flight
+        push_tiles_pipelined<OPT, 1>(a.push, s_grads, n, tile_lo + tile_cta, tile_hi, tile_ctas, &s_t, s_tr, pub0, vec0, probe ? tpt : nullptr,
+                                     off_bf16, off_f32);
+      else
+        for (int tile = tile_lo + tile_cta; tile < tile_hi; tile += tile_ctas)
+          push_tile<OPT, false, 1>(a.push, s_grads, n, tile, &s_t, false, s_tr, pub0, vec0, probe ? tpt : nullptr, off_bf16, off_f32);
+    }
     __syncthreads();
     const unsigned long long tp1 = probe ? gtime_ns() : 0ull;
     if (probe && tpt[0] != 0ull) {
@@ -1096,11 +1158,7 @@ post_flags_kernel(const SfPostFlagsArgs a) {
     return;
   }
   if (tid == 0) {
-    if (a.loss_acc != nullptr) {
-      *a.loss_out = *a.loss_acc;
-      *a.loss_acc = 0.f;
-    }
-    signal_done(a.loss_out, a.done_dev);
+    publish_loss(a.loss_out, a.loss_acc, a.done_dev);
   }
   if (!a.drop && a.phase == 2 && tid < a.n_shards) {
     // every gradient store (wgrad epilogues, tail forwarding) belongs to a kernel that COMPLETED before this one started

@@ -3,8 +3,8 @@
 Execution modes (chosen automatically):
 
 =============================  =================================================================
-SPMD + GPUs (torchrun)          one rank per GPU; rank 0's GPU holds the master segment, exported
-                                to the other ranks through CUDA IPC; B200Engine everywhere.
+SPMD + GPUs (torchrun)          one rank per GPU; the master is sharded over the GPUs' symmetric VMM segments
+                                (parallel/sharded.py; NVSwitch multicast publish); B200Engine everywhere.
 SPMD, CPU only (gloo)           rank 0 hosts the ParameterServer + GlooServer threads; every rank
                                 (0 included) runs a TorchEngine  (BASELINE.json config 1).
 single process + GPUs           one worker thread per GPU (peer access to the master on cuda:0).
@@ -17,8 +17,10 @@ The reference's fixed costs are gone: no server process spawn, no 8 s sleep
 from __future__ import annotations
 
 import os
+import sys
 import threading
 import warnings
+from collections import Counter
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -35,6 +37,10 @@ from .param_server import GlooServer, GlooTransport, LocalTransport, ParameterSe
 from .worker import B200Engine, Engine, TorchEngine, run_partition
 
 Partition = Tuple[np.ndarray, Optional[np.ndarray]]
+
+
+# how many sessions each engine kind served in this process (printed by the test-suite summary and by bench.py)
+ENGINE_USES: Counter = Counter()
 
 
 class TrainingSession:
@@ -62,19 +68,26 @@ class TrainingSession:
         self.ctx = D.get_context()
         self.use_cuda = torch.cuda.is_available() and engine != "torch" and os.environ.get("SPARKFLOW_ENGINE", "") != "torch"
         self.engine_kind = "torch"
+        self.engine_reason = "no CUDA device" if not torch.cuda.is_available() else "engine='torch' requested"
         if self.use_cuda:
             try:
                 from .plan_builder import check_grammar
 
                 check_grammar(compile_graph(self.ir, tf_input, tf_label))
                 self.engine_kind = "b200"
+                self.engine_reason = "graph compiled to the native sm_100a plan"
             except UnsupportedGraph as exc:
                 if engine == "b200":
                     raise
+                self.engine_reason = f"graph outside the compiled plan family: {exc}"
                 warnings.warn(f"sparkflow_b200: graph is outside the compiled sm_100a plan family ({exc}); "
                               "running the generic PyTorch interpreter engine on the GPU instead", RuntimeWarning)
         elif engine == "b200":
             raise RuntimeError("engine='b200' requested but no CUDA device is available")
+        ENGINE_USES[self.engine_kind] += 1
+        if torch.cuda.is_available() and (self.engine_kind != "b200" or self.verbose or os.environ.get("SPARKFLOW_LOG_ENGINE")):
+            # never silent about which engine trains the model on a GPU box
+            print(f"[sparkflow_b200] engine={self.engine_kind} ({self.engine_reason})", file=sys.stderr, flush=True)
         self.master = None           # MasterState (GPU) or ParameterServer (host)
         self.gloo_server: Optional[GlooServer] = None
         self._gloo_transport: Optional[GlooTransport] = None      # one per non-master rank, shared by its partitions

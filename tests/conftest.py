@@ -43,6 +43,25 @@ def pytest_runtest_makereport(item, call):
             pass
 
 
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Which engine actually ran: a GPU run that only exercised the PyTorch interpreter must not look like a native run."""
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return
+        from sparkflow_b200.ops import native
+        from sparkflow_b200.parallel.session import ENGINE_USES
+
+        ext = native.cuda_ext()
+        terminalreporter.write_line(
+            "sparkflow_b200 engines used by TrainingSession in this run: "
+            + (", ".join(f"{k}={v}" for k, v in sorted(ENGINE_USES.items())) or "none")
+            + f"; native extension: {getattr(ext, '__file__', '?')}")
+    except Exception as exc:  # pragma: no cover
+        terminalreporter.write_line(f"sparkflow_b200 engine summary unavailable: {exc}")
+
+
 @pytest.fixture(scope="session")
 def tf_checkpoint(tmp_path_factory):
     """A self-generated TF-V2 checkpoint of the reference fixture's architecture (2-10 tanh-10 tanh-1 sigmoid, Adam

@@ -37,22 +37,30 @@ rows = []
 for r in sorted(rec, key=lambda r: (int(r["t0"]))):
     rows.append(dict(kid=int(r["kid"]), block=int(r["block"]), t0=(int(r["t0"]) - base) / 1e3, t1=(int(r["t1"]) - base) / 1e3,
                      t2=(int(r["t2"]) - base) / 1e3))
-# per-launch summary: group consecutive same-kid CTA records
+# per-launch summary: CTAs of one launch leave griddepcontrol.wait together, so records of one kernel id are grouped by
+# the proximity of their `ready` stamps (pre-launched successors START early and would otherwise be merged)
 summ = []
-cur = None
+by_kid = {}
 for r in [x for x in rows if x["kid"] < 100]:
-    if cur is None or r["kid"] != cur["kid"] or r["t0"] > cur["end"] + 0.2 or (r["block"] == 0 and cur["ctas"] > 0 and r["t0"] > cur["start"] + 0.5):
-        cur = dict(kid=r["kid"], start=r["t0"], ready=r["t1"], end=r["t2"], ctas=0)
-        summ.append(cur)
-    cur["ctas"] += 1
-    cur["ready"] = max(cur["ready"], r["t1"])
-    cur["end"] = max(cur["end"], r["t2"])
+    by_kid.setdefault(r["kid"], []).append(r)
+for kid, rs in by_kid.items():
+    rs.sort(key=lambda r: r["t1"])
+    cur = None
+    for r in rs:
+        if cur is None or r["t1"] > cur["last_ready"] + 0.3:
+            cur = dict(kid=kid, start=r["t0"], ready=r["t1"], end=r["t2"], ctas=0, last_ready=r["t1"])
+            summ.append(cur)
+        cur["ctas"] += 1
+        cur["start"] = min(cur["start"], r["t0"])
+        cur["last_ready"] = r["t1"]
+        cur["end"] = max(cur["end"], r["t2"])
+summ.sort(key=lambda c: c["ready"])
 names = {1: "gemm", 2: "cast", 3: "softmax", 4: "mse", 5: "argmax", 6: "push", 7: "pull", 8: "im2col", 9: "col2im", 10: "pool_fwd", 11: "pool_bwd"}
 print("plan:", plan.names())
 print("%-8s %5s %9s %9s %9s %8s" % ("kernel", "ctas", "start_us", "ready_us", "end_us", "dur_us"))
 for s in summ:
     print("%-8s %5d %9.2f %9.2f %9.2f %8.2f" % (names.get(s["kid"], s["kid"]), s["ctas"], s["start"], s["ready"], s["end"], s["end"] - s["ready"]))
-print("--- gemm phases (block 0 of each gemm): 101 = MMA thread [role start, first operands, last MMA issued]; 102 = epilogue [wait start, acc ready, done]")
+print("--- gemm phases (block 0 of each gemm): 101 = MMA thread [role start, first operands, last MMA issued]; 102 = epilogue [wait start, acc ready, done]; 103 = [chunk 0 in registers, alpha+bias, activation]; 104 = [dropout, loss head, act'(aux)]; 105 = [padding+colsum, fp32 out, bf16 out]")
 for r in rows:
     if r["kid"] >= 100 and r["block"] == 0:
         print(r)
