@@ -55,6 +55,76 @@ im2col_kernel(const __nv_bfloat16* __restrict__ in, int n, int h, int w, int c, 
   trace.end(KID_IM2COL);
 }
 
+// Fast path (C % 8 == 0, ld_out % 8 == 0, no transposed copy - the MN-major wgrad reads `out` itself): one 16-byte
+// vector = 8 channels of one filter tap per thread; loads and stores are both contiguous along k.
+__global__ void __launch_bounds__(256)
+im2col_vec8_kernel(const uint4* __restrict__ in, int n, int h, int w, int c8, int kh, int kw, uint4* __restrict__ out, int ld8) {
+  TraceScope trace;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.mark();
+  const int oh = h - kh + 1, ow = w - kw + 1;
+  const int M = n * oh * ow, K8 = kh * kw * c8;
+  const long long total = static_cast<long long>(M) * ld8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int m = static_cast<int>(i / ld8), q = static_cast<int>(i - static_cast<long long>(m) * ld8);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);                    // pad columns carry zeros
+    if (q < K8) {
+      const int tap = q / c8, cc = q - tap * c8;
+      const int dy = tap / kw, dx = tap - dy * kw;
+      const int b = m / (oh * ow), r = m - b * (oh * ow);
+      const int y = r / ow, x = r - y * ow;
+      v = in[(static_cast<size_t>(b * h + y + dy) * w + (x + dx)) * c8 + cc];
+    }
+    out[i] = v;
+  }
+  trace.end(KID_IM2COL);
+}
+
+__device__ __forceinline__ void acc_bf16x8(float (&acc)[8], const uint4& q) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const float2 f = __bfloat1622float2(h2[t]);
+    acc[2 * t] += f.x;
+    acc[2 * t + 1] += f.y;
+  }
+}
+
+// col2im gather, 8 channels per thread (C % 8 == 0, ld_cols % 8 == 0)
+__global__ void __launch_bounds__(256)
+col2im_vec8_kernel(const uint4* __restrict__ dcols, int ld8, int n, int h, int w, int c8, int kh, int kw, uint4* __restrict__ din) {
+  TraceScope trace;
+  pdl_launch_dependents();
+  pdl_wait();
+  trace.mark();
+  const int oh = h - kh + 1, ow = w - kw + 1;
+  const int total = n * h * w * c8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int cc = i % c8;
+    int t = i / c8;
+    const int x = t % w;
+    t /= w;
+    const int y = t % h;
+    const int b = t / h;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int dy_lo = y - (oh - 1) > 0 ? y - (oh - 1) : 0, dy_hi = y < kh - 1 ? y : kh - 1;
+    const int dx_lo = x - (ow - 1) > 0 ? x - (ow - 1) : 0, dx_hi = x < kw - 1 ? x : kw - 1;
+    for (int dy = dy_lo; dy <= dy_hi; ++dy) {
+      const uint4* row = dcols + (static_cast<size_t>(b * oh + (y - dy)) * ow + x) * ld8 + (dy * kw) * c8 + cc;
+      for (int dx = dx_lo; dx <= dx_hi; ++dx) acc_bf16x8(acc, row[dx * c8 - static_cast<long long>(dx) * ld8]);
+    }
+    uint4 q;
+    q.x = pack_bf16x2(acc[0], acc[1]);
+    q.y = pack_bf16x2(acc[2], acc[3]);
+    q.z = pack_bf16x2(acc[4], acc[5]);
+    q.w = pack_bf16x2(acc[6], acc[7]);
+    din[i] = q;
+  }
+  trace.end(KID_COL2IM);
+}
+
 // ------------------------------------------------------------------------------------------------
 // col2im as a gather (no atomics): din[b, y, x, c] = sum_{dy,dx} dcols[(b, y-dy, x-dx), (dy*kw+dx)*C + c]
 // ------------------------------------------------------------------------------------------------
@@ -205,6 +275,12 @@ static inline int grid_1d(size_t total) {
 extern "C" int sf_im2col_nhwc(const __nv_bfloat16* in, int n, int h, int w, int c, int kh, int kw, __nv_bfloat16* out,
                               int ld_out, __nv_bfloat16* outT, int ld_t, cudaStream_t st) {
   const int M = n * (h - kh + 1) * (w - kw + 1), K = kh * kw * c;
+  if (outT == nullptr && out != nullptr && (c & 7) == 0 && (ld_out & 7) == 0 && ld_out >= K && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const size_t total = static_cast<size_t>(M) * (ld_out / 8);
+    return static_cast<int>(sf::launch(sf::im2col_vec8_kernel, dim3(grid_1d(total)), dim3(256), 0, st, reinterpret_cast<const uint4*>(in), n, h, w,
+                                       c / 8, kh, kw, reinterpret_cast<uint4*>(out), ld_out / 8));
+  }
   const int span_k = (out && ld_out > K) ? ld_out : K;
   dim3 grid((M + 31) / 32, (span_k + 31) / 32);
   return static_cast<int>(sf::launch(sf::im2col_kernel, grid, dim3(256), 0, st, in, n, h, w, c, kh, kw, out, ld_out, outT, ld_t));
@@ -213,6 +289,10 @@ extern "C" int sf_im2col_nhwc(const __nv_bfloat16* in, int n, int h, int w, int 
 extern "C" int sf_col2im_nhwc(const __nv_bfloat16* dcols, int ld_cols, int n, int h, int w, int c, int kh, int kw,
                               __nv_bfloat16* din, cudaStream_t st) {
   const size_t total = static_cast<size_t>(n) * h * w * c;
+  if ((c & 7) == 0 && (ld_cols & 7) == 0 && total / 8 < (1u << 30) && (reinterpret_cast<uintptr_t>(dcols) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(din) & 15) == 0)
+    return static_cast<int>(sf::launch(sf::col2im_vec8_kernel, dim3(grid_1d(total / 8)), dim3(256), 0, st, reinterpret_cast<const uint4*>(dcols),
+                                       ld_cols / 8, n, h, w, c / 8, kh, kw, reinterpret_cast<uint4*>(din)));
   return static_cast<int>(sf::launch(sf::col2im_kernel, dim3(grid_1d(total)), dim3(256), 0, st, dcols, ld_cols, n, h, w, c, kh, kw, din));
 }
 
@@ -355,7 +435,7 @@ template <int KH, int KW, int CIN>
 __global__ void __launch_bounds__(kConv1Threads)
 conv_first_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int cin_rt, int kh_rt, int kw_rt, int cout,
                         const __nv_bfloat16* __restrict__ g_pool, const __nv_bfloat16* __restrict__ pooled,
-                        const uint8_t* __restrict__ argmax, int act, float* __restrict__ dW, float* __restrict__ db) {
+                        const uint8_t* __restrict__ argmax, int act, float* __restrict__ dW, float* __restrict__ db, int stage) {
   extern __shared__ float conv1_smem[];
   TraceScope trace;
   pdl_launch_dependents();
@@ -378,17 +458,35 @@ conv_first_wgrad_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w
   float bacc = 0.f;
   pdl_wait();
   trace.mark();
+  // s_g / s_am: this image's dL/dz at the pooling winners (gradient x activation derivative) and the winner positions,
+  // staged with coalesced loads (three dependent global loads per pooled pixel were the kernel's critical path)
+  float* s_g = s_red + n_grp * (K + 1) * cout;
+  uint8_t* s_am = reinterpret_cast<uint8_t*>(s_g + (stage ? ph * pw * cout : 0));
   for (int img = blockIdx.x; img < n; img += gridDim.x) {
     __syncthreads();
     const __nv_bfloat16* xi = x + static_cast<size_t>(img) * h * w * cin;
     for (int i = tid; i < h * w * cin; i += kConv1Threads) s_x[i] = __bfloat162float(xi[i]);
+    if (stage) {
+      const size_t o0 = static_cast<size_t>(img) * ph * pw * cout;
+      for (int i = tid; i < ph * pw * cout; i += kConv1Threads) {
+        const float a = __bfloat162float(pooled[o0 + i]);
+        s_g[i] = __bfloat162float(g_pool[o0 + i]) * pool_dact(a, act);
+        s_am[i] = argmax[o0 + i];
+      }
+    }
     __syncthreads();
     for (int p = grp; p < ph * pw; p += n_grp) {
-      const size_t o = (static_cast<size_t>(img) * ph * pw + p) * cout + c;
-      const float a = __bfloat162float(pooled[o]);
-      const float g = __bfloat162float(g_pool[o]) * pool_dact(a, act);
+      float g;
+      int am;
+      if (stage) {
+        g = s_g[p * cout + c];
+        am = s_am[p * cout + c];
+      } else {
+        const size_t o = (static_cast<size_t>(img) * ph * pw + p) * cout + c;
+        g = __bfloat162float(g_pool[o]) * pool_dact(__bfloat162float(pooled[o]), act);
+        am = argmax[o];
+      }
       if (g == 0.f) continue;
-      const int am = argmax[o];
       const int py = p / pw, px = p - py * pw;
       const float* r = s_x + ((2 * py + (am >> 1)) * w + 2 * px + (am & 1)) * cin;
       bacc += g;
@@ -456,8 +554,12 @@ static int conv_first_wgrad_launch(const __nv_bfloat16* x, int n, int h, int w, 
                                    const __nv_bfloat16* pooled, const uint8_t* argmax, int act, float* dW, float* db, cudaStream_t st) {
   const int K = kh * kw * cin;
   const int n_grp = sf::kConv1Threads / cout;
-  const size_t smem = (static_cast<size_t>(h) * w * cin + static_cast<size_t>(n_grp) * (K + 1) * cout) * sizeof(float);
+  size_t smem = (static_cast<size_t>(h) * w * cin + static_cast<size_t>(n_grp) * (K + 1) * cout) * sizeof(float);
   if (smem > 96 * 1024) return -8;
+  const size_t pc = static_cast<size_t>((h - kh + 1) / 2) * ((w - kw + 1) / 2) * cout;
+  const size_t stage_bytes = pc * sizeof(float) + ((pc + 15) / 16) * 16;
+  const int stage = smem + stage_bytes <= 96 * 1024 ? 1 : 0;
+  if (stage) smem += stage_bytes;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(sf::conv_first_wgrad_kernel<KH, KW, CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
@@ -467,7 +569,7 @@ static int conv_first_wgrad_launch(const __nv_bfloat16* x, int n, int h, int w, 
   int grid = n < 148 * 2 ? n : 148 * 2;           // one (or a few) images per CTA; one atomic per gradient word and CTA
   if (grid < 1) grid = 1;
   return static_cast<int>(sf::launch(sf::conv_first_wgrad_kernel<KH, KW, CIN>, dim3(grid), dim3(sf::kConv1Threads), smem, st, x, n, h, w, cin, kh, kw,
-                                     cout, g_pool, pooled, argmax, act, dW, db));
+                                     cout, g_pool, pooled, argmax, act, dW, db, stage));
 }
 
 #define SF_CONV1_DISPATCH(FN, ...)                                             \

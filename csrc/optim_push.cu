@@ -264,7 +264,11 @@ __device__ __forceinline__ void tile_load_grad(const float* grad, int64_t e, int
     const float4 gv = *reinterpret_cast<const float4*>(grad + e);
     g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
   } else {
-    for (int j = 0; j < nv; ++j) g[j] = grad[e + j];
+    // compile-time indices only: a runtime-bounded loop here would index g[] dynamically and push the whole tile
+    // state (gradient, tuples, geometry) into local memory
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nv) g[j] = grad[e + j];
   }
 }
 
@@ -305,8 +309,13 @@ __device__ __forceinline__ void push_tile_load(const SfPushArgs& a, float* grad0
     }
     if (ZERO && T.nv[half] > 0 && !dry) {
       // the gradient is consumed: zero it for the next step's accumulating epilogues
-      if (T.vec) *reinterpret_cast<float4*>(grad0 + T.e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
-      else for (int j = 0; j < T.nv[half]; ++j) grad0[T.e[half] + j] = 0.f;
+      if (T.vec) {
+        *reinterpret_cast<float4*>(grad0 + T.e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < T.nv[half]) grad0[T.e[half] + j] = 0.f;
+      }
     }
   }
 }
@@ -358,8 +367,13 @@ __device__ __forceinline__ void push_tile_apply(const SfPushArgs& a, float* cons
 #pragma unroll
       for (int half = 0; half < HALVES; ++half) {
         if (T.nv[half] == 0) continue;
-        if (T.vec) *reinterpret_cast<float4*>(grads[k] + T.e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
-        else for (int j = 0; j < T.nv[half]; ++j) grads[k][T.e[half] + j] = 0.f;
+        if (T.vec) {
+          *reinterpret_cast<float4*>(grads[k] + T.e[half]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < T.nv[half]) grads[k][T.e[half] + j] = 0.f;
+        }
       }
   }
   if (tp != nullptr) tp[1] = gtime_ns() + static_cast<unsigned long long>(T.u[0][0].p == 12345.678f);      // optimizer math done (loads consumed)
