@@ -66,7 +66,8 @@ def reference_arm(args) -> int:
             why = "reference dependencies import but the TF-1.x graph API (tf.placeholder/tf.layers/tf.Session) is required"
     except Exception as exc:  # pragma: no cover
         why = f"{type(exc).__name__}: {exc}"
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:        # under torchrun every rank runs this: ONE line
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 
