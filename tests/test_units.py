@@ -779,3 +779,119 @@ def test_save_tensorflow_model_roundtrip(tmp_path):
     x = np.random.default_rng(0).random((5, 10), dtype=np.float32)
     np.testing.assert_allclose(run_inference(back.getOrDefault(back.modelJson), w2, x, "x:0", "outer/Sigmoid:0"),
                                run_inference(graph, w, x, "x:0", "outer/Sigmoid:0"), rtol=1e-6)
+
+
+def test_sharded_two_slot_seqlock_protocol_model():
+    """Executable model of the sharded master's lock-mode publish (csrc/optim_push.cu: applier_kernel / sync_pull_kernel,
+    DESIGN.md 2.9): per shard `begin` = passes started, `end` = applier-CTA completions, pass v lands in publish slot v & 1.
+    A pull never waits: it copies the newest COMPLETE pass (begin if end == begin * G, else begin - 1), re-reads `begin`
+    after the copy and retries when the slot it copied may have been rewritten (begin - version > 1); with several copy
+    CTAs the shard's leader picks the version for all of them and every CTA must come out clean.  Random interleavings at
+    single-memory-operation granularity: an accepted snapshot is never torn, versions never go back, a pull is never more
+    than one pass behind the state at its start, and the writer never depends on a reader."""
+    import random
+
+    G, T, CPS = 3, 6, 2                      # applier CTAs, tiles of the shard, copy CTAs of a pull
+    for seed in range(200):
+        rng = random.Random(seed)
+        mem = {"begin": 0, "end": 0, "slots": [[0] * T, [0] * T]}
+        accepted, tasks = [], []
+        stats = {"retries": 0}
+
+        def applier_cta(v, c):
+            for tile in range(c, T, G):
+                mem["slots"][v & 1][tile] = v           # publish store of one tile
+                yield
+            mem["end"] += 1                             # after this CTA's fence: completion counted in every replica
+            yield
+
+        def applier_leader(n_pass):
+            v = 0
+            while v < n_pass:
+                while mem["end"] != v * G:              # every CTA of the previous pass fenced its stores
+                    yield
+                v += 1
+                mem["begin"] = v                        # stamped BEFORE the first store of the pass can land
+                yield
+                for c in range(G):
+                    tasks.append(applier_cta(v, c))
+
+        def pull(k, n_pull):
+            last = 0
+            for _ in range(n_pull):
+                while True:
+                    start_begin = mem["begin"]
+                    b = mem["begin"]
+                    yield
+                    e = mem["end"]
+                    yield
+                    ver = b if e == b * G else b - 1
+                    snap, clean = [None] * T, True
+                    for part in range(CPS):             # the copy CTAs run one after the other here; each re-checks itself
+                        for tile in range(part, T, CPS):
+                            snap[tile] = mem["slots"][ver & 1][tile]
+                            yield
+                        b2 = mem["begin"]
+                        clean = clean and (b2 - ver <= 1)
+                        yield
+                    if clean:
+                        break
+                    stats["retries"] += 1
+                assert min(snap) == max(snap) == ver, ("torn snapshot accepted", seed, k, ver, snap)
+                assert ver >= last, ("version went back", seed, k, last, ver)
+                assert ver >= start_begin - 1, ("stale snapshot", seed, k, start_begin, ver)
+                last = ver
+                accepted.append((k, ver))
+                for _ in range(rng.randrange(0, 12)):   # the worker's step between two pulls
+                    yield
+
+        tasks += [applier_leader(12)] + [pull(k, 10) for k in range(3)]
+        steps = 0
+        while tasks:
+            i = rng.randrange(len(tasks))
+            try:
+                next(tasks[i])
+            except StopIteration:
+                tasks.pop(i)
+            steps += 1
+            assert steps < 200000, "model did not terminate (a pull starved?)"
+        assert mem["begin"] == 12 and mem["end"] == 12 * G               # the writer finished all passes regardless of readers
+        assert len(accepted) == 30
+
+
+def test_symmetric_heap_fd_rendezvous_and_shard_bounds(tmp_path):
+    """Host-side plumbing of the sharded master that needs no GPU: (a) physical-memory handles travel between ranks as file
+    descriptors over abstract Unix sockets (parallel/symm.py: _FdServer / _fetch_fd) - checked with an ordinary file
+    descriptor; (b) shard_bounds splits the push tiles into contiguous, balanced ranges, and the owner rule the wgrad
+    epilogue / post kernel evaluate (owner = #{r >= 1 : tile >= bounds[r]}, csrc/gemm_sm100.cu) inverts it."""
+    import uuid
+
+    from sparkflow_b200.parallel.sharded import shard_bounds
+    from sparkflow_b200.parallel.symm import _FdServer, _fetch_fd
+
+    path = tmp_path / "payload.bin"
+    path.write_bytes(b"physical handle stand-in")
+    fd = os.open(str(path), os.O_RDONLY)
+    name = "sparkflow_b200-test-" + uuid.uuid4().hex
+    srv = _FdServer(name)
+    try:
+        srv.offer("seg", fd)
+        got = _fetch_fd(name, "seg", timeout=5.0)
+        assert got != fd and os.fstat(got).st_ino == os.fstat(fd).st_ino          # a NEW descriptor of the same open file
+        assert os.pread(got, 64, 0) == b"physical handle stand-in"
+        os.close(got)
+        with pytest.raises(TimeoutError):
+            _fetch_fd(name, "no-such-key", timeout=0.3)
+    finally:
+        srv.close()
+        os.close(fd)
+
+    for n_tiles in (1, 7, 143, 4340, 34746):
+        for n in (1, 2, 3, 8):
+            b = shard_bounds(n_tiles, n)
+            assert b[0] == 0 and b[-1] == n_tiles and len(b) == n + 1
+            sizes = [b[r + 1] - b[r] for r in range(n)]
+            assert all(s >= 0 for s in sizes) and max(sizes) - min(sizes) <= 1
+            for tile in {0, n_tiles // 3, n_tiles // 2, n_tiles - 1}:
+                owner = sum(1 for r in range(1, n) if tile >= b[r])
+                assert b[owner] <= tile < b[owner + 1] or sizes[owner] == 0
