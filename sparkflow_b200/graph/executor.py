@@ -480,6 +480,229 @@ def _one_hot(n, ins, c):
 
 
 # ---------------------------------------------------------------------------
+# ops beyond what the reference's own examples need: real TF-1.x graphs (embeddings, tf.cond around dropout / batch-norm,
+# fused batch-norm, transposed / depthwise convolutions, ...) train on the interpreter engine through these
+# ---------------------------------------------------------------------------
+class _Dead:
+    """Value on the untaken side of a tf.cond (`Switch`): every op that consumes it produces it again; `Merge` forwards
+    whichever input is alive."""
+
+    def __repr__(self):
+        return "<dead tensor>"
+
+
+DEAD = _Dead()
+
+
+class _DeadOutputs:
+    def __getitem__(self, i):
+        return DEAD
+
+
+@op("Switch", "RefSwitch")
+def _switch(n, ins, c):
+    data, pred = ins
+    take_true = bool(_to_np(pred).reshape(-1)[0])
+    return (DEAD, data) if take_true else (data, DEAD)
+
+
+@op("Merge", "RefMerge")
+def _merge(n, ins, c):
+    for i, v in enumerate(ins):
+        if v is not DEAD:
+            return (v, np.asarray(i, dtype=np.int64))
+    return (DEAD, DEAD)
+
+
+@op("GatherV2", "Gather", "ResourceGather")
+def _gather(n, ins, c):
+    params, idx = ins[0], ins[1]
+    axis = int(_to_np(ins[2])) if len(ins) > 2 else 0
+    if _is_np(params) and _is_np(idx):
+        return (np.take(np.asarray(params), np.asarray(idx), axis=axis),)
+    p = c.t(params)
+    i = c.t(idx, torch.int64)
+    out = torch.index_select(p, axis % p.dim(), i.reshape(-1))
+    shape = list(p.shape[:axis % p.dim()]) + list(i.shape) + list(p.shape[axis % p.dim() + 1:])
+    return (out.reshape(shape),)
+
+
+@op("Split")
+def _split(n, ins, c):
+    axis, x = int(_to_np(ins[0])), ins[1]
+    return tuple(torch.chunk(c.t(x), int(n.attrs.get("num_split", 1)), dim=axis))
+
+
+@op("SplitV")
+def _splitv(n, ins, c):
+    x, sizes, axis = c.t(ins[0]), [int(v) for v in _to_np(ins[1]).reshape(-1)], int(_to_np(ins[2]))
+    if -1 in sizes:
+        sizes[sizes.index(-1)] = x.shape[axis] - (sum(sizes) + 1)
+    return tuple(torch.split(x, sizes, dim=axis))
+
+
+@op("Unpack")
+def _unpack(n, ins, c):
+    return tuple(torch.unbind(c.t(ins[0]), dim=int(n.attrs.get("axis", 0))))
+
+
+@op("Pad", "PadV2")
+def _pad(n, ins, c):
+    x = c.t(ins[0])
+    pads = _to_np(ins[1]).reshape(-1, 2).astype(np.int64)
+    flat: List[int] = []
+    for lo, hi in pads[::-1]:                      # torch pads the LAST dimension first
+        flat += [int(lo), int(hi)]
+    value = float(_to_np(ins[2])) if n.op == "PadV2" and len(ins) > 2 else 0.0
+    return (F.pad(x, flat, value=value),)
+
+
+@op("MirrorPad")
+def _mirror_pad(n, ins, c):
+    x = c.t(ins[0])
+    pads = _to_np(ins[1]).reshape(-1, 2).astype(np.int64)
+    mode = n.attrs.get("mode", "REFLECT")
+    mode = (mode.decode() if isinstance(mode, bytes) else str(mode)).upper()
+    for d, (lo, hi) in enumerate(pads):
+        if lo or hi:                               # one gather per padded dimension; numpy supplies the index pattern
+            idx = np.pad(np.arange(x.shape[d]), (int(lo), int(hi)), mode="reflect" if mode == "REFLECT" else "symmetric")
+            x = torch.index_select(x, d, torch.as_tensor(idx, device=x.device))
+    return (x,)
+
+
+@op("BatchMatMul", "BatchMatMulV2")
+def _batch_matmul(n, ins, c):
+    a, b = c.t(ins[0]), c.t(ins[1])
+    if n.attrs.get("adj_x"):
+        a = a.transpose(-1, -2)
+    if n.attrs.get("adj_y"):
+        b = b.transpose(-1, -2)
+    return (a @ b,)
+
+
+@op("FusedBatchNorm", "FusedBatchNormV2", "FusedBatchNormV3")
+def _fused_batch_norm(n, ins, c):
+    x, scale, offset, mean, var = (c.t(v) for v in ins[:5])
+    if n.attrs.get("data_format", "NHWC") != "NHWC":
+        raise UnsupportedOp("FusedBatchNorm data_format NCHW")
+    eps = float(n.attrs.get("epsilon", 1e-3))
+    if n.attrs.get("is_training", True):
+        dims = list(range(x.dim() - 1))
+        bm = x.mean(dim=dims)
+        bv = x.var(dim=dims, unbiased=False)
+        cnt = x.numel() // x.shape[-1]
+        y = (x - bm) * torch.rsqrt(bv + eps) * scale + offset
+        return (y, bm, bv * (cnt / max(cnt - 1, 1)), bm, bv, bv)
+    y = (x - mean) * torch.rsqrt(var + eps) * scale + offset
+    return (y, mean, var, mean, var, var)
+
+
+OPS["Erf"] = _unary(torch.erf)
+OPS["Sin"] = _unary(torch.sin)
+OPS["Cos"] = _unary(torch.cos)
+OPS["Round"] = OPS["Rint"] = _unary(torch.round, np.round)
+OPS["IsNan"] = _unary(torch.isnan)
+OPS["FloorMod"] = _binary(torch.remainder, np.mod)
+OPS["LogicalOr"] = lambda n, ins, c: (torch.logical_or(c.t(ins[0], torch.bool), c.t(ins[1], torch.bool)),)
+
+
+@op("ClipByValue")
+def _clip(n, ins, c):
+    x, lo, hi = (c.t(v) for v in ins)
+    return (torch.minimum(torch.maximum(x, lo), hi),)
+
+
+@op("Cumsum")
+def _cumsum(n, ins, c):
+    x, axis = c.t(ins[0]), int(_to_np(ins[1]))
+    if n.attrs.get("reverse"):
+        x = x.flip(axis)
+    y = torch.cumsum(x, dim=axis)
+    if n.attrs.get("exclusive"):
+        y = y - x
+    return (y.flip(axis) if n.attrs.get("reverse") else y,)
+
+
+def _bool_reduction(fn):
+    def run(n, ins, c):
+        x = c.t(ins[0], torch.bool)
+        axes = [int(a) for a in _to_np(ins[1]).reshape(-1)]
+        keep = bool(n.attrs.get("keep_dims", False))
+        for a in sorted((a % max(x.dim(), 1) for a in axes), reverse=True) if x.dim() else []:
+            x = fn(x, dim=a, keepdim=keep)
+        return (x,)
+    return run
+
+
+OPS["Any"] = _bool_reduction(torch.any)
+OPS["All"] = _bool_reduction(torch.all)
+
+
+@op("TopKV2", "TopK")
+def _topk(n, ins, c):
+    k = int(_to_np(ins[1])) if len(ins) > 1 else int(n.attrs.get("k", 1))
+    v, i = torch.topk(c.t(ins[0]), k, dim=-1, sorted=True)
+    return (v, i)
+
+
+@op("ReverseV2")
+def _reverse(n, ins, c):
+    return (c.t(ins[0]).flip([int(a) for a in _to_np(ins[1]).reshape(-1)]),)
+
+
+@op("Conv2DBackpropInput")
+def _conv2d_transpose(n, ins, c):
+    """Forward use = tf.nn.conv2d_transpose: inputs (output_shape, filter HWOI-as-HWIO-of-the-forward-conv, value)."""
+    out_shape, w, y = [int(v) for v in _to_np(ins[0]).reshape(-1)], c.t(ins[1]), c.t(ins[2])
+    if n.attrs.get("data_format", "NHWC") != "NHWC":
+        raise UnsupportedOp("Conv2DBackpropInput data_format NCHW")
+    st = n.attrs.get("strides", [1, 1, 1, 1])
+    kh, kw = w.shape[0], w.shape[1]
+    pad_h = pad_w = (0, 0)
+    if n.attrs.get("padding", "VALID") == "SAME":
+        pad_h, pad_w = _same_pad(out_shape[1], kh, st[1]), _same_pad(out_shape[2], kw, st[2])
+    yt = y.permute(0, 3, 1, 2)
+    wt = w.permute(3, 2, 0, 1)                     # [C_of_value, C_out, kh, kw] is what conv_transpose2d expects
+    full = F.conv_transpose2d(yt, wt, stride=(st[1], st[2]))
+    # crop the padding of the forward convolution / extend to the requested output size
+    need_h, need_w = out_shape[1] + pad_h[0] + pad_h[1], out_shape[2] + pad_w[0] + pad_w[1]
+    if full.shape[2] < need_h or full.shape[3] < need_w:
+        full = F.pad(full, (0, max(need_w - full.shape[3], 0), 0, max(need_h - full.shape[2], 0)))
+    full = full[:, :, pad_h[0]:pad_h[0] + out_shape[1], pad_w[0]:pad_w[0] + out_shape[2]]
+    return (full.permute(0, 2, 3, 1),)
+
+
+@op("DepthwiseConv2dNative")
+def _depthwise(n, ins, c):
+    x, w = c.t(ins[0]), c.t(ins[1])                 # NHWC, [kh, kw, C, multiplier]
+    if n.attrs.get("data_format", "NHWC") != "NHWC":
+        raise UnsupportedOp("DepthwiseConv2dNative data_format NCHW")
+    st = n.attrs.get("strides", [1, 1, 1, 1])
+    dil = n.attrs.get("dilations", [1, 1, 1, 1])
+    kh, kw, ch, mult = w.shape
+    xt = x.permute(0, 3, 1, 2)
+    wt = w.permute(2, 3, 0, 1).reshape(ch * mult, 1, kh, kw)
+    if n.attrs.get("padding", "VALID") == "SAME":
+        ph = _same_pad(xt.shape[2], (kh - 1) * dil[1] + 1, st[1])
+        pw = _same_pad(xt.shape[3], (kw - 1) * dil[2] + 1, st[2])
+        xt = F.pad(xt, (pw[0], pw[1], ph[0], ph[1]))
+    y = F.conv2d(xt, wt, stride=(st[1], st[2]), dilation=(dil[1], dil[2]), groups=ch)
+    return (y.permute(0, 2, 3, 1),)
+
+
+@op("ResizeNearestNeighbor")
+def _resize_nearest(n, ins, c):
+    x = c.t(ins[0])
+    oh, ow = (int(v) for v in _to_np(ins[1]).reshape(-1))
+    if n.attrs.get("align_corners") or n.attrs.get("half_pixel_centers"):
+        raise UnsupportedOp("ResizeNearestNeighbor with align_corners / half_pixel_centers")
+    ih, iw = x.shape[1], x.shape[2]
+    ys = torch.clamp((torch.arange(oh, device=x.device) * (ih / oh)).floor().long(), max=ih - 1)
+    xs = torch.clamp((torch.arange(ow, device=x.device) * (iw / ow)).floor().long(), max=iw - 1)
+    return (x[:, ys][:, :, xs],)
+
+
+# ---------------------------------------------------------------------------
 # random ops (initializers, dropout)
 # ---------------------------------------------------------------------------
 def _rand_shape(ins):
@@ -597,6 +820,9 @@ class GraphProgram:
                         stack.append((src, False))
                 continue
             ins = [fed[(s, i)] if (s, i) in fed else cache[s][i] for s, i in node.inputs]
+            if node.op not in ("Merge", "RefMerge") and any(v is DEAD for v in ins):
+                cache[name] = _DeadOutputs()          # untaken branch of a tf.cond
+                continue
             fn = OPS.get(node.op)
             if fn is None:
                 raise UnsupportedOp(f"graph op '{node.op}' (node '{node.name}') is not supported by sparkflow_b200; "

@@ -23,6 +23,8 @@ from .ops import (abs, add, argmax, cast, concat, constant, constant_initializer
 from .ops import (ceil, clip_by_value, equal, floor, greater, greater_equal, less, less_equal, log1p, logical_and,  # noqa: F401
                   logical_not, not_equal, ones_like, reciprocal, reduce_min, reduce_prod, rsqrt, sign, stack, tile, where,
                   zeros_like)
+from .ops import (cond, cos, cumsum, erf, floormod, gather, logical_or, one_hot, pad, reduce_all, reduce_any, round, sin, split,  # noqa: A004,F401
+                  unstack)
 from .session import InteractiveSession, Session, get_default_session  # noqa: F401
 
 __version__ = "1.10.0-sparkflow_b200"
@@ -66,6 +68,7 @@ mul = multiply
 neg = negative
 to_float = lambda x, name="ToFloat": cast(x, float32, name)  # noqa: E731
 arg_max = argmax
+mod = floormod
 
 nn = _types.SimpleNamespace(
     relu=_ops.relu, sigmoid=_ops.sigmoid, tanh=_ops.tanh, softmax=_ops.softmax, softplus=_ops.softplus, elu=_ops.elu,
@@ -74,17 +77,20 @@ nn = _types.SimpleNamespace(
     softmax_cross_entropy_with_logits_v2=_ops.softmax_cross_entropy_with_logits,
     sigmoid_cross_entropy_with_logits=_ops.sigmoid_cross_entropy_with_logits,
     relu6=_ops.relu6, selu=_ops.selu, softsign=_ops.softsign, log_softmax=_ops.log_softmax, l2_loss=_ops.l2_loss,
-    l2_normalize=_ops.l2_normalize,
+    l2_normalize=_ops.l2_normalize, embedding_lookup=_ops.embedding_lookup,
+    sparse_softmax_cross_entropy_with_logits=_ops.sparse_softmax_cross_entropy_with_logits, conv2d_transpose=_ops.conv2d_transpose,
+    depthwise_conv2d=_ops.depthwise_conv2d, top_k=_ops.top_k,
 )
 layers = _types.SimpleNamespace(
     dense=_ops.dense, conv2d=_ops.conv2d_layer, max_pooling2d=_ops.max_pooling2d, average_pooling2d=_ops.average_pooling2d,
     flatten=_ops.flatten, dropout=_ops.dropout_layer, batch_normalization=_ops.batch_normalization,
+    conv2d_transpose=_ops.conv2d_transpose_layer,
 )
 losses = _types.SimpleNamespace(
     softmax_cross_entropy=_ops.softmax_cross_entropy, mean_squared_error=_ops.mean_squared_error,
     sigmoid_cross_entropy=_ops.sigmoid_cross_entropy, absolute_difference=_ops.absolute_difference,
     add_loss=_ops.add_loss, get_losses=_ops.get_losses, log_loss=_ops.log_loss, hinge_loss=_ops.hinge_loss,
-    huber_loss=_ops.huber_loss,
+    huber_loss=_ops.huber_loss, sparse_softmax_cross_entropy=_ops.sparse_softmax_cross_entropy,
 )
 initializers = _types.SimpleNamespace(
     glorot_uniform=glorot_uniform_initializer, glorot_normal=glorot_normal_initializer, zeros=zeros_initializer,

@@ -208,6 +208,32 @@ class Tensor:
         from . import ops
 
         return ops.matmul(self, o)
+
+    def __getitem__(self, key):
+        from . import ops
+
+        return ops.strided_slice_from_key(self, key)
+
+    def __pow__(self, o): return self._bin(o, "Pow")
+    def __gt__(self, o):
+        from . import ops
+
+        return ops.greater(self, o)
+
+    def __ge__(self, o):
+        from . import ops
+
+        return ops.greater_equal(self, o)
+
+    def __lt__(self, o):
+        from . import ops
+
+        return ops.less(self, o)
+
+    def __le__(self, o):
+        from . import ops
+
+        return ops.less_equal(self, o)
     __hash__ = object.__hash__
 
 

@@ -928,3 +928,268 @@ def batch_normalization(inputs, axis=-1, momentum=0.99, epsilon=1e-3, center=Tru
         if beta is not None:
             out = binary("Add", out, per_channel(beta.value()), name="batchnorm/add_1")
         return out
+
+
+# ---------------------------------------------------------------------------
+# more of the TF-1.x surface (embeddings, sparse labels, splits / pads, transposed and depthwise convolutions, tf.cond)
+# ---------------------------------------------------------------------------
+def _const_i32(value, name):
+    return constant(np.asarray(value, np.int32), dtype=core.int32, name=name)
+
+
+def one_hot(indices, depth, on_value=1.0, off_value=0.0, axis=-1, dtype=core.float32, name=None) -> Tensor:
+    idx = convert_to_tensor(indices)
+    dt = as_dtype(dtype)
+    d = _const_i32(depth, "depth")
+    on, off = constant(on_value, dtype=dt, name="on_value"), constant(off_value, dtype=dt, name="off_value")
+    sh = None if idx._shape is None else tuple(idx._shape) + (int(depth),)
+    return _g().add_node("OneHot", name or "one_hot", [idx, d, on, off], {"T": attr_type(dt), "TI": attr_type(idx.dtype), "axis": attr_i(axis)},
+                         [dt], [sh]).outputs[0]
+
+
+def gather(params, indices, validate_indices=None, name=None, axis=0) -> Tensor:
+    p, idx = convert_to_tensor(params), convert_to_tensor(indices)
+    ax = _const_i32(axis, "axis")
+    sh = None
+    if p._shape is not None and idx._shape is not None:
+        a = axis % len(p._shape)
+        sh = tuple(p._shape[:a]) + tuple(idx._shape) + tuple(p._shape[a + 1:])
+    return _g().add_node("GatherV2", name or "GatherV2", [p, idx, ax],
+                         {"Tparams": attr_type(p.dtype), "Tindices": attr_type(idx.dtype), "Taxis": attr_type(core.int32)}, [p.dtype], [sh]).outputs[0]
+
+
+def embedding_lookup(params, ids, partition_strategy="mod", name=None, validate_indices=True, max_norm=None) -> Tensor:
+    if isinstance(params, (list, tuple)):
+        if len(params) != 1:
+            raise NotImplementedError("embedding_lookup over a sharded list of tables")
+        params = params[0]
+    return gather(params, ids, name=name or "embedding_lookup")
+
+
+def split(value, num_or_size_splits, axis=0, num=None, name="split"):
+    x = convert_to_tensor(value)
+    g = _g()
+    dim = None if x._shape is None else x._shape[axis % len(x._shape)]
+
+    def oshape(part):
+        if x._shape is None:
+            return None
+        lst = list(x._shape)
+        lst[axis % len(lst)] = part
+        return tuple(lst)
+
+    if isinstance(num_or_size_splits, int):
+        k = num_or_size_splits
+        ax = _const_i32(axis, "split_dim")
+        part = None if dim is None else dim // k
+        op = g.add_node("Split", name, [ax, x], {"T": attr_type(x.dtype), "num_split": attr_i(k)}, [x.dtype] * k, [oshape(part)] * k)
+        return list(op.outputs)
+    sizes = [int(s) for s in num_or_size_splits]
+    sz, ax = _const_i32(sizes, "size_splits"), _const_i32(axis, "split_dim")
+    op = g.add_node("SplitV", name, [x, sz, ax], {"T": attr_type(x.dtype), "Tlen": attr_type(core.int32), "num_split": attr_i(len(sizes))},
+                    [x.dtype] * len(sizes), [oshape(None if s < 0 else s) for s in sizes])
+    return list(op.outputs)
+
+
+def unstack(value, num=None, axis=0, name="unstack"):
+    x = convert_to_tensor(value)
+    if num is None:
+        if x._shape is None or x._shape[axis % len(x._shape)] is None:
+            raise ValueError("unstack needs a static size along `axis` (or `num`)")
+        num = x._shape[axis % len(x._shape)]
+    sh = None if x._shape is None else tuple(d for i, d in enumerate(x._shape) if i != axis % len(x._shape))
+    op = _g().add_node("Unpack", name, [x], {"T": attr_type(x.dtype), "num": attr_i(num), "axis": attr_i(axis)}, [x.dtype] * num, [sh] * num)
+    return list(op.outputs)
+
+
+def pad(tensor, paddings, mode="CONSTANT", name=None, constant_values=0) -> Tensor:
+    x = convert_to_tensor(tensor)
+    pads = np.asarray(paddings, np.int32).reshape(-1, 2)
+    p = _const_i32(pads, "paddings")
+    sh = None if x._shape is None else tuple(None if d is None else d + int(lo) + int(hi) for d, (lo, hi) in zip(x._shape, pads))
+    mode = mode.upper()
+    if mode == "CONSTANT":
+        if constant_values:
+            cv = constant(constant_values, dtype=x.dtype, name="constant_values")
+            return _g().add_node("PadV2", name or "PadV2", [x, p, cv], {"T": attr_type(x.dtype), "Tpaddings": attr_type(core.int32)}, [x.dtype], [sh]).outputs[0]
+        return _g().add_node("Pad", name or "Pad", [x, p], {"T": attr_type(x.dtype), "Tpaddings": attr_type(core.int32)}, [x.dtype], [sh]).outputs[0]
+    return _g().add_node("MirrorPad", name or "MirrorPad", [x, p], {"T": attr_type(x.dtype), "Tpaddings": attr_type(core.int32), "mode": attr_s(mode)},
+                         [x.dtype], [sh]).outputs[0]
+
+
+def sparse_softmax_cross_entropy_with_logits(labels=None, logits=None, name=None, _sentinel=None):
+    logits_t, labels_t = convert_to_tensor(logits), convert_to_tensor(labels)
+    op = _g().add_node("SparseSoftmaxCrossEntropyWithLogits", name or "SparseSoftmaxCrossEntropyWithLogits", [logits_t, labels_t],
+                       {"T": attr_type(logits_t.dtype), "Tlabels": attr_type(labels_t.dtype)}, [logits_t.dtype, logits_t.dtype],
+                       [None if logits_t._shape is None else (logits_t._shape[0],), logits_t._shape])
+    return op.outputs[0]
+
+
+def sparse_softmax_cross_entropy(labels, logits, weights=1.0, scope=None, loss_collection=GraphKeys.LOSSES, reduction=None):
+    with _g().name_scope(scope or "sparse_softmax_cross_entropy_loss"):
+        per = sparse_softmax_cross_entropy_with_logits(labels=labels, logits=logits, name="xentropy")
+        if not (isinstance(weights, (int, float)) and weights == 1.0):
+            per = binary("Mul", per, weights, name="Mul")
+        return _finish_loss(per, loss_collection)
+
+
+def conv2d_transpose(value, filter, output_shape, strides, padding="SAME", data_format="NHWC", name=None) -> Tensor:  # noqa: A002
+    """``tf.nn.conv2d_transpose``: filter is [kh, kw, out_channels, in_channels]; emitted as TF does, as the input-gradient
+    op of the forward convolution."""
+    y, w = convert_to_tensor(value), convert_to_tensor(filter)
+    osh = [int(d) if d is not None else -1 for d in output_shape] if not isinstance(output_shape, (Tensor, Variable)) else None
+    sizes = convert_to_tensor(output_shape) if osh is None else _const_i32(osh, "output_shape")
+    sh = None if osh is None else tuple(None if d < 0 else d for d in osh)
+    return _g().add_node("Conv2DBackpropInput", name or "conv2d_transpose", [sizes, w, y],
+                         {"T": attr_type(y.dtype), "strides": attr_ilist(strides), "padding": attr_s(padding.upper()), "data_format": attr_s(data_format),
+                          "dilations": attr_ilist([1, 1, 1, 1]), "use_cudnn_on_gpu": attr_b(True)}, [y.dtype], [sh]).outputs[0]
+
+
+def conv2d_transpose_layer(inputs, filters, kernel_size, strides=(1, 1), padding="valid", activation=None, use_bias=True,
+                           kernel_initializer=None, bias_initializer=None, name=None, trainable=True, **_unused) -> Tensor:
+    """``tf.layers.conv2d_transpose`` (NHWC, static spatial sizes)."""
+    x = convert_to_tensor(inputs)
+    kh, kw = _pair(kernel_size)
+    sh, sw = _pair(strides)
+    n, h, w, cin = x._shape
+    if h is None or w is None:
+        raise ValueError("conv2d_transpose needs static height / width")
+    padding = padding.upper()
+    oh = h * sh if padding == "SAME" else h * sh + max(kh - sh, 0)
+    ow = w * sw if padding == "SAME" else w * sw + max(kw - sw, 0)
+    g = _g()
+    with g.name_scope(name or "conv2d_transpose") as scope:
+        kernel = get_variable(scope + "kernel", [kh, kw, filters, cin], x.dtype, kernel_initializer or glorot_uniform_initializer(), trainable)
+        if n is None:
+            bs = g.add_node("StridedSlice", "strided_slice", [shape(x), _const_i32([0], "ss/b"), _const_i32([1], "ss/e"), _const_i32([1], "ss/s")],
+                            {"T": attr_type(core.int32), "Index": attr_type(core.int32), "shrink_axis_mask": attr_i(1), "begin_mask": attr_i(0),
+                             "end_mask": attr_i(0), "ellipsis_mask": attr_i(0), "new_axis_mask": attr_i(0)}, [core.int32], [()]).outputs[0]
+            sizes = stack([bs, _const_i32(oh, "oh"), _const_i32(ow, "ow"), _const_i32(filters, "oc")], name="output_shape")
+            y = g.add_node("Conv2DBackpropInput", "conv2d_transpose", [sizes, convert_to_tensor(kernel), x],
+                           {"T": attr_type(x.dtype), "strides": attr_ilist([1, sh, sw, 1]), "padding": attr_s(padding), "data_format": attr_s("NHWC"),
+                            "dilations": attr_ilist([1, 1, 1, 1]), "use_cudnn_on_gpu": attr_b(True)}, [x.dtype], [(None, oh, ow, filters)]).outputs[0]
+        else:
+            y = conv2d_transpose(x, kernel, [n, oh, ow, filters], [1, sh, sw, 1], padding)
+        if use_bias:
+            bias = get_variable(scope + "bias", [filters], x.dtype, bias_initializer or zeros_initializer(), trainable)
+            y = bias_add(y, bias)
+        return _apply_activation(activation, y)
+
+
+def depthwise_conv2d(input, filter, strides, padding, rate=None, name=None, data_format="NHWC") -> Tensor:  # noqa: A002
+    x, w = convert_to_tensor(input), convert_to_tensor(filter)
+    padding = padding.upper()
+    kh, kw, ch, mult = w._shape
+    n, h, wd, _ = x._shape if x._shape is not None else (None,) * 4
+    dil = [1, 1, 1, 1] if rate is None else [1, rate[0], rate[1], 1]
+    oshape = (n, _conv_out(h, (kh - 1) * dil[1] + 1, strides[1], padding), _conv_out(wd, (kw - 1) * dil[2] + 1, strides[2], padding), ch * mult)
+    return _g().add_node("DepthwiseConv2dNative", name or "depthwise", [x, w],
+                         {"T": attr_type(x.dtype), "strides": attr_ilist(strides), "padding": attr_s(padding), "data_format": attr_s(data_format),
+                          "dilations": attr_ilist(dil)}, [x.dtype], [oshape]).outputs[0]
+
+
+def erf(x, name=None): return unary("Erf", x, name)
+def sin(x, name=None): return unary("Sin", x, name)
+def cos(x, name=None): return unary("Cos", x, name)
+def round(x, name=None): return unary("Round", x, name)  # noqa: A001
+def floormod(a, b, name=None): return binary("FloorMod", a, b, name)
+
+
+def logical_or(a, b, name=None):
+    a, b = convert_to_tensor(a, dtype=core.bool_), convert_to_tensor(b, dtype=core.bool_)
+    return _g().add_node("LogicalOr", name or "LogicalOr", [a, b], {}, [core.bool_], [_bshape(a._shape, b._shape)]).outputs[0]
+
+
+def cumsum(x, axis=0, exclusive=False, reverse=False, name=None) -> Tensor:
+    x = convert_to_tensor(x)
+    ax = _const_i32(axis, "axis")
+    return _g().add_node("Cumsum", name or "Cumsum", [x, ax], {"T": attr_type(x.dtype), "Tidx": attr_type(core.int32), "exclusive": attr_b(exclusive),
+                                                            "reverse": attr_b(reverse)}, [x.dtype], [x._shape]).outputs[0]
+
+
+def _bool_reduce(op, x, axis, keepdims, name):
+    x = convert_to_tensor(x, dtype=core.bool_)
+    rank = len(x._shape)
+    axes = list(range(rank)) if axis is None else ([axis] if isinstance(axis, int) else list(axis))
+    ax = _const_i32(axes, "reduction_indices")
+    norm = [a % rank for a in axes]
+    sh = tuple((1 if i in norm else d) for i, d in enumerate(x._shape) if keepdims or i not in norm)
+    return _g().add_node(op, name or op, [x, ax], {"Tidx": attr_type(core.int32), "keep_dims": attr_b(bool(keepdims))}, [core.bool_], [sh]).outputs[0]
+
+
+def reduce_any(x, axis=None, keepdims=False, name=None, keep_dims=None): return _bool_reduce("Any", x, axis, keepdims or bool(keep_dims), name)
+def reduce_all(x, axis=None, keepdims=False, name=None, keep_dims=None): return _bool_reduce("All", x, axis, keepdims or bool(keep_dims), name)
+
+
+def top_k(input, k=1, sorted=True, name=None):  # noqa: A002
+    x = convert_to_tensor(input)
+    kk = _const_i32(k, "k")
+    sh = None if x._shape is None else tuple(x._shape[:-1]) + (int(k),)
+    op = _g().add_node("TopKV2", name or "TopKV2", [x, kk], {"T": attr_type(x.dtype), "sorted": attr_b(sorted)}, [x.dtype, core.int32], [sh, sh])
+    return op.outputs[0], op.outputs[1]
+
+
+def cond(pred, true_fn=None, false_fn=None, strict=False, name=None, fn1=None, fn2=None):
+    """``tf.cond``.  A python bool picks the branch at graph-construction time; a tensor predicate emits the
+    ``Switch`` / ``Merge`` pair TF-1.x graphs carry (both branches are built; the engine evaluates the live one)."""
+    true_fn, false_fn = true_fn or fn1, false_fn or fn2
+    if isinstance(pred, (bool, np.bool_)):
+        return true_fn() if pred else false_fn()
+    p = convert_to_tensor(pred, dtype=core.bool_)
+    g = _g()
+    with g.name_scope(name or "cond"):
+        t, f = true_fn(), false_fn()
+        single = not isinstance(t, (list, tuple))
+        ts, fs = ([t], [f]) if single else (list(t), list(f))
+        outs = []
+        for a, b in zip(ts, fs):
+            a, b = convert_to_tensor(a), convert_to_tensor(b)
+            sa = g.add_node("Switch", "Switch_t", [a, p], {"T": attr_type(a.dtype)}, [a.dtype, a.dtype], [a._shape, a._shape])
+            sb = g.add_node("Switch", "Switch_f", [b, p], {"T": attr_type(b.dtype)}, [b.dtype, b.dtype], [b._shape, b._shape])
+            m = g.add_node("Merge", "Merge", [sb.outputs[0], sa.outputs[1]], {"T": attr_type(a.dtype), "N": attr_i(2)}, [a.dtype, core.int32],
+                           [a._shape if a._shape == b._shape else None, ()])
+            outs.append(m.outputs[0])
+        return outs[0] if single else outs
+
+
+def strided_slice_from_key(x: Tensor, key) -> Tensor:
+    """``tensor[...]`` with ints and slices (no Ellipsis / newaxis): emits the ``StridedSlice`` node TF emits, with begin /
+    end / shrink masks."""
+    x = convert_to_tensor(x)
+    keys = key if isinstance(key, tuple) else (key,)
+    if any(k is Ellipsis or k is None for k in keys):
+        raise NotImplementedError("tensor[...] / tensor[None]: use tf.expand_dims / explicit slices")
+    begin, end, strides = [], [], []
+    bm = em = sm = 0
+    shape = []
+    static = x._shape
+    for i, k in enumerate(keys):
+        dim = None if static is None else static[i]
+        if isinstance(k, slice):
+            st = 1 if k.step is None else int(k.step)
+            if st <= 0:
+                raise NotImplementedError("negative slice steps")
+            if k.start is None:
+                bm |= 1 << i
+            if k.stop is None:
+                em |= 1 << i
+            b, e = int(k.start or 0), int(k.stop or 0)
+            begin.append(b); end.append(e); strides.append(st)
+            if dim is None:
+                shape.append(None if (k.stop is None or b < 0 or e < 0) else max((e - b + st - 1) // st, 0))
+            else:
+                shape.append(len(range(*k.indices(dim))))
+        else:
+            k = int(k)
+            sm |= 1 << i
+            begin.append(k); end.append(k + 1 if k != -1 else 0); strides.append(1)
+            if k == -1:
+                em |= 1 << i
+    oshape = None if static is None else tuple(shape) + tuple(static[len(keys):])
+    g = _g()
+    name = g.unique_name("strided_slice")
+    mk = lambda v, n: g.add_node("Const", f"{name}/{n}", attrs={"dtype": attr_type(core.int32), "value": attr_tensor(np.asarray(v, np.int32), core.int32)},  # noqa: E731
+                                 out_dtypes=[core.int32], out_shapes=[(len(v),)], exact_name=True).outputs[0]
+    return g.add_node("StridedSlice", name, [x, mk(begin, "stack"), mk(end, "stack_1"), mk(strides, "stack_2")],
+                      {"T": attr_type(x.dtype), "Index": attr_type(core.int32), "begin_mask": attr_i(bm), "end_mask": attr_i(em),
+                       "ellipsis_mask": attr_i(0), "new_axis_mask": attr_i(0), "shrink_axis_mask": attr_i(sm)}, [x.dtype], [oshape], exact_name=True).outputs[0]
