@@ -58,6 +58,7 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
                   loss_callback: Optional[Callable[[float, int, str], None]] = None, partition_id: Optional[str] = None,
                   seed: Optional[int] = None, on_iteration: Optional[Callable[[int], None]] = None) -> str:
     from ..utils.metrics import MetricsLogger
+    from ..utils.trace import nvtx_pop, nvtx_push
 
     metrics = MetricsLogger()
     partition_id = partition_id or uuid.uuid4().hex
@@ -70,6 +71,7 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
     fast = hasattr(engine, "train_contiguous")
     sweep = mini_stochastic_iters < 1 and mini_batch_size >= 1
     for i in range(iters):
+        nvtx_push(f"sparkflow {partition_id} iteration {i}")
         if shuffle:
             order = rng.permutation(n)
             if fast and sweep:
@@ -117,6 +119,7 @@ def run_partition(engine: Engine, features: np.ndarray, labels: Optional[np.ndar
             metrics.log(event="iteration", partition=partition_id, iteration=i, rows=n)
         if on_iteration is not None:
             on_iteration(i)
+        nvtx_pop()
     engine.finish()
     return partition_id
 

@@ -6,6 +6,7 @@ end times, so launch gaps, PDL overlap and branch concurrency of a CUDA-graph st
 a profiler attached (ncu serialises kernels; this does not)."""
 from __future__ import annotations
 
+import os
 from typing import Dict, List
 
 import numpy as np
@@ -65,3 +66,20 @@ class DeviceTrace:
             g["end_us"] = (g.pop("end_abs") - base) / 1e3
             g.pop("_last_t0")
         return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# NVTX ranges (SPARKFLOW_NVTX=1): partition / iteration ranges of the worker loop for nsys / ncu range filters.  Off by
+# default: the hot loop pays nothing.
+# ---------------------------------------------------------------------------------------------------------------------
+_NVTX = os.environ.get("SPARKFLOW_NVTX") == "1"
+
+
+def nvtx_push(name: str) -> None:
+    if _NVTX and torch.cuda.is_available():
+        torch.cuda.nvtx.range_push(name)
+
+
+def nvtx_pop() -> None:
+    if _NVTX and torch.cuda.is_available():
+        torch.cuda.nvtx.range_pop()
